@@ -1,0 +1,139 @@
+"""Pin the C restatement (oracle/c/b9_oracle.c) to the Python oracle, whose Python halves are the
+reference's own stdlib calls. Every task: same status, same result bytes, same queue wire bytes."""
+import base64
+import json
+import random
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from beta9_b200 import synth
+from oracle import coracle
+from oracle.pyoracle import loop
+
+PY2C = {"COMPLETE": coracle.COMPLETE, "ERROR": coracle.ERROR, "REJECTED": coracle.REJECTED}
+
+
+def compare(batch, handler, allow_unsupported=False):
+    r = coracle.run_batch(batch.task_ids, batch.payload, batch.offsets, handler, keep_wire=True)
+    pr = loop.run_task_loop(batch.tasks(), [bytes(x) for x in batch.task_ids], handler, keep_wire=True)
+    n_unsup = 0
+    for i, p in enumerate(pr):
+        if r.status[i] == coracle.UNSUPPORTED:
+            assert allow_unsupported, (i, batch.task(i))
+            n_unsup += 1
+            continue
+        assert PY2C[p.status] == r.status[i], (i, batch.task(i), p.status, r.status[i])
+        assert p.result == r.result(i), (i, batch.task(i))
+        assert (p.wire or b"") == r.wire_msg(i), (i, batch.task(i))
+    return n_unsup
+
+
+def test_identity_strings_with_adversarial():
+    compare(synth.strings_batch(3000, 64, adversarial_frac=0.3), "identity")
+    compare(synth.strings_batch(500, 256, adversarial_frac=0.5, seed=7), "crc32")
+
+
+def test_crc_zipf():
+    compare(synth.crc_batch(3000), "crc32")
+    compare(synth.crc_batch(500, seed=3), "identity")
+
+
+def test_vadd():
+    compare(synth.vadd_batch(2000), "vadd_f32")
+    compare(synth.vadd_batch(300, floats_per_vec=5, seed=1), "vadd_f32")
+
+
+def test_json_sum():
+    compare(synth.json_batch(500), "json_sum")
+    compare(synth.json_batch(100, doc_bytes=300, seed=2), "identity")
+
+
+HANDCRAFTED = [
+    b'{"args": ["x"], "kwargs": {}}', b'{"args":["x"]}', b' { "kwargs" : { } , "args" : [ "x" ] } ',
+    b'{"args": [""], "kwargs": {}}', b'{"args": [], "kwargs": {}}', b'{"args": ["a", "b"], "kwargs": {}}',
+    b'{"args": ["a"], "kwargs": {"k": 1}}', b'{"args": ["a"], "kwargs": null}', b'{"args": null}', b"null", b"{}",
+    b"[]", b'"x"', b"", b"{", b'{"args": ["x"],}', b'{"args": ["\\ud83d"]}', b'{"args": ["\\ud83d\\ude00"]}',
+    b'{"args": ["\\ude00\\ud83d"]}', b'{"args": ["\xff"]}', b'{"args": ["\xc3\xa9\xe2\x80\xa8"]}',
+    b'{"args": ["\\u0000\\u001f\\u007f\\u0080\\u2028\\uffff"]}', b'{"args": ["<>&/\\/"]}',
+    b'{"args": ["\x01"]}', b'{"args": ["\\q"]}', b'{"ARGS": ["up"]}', b'{"args": ["1"], "args": ["2"]}',
+    b'{"kwargs": {"a": 1}, "kwargs": {}, "args": ["x"]}', b'{"args": [0]}', b'{"args": [-0]}', b'{"args": [1.0]}',
+    b'{"args": [1e3]}', b'{"args": [1.5]}', b'{"args": [9007199254740992]}', b'{"args": [9007199254740994]}',
+    b'{"args": [1e999]}', b'{"x": 1e999, "args": ["ok"]}', b'{"args": [true]}', b'{"args": [false]}',
+    b'{"args": [null]}', b'{"args": [[]]}', b'{"args": [{}]}', b'{"args": [[1, "a", null, true, {"b": [], "a": "<"}]]}',
+    b'{"args": [{"b": 1, "a": 2, "b": 3}]}', b'{"args": [{"values": [1, 2, 3]}]}', b'{"args": [{"values": []}]}',
+    b'{"args": [{"values": [true, 2]}]}', b'{"args": [{"values": [1, "a"]}]}', b'{"args": [{"values": "ab"}]}',
+    b'{"args": [{"values": ""}]}', b'{"args": [{"values": {}}]}', b'{"args": [{"values": {"a": 1}}]}',
+    b'{"args": [{"values": null}]}', b'{"args": [{"valuez": [1]}]}', b'{"args": [{"values": [1], "values": [5, 6]}]}',
+    b'{"args": [{"valu\\u0065s": [4]}]}', b'{"args": [{"values": [-5, 5]}]}', b'{"args": [{"values": [1.5]}]}',
+    b'{"args": [{"values": [[1]]}]}', b'{"args": [[1, 2]]}', b'{"args": ["AAAA"]}', b'{"args": ["AAA="]}',
+    b'{"args": ["AA=="]}', b'{"args": ["A==="]}', b'{"args": ["AAA"]}', b'{"args": ["AA\\nAA"]}', b'{"args": ["=AAA"]}',
+    b'{"args": ["AAAAAAAAAAA="]}', b'{"args": ["AAAAAAAAAAAAAAAAAAAAAA=="]}', b'{"args": ["AB==AAAA"]}',
+    b'{"args": ["A-AA"]}', b'{"args": ["\\u00e9AAA"]}', b'{"args": ["QUJDREVGR0g="]}', b'{"args": ["AAAAAAAAAAB="]}',
+]
+
+
+@pytest.mark.parametrize("handler", ["identity", "crc32", "vadd_f32", "json_sum"])
+def test_handcrafted(handler):
+    compare(synth.from_payloads(HANDCRAFTED), handler, allow_unsupported=True)
+
+
+def test_handcrafted_unsupported_is_only_floats():
+    b = synth.from_payloads(HANDCRAFTED)
+    r = coracle.run_batch(b.task_ids, b.payload, b.offsets, "identity")
+    unsup = {HANDCRAFTED[i] for i in range(b.n) if r.status[i] == coracle.UNSUPPORTED}
+    assert unsup == {b'{"args": [1.5]}', b'{"args": [9007199254740994]}', b'{"args": [{"values": [1.5]}]}'}
+
+
+# ---- fuzz: arbitrary JSON documents as args / kwargs, serialised the way the SDK does
+json_leaf = st.one_of(st.none(), st.booleans(), st.integers(-2**53, 2**53),
+                      st.text(max_size=12), st.text(alphabet='"\\<>&/\n\t\x00\x7fé 😀\U0001f600ab', max_size=8))
+json_val = st.recursive(json_leaf, lambda c: st.one_of(st.lists(c, max_size=4),
+                                                      st.dictionaries(st.text(max_size=5), c, max_size=4)), max_leaves=12)
+
+
+@settings(max_examples=300, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.lists(st.tuples(st.lists(json_val, max_size=2), st.dictionaries(st.text(max_size=4), json_val, max_size=1)),
+                min_size=1, max_size=6), st.sampled_from(["identity", "crc32", "vadd_f32", "json_sum"]))
+def test_fuzz_sdk_payloads(tasks, handler):
+    payloads = [loop.sdk_put_payload(*a, **{k: v for k, v in kw.items()}) for a, kw in tasks]
+    compare(synth.from_payloads(payloads), handler)
+
+
+@settings(max_examples=300, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.lists(st.binary(max_size=40), min_size=1, max_size=6), st.sampled_from(["identity", "crc32"]))
+def test_fuzz_raw_bytes_in_string(blobs, handler):
+    # arbitrary bytes (invalid UTF-8, stray quotes, control bytes) between the canonical frame
+    payloads = [synth.PREFIX + b + synth.SUFFIX for b in blobs]
+    compare(synth.from_payloads(payloads), handler, allow_unsupported=True)
+
+
+def test_fuzz_mutations():
+    rnd = random.Random(0xB9)
+    base = [loop.sdk_put_payload("hello \"w\" \\ é"), loop.sdk_put_payload({"values": [1, 2, 3], "id": 7}),
+            loop.sdk_put_payload(base64.b64encode(bytes(range(64))).decode())]
+    payloads = []
+    for _ in range(3000):
+        p = bytearray(rnd.choice(base))
+        for _ in range(rnd.randint(1, 3)):
+            k = rnd.randrange(len(p))
+            op = rnd.random()
+            if op < 0.4:
+                p[k] = rnd.randrange(256)
+            elif op < 0.7:
+                del p[k]
+            else:
+                p.insert(k, rnd.choice(b'"\\{}[],: \x00\xffu0'))
+        payloads.append(bytes(p))
+    b = synth.from_payloads(payloads)
+    for h in ("identity", "crc32", "vadd_f32", "json_sum"):
+        compare(b, h, allow_unsupported=True)
+
+
+def test_threads_give_same_answer():
+    b = synth.strings_batch(5000, 64, adversarial_frac=0.2)
+    r1 = coracle.run_batch(b.task_ids, b.payload, b.offsets, "identity", nthreads=1)
+    r4 = coracle.run_batch(b.task_ids, b.payload, b.offsets, "identity", nthreads=4)
+    assert np.array_equal(r1.status, r4.status) and np.array_equal(r1.offsets, r4.offsets)
+    assert np.array_equal(r1.payload, r4.payload)

@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — tasks/sec of the task fan-out hot path on N B200s (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: every pending task of the batch is popped,
+deserialised, run through the handler and serialised (one persistent drain kernel per GPU).
+Workload = BASELINE.json configs[1]: 1M x 256-character identity tasks per GPU (weak scaling:
+every rank owns its own shard of the pending ring; no data-path collective).
+
+  value      whole-job tasks/s with the batch already resident in HBM (kernel-resident number)
+  e2e        the same through the C ABI with HOST buffers: b9_batch_push (H2D) + b9_drain (D2H)
+  roofline   drain kernel: SURVEY.md §8(d) algorithmic bytes (578 B/task) / CUDA-event kernel time
+  cpu_baseline  the oracle's C port of the reference loop on this box's host cores (rank 0, N=1)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_TASK = {"identity": 578.0}   # 256 in + 258 out + 2 x 32 B of index/id/header
+L2_BYTES = 126e6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tasks", type=int, default=1_000_000, help="tasks per GPU per step")
+    ap.add_argument("--chars", type=int, default=256)
+    ap.add_argument("--handler", default="identity")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def workload(args, rank):
+    from beta9_b200 import synth
+    if args.handler == "identity":
+        return synth.strings_batch(args.tasks, args.chars, seed=synth.SEED + 1000 * rank)
+    raise SystemExit(f"bench: handler {args.handler} has no bench workload yet")
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU task loop on this box's host cores. The Go gateway and
+    the Python runner cannot be built/imported here (no Go toolchain, SDK deps missing), so this is
+    the oracle's C port of that loop (oracle/c/b9_oracle.c), multi-threaded over all cores; Redis,
+    Postgres, gRPC and the object store are left out, which flatters the reference."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import coracle
+    batch = workload(args, 0)
+    cores = os.cpu_count() or 1
+    times = []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        coracle.run_batch(batch.task_ids, batch.payload, batch.offsets, args.handler, nthreads=cores,
+                          out_cap=int(batch.payload.size) + 64)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    v = batch.n * len(times) / total
+    line = {
+        "impl": "reference", "metric": "tasks_per_sec", "value": v, "unit": "tasks/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"configs[1]: {batch.n} x {args.chars}-char identity tasks, reference CPU loop (C port), "
+                               f"one bounded sample of {batch.n} tasks per step", "handler": args.handler},
+        "cpu_baseline": {"value": v, "unit": "tasks/s", "cores": cores, "kind": "port",
+                         "sample": f"{batch.n} tasks x {len(times)} steps, {cores} threads"},
+        "e2e": {"value": v, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    rank, local_rank, world = dist_env()
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the b200 arm has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from beta9_b200 import _lib as L
+    from beta9_b200.device_queue import DeviceQueue
+    batch = workload(args, rank)
+    n = batch.n
+    in_bytes = int(batch.payload.size)
+    dq = DeviceQueue(device=local_rank, ring_bytes=max(1 << 30, 4 * in_bytes), ring_tasks=max(1 << 21, 4 * n),
+                     max_drain_tasks=max(1 << 21, n), max_result_bytes=max(1 << 30, 2 * in_bytes))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ device-resident steps
+    dq.push_batch(batch.task_ids, batch.payload, batch.offsets)
+    kernel_ms = []
+    for _ in range(args.warmup):
+        dq.drain_launch(args.handler, n, peek=True)
+    sampler = ClockSampler(local_rank)
+    launches0 = dq.stats().kernel_launches
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        got = dq.drain_launch(args.handler, n, peek=True)
+        kernel_ms.append(dq.stats().last_drain_kernel_ms)
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop()
+    launches = dq.stats().kernel_launches - launches0
+    assert got == n, (got, n)
+    out_bytes = int(dq.stats().last_drain_out_bytes)
+    elapsed = reduce_max(t1 - t0)
+    value = world * n * args.steps / elapsed
+    k_ms = reduce_max(statistics.mean(kernel_ms))
+    # drop the resident batch
+    dq.drain_launch(args.handler, n, peek=False)
+    res = dq.fetch()
+    assert res.n == n and dq.depth() == 0
+
+    # ------------------------------------------------------------------ end to end through the C ABI, host buffers
+    pin_ids = dq.pinned(n * 16); pin_pl = dq.pinned(in_bytes); pin_off = dq.pinned((n + 1) * 8)
+    pin_ids.array[:] = batch.task_ids.reshape(-1); pin_pl.array[:] = batch.payload
+    pin_off.view(np.uint64, n + 1)[:] = batch.offsets
+    cap_bytes = out_bytes + 4096
+    o_ids = dq.pinned(n * 16); o_st = dq.pinned(n); o_has = dq.pinned(n); o_off = dq.pinned((n + 1) * 8); o_pl = dq.pinned(cap_bytes)
+    resbuf = L.Results(o_ids.ptr, o_st.ptr, o_has.ptr, o_off.ptr, o_pl.ptr, n, cap_bytes, 0, 0, 0, 0)
+    lib = L.load()
+    hid = {"identity": 0, "crc32": 1, "vadd_f32": 2, "json_sum": 3}[args.handler]
+
+    def e2e_step():
+        rc = lib.b9_batch_push(dq._ctx, pin_ids.ptr, pin_pl.ptr, pin_off.ptr, n, None)
+        if rc != 0:
+            raise SystemExit("push failed: " + L.last_error())
+        r = lib.b9_drain(dq._ctx, hid, n, C.byref(resbuf))
+        if r != n:
+            raise SystemExit(f"drain returned {r}: " + L.last_error())
+
+    for _ in range(3):
+        e2e_step()
+    s0 = dq.stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    t1 = time.perf_counter()
+    s1 = dq.stats()
+    e2e_elapsed = reduce_max(t1 - t0)
+    e2e_value = world * n * args.e2e_steps / e2e_elapsed
+    h2d = (s1.bytes_h2d - s0.bytes_h2d) // args.e2e_steps
+    d2h = (s1.bytes_d2h - s0.bytes_d2h) // args.e2e_steps
+    # the records that came back are the real ones
+    assert bytes(o_pl.array[:8]) == res.payload[:8].tobytes()
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import coracle
+        cores = os.cpu_count() or 1
+        best = None
+        for _ in range(3):
+            c0 = time.perf_counter()
+            o = coracle.run_batch(batch.task_ids, batch.payload, batch.offsets, args.handler, nthreads=cores, out_cap=in_bytes + 64)
+            dt = time.perf_counter() - c0
+            best = dt if best is None else min(best, dt)
+        # while we are here: the device answers are the oracle's answers
+        assert np.array_equal(o.payload, res.payload) and np.array_equal(o.status, res.status)
+        cpu = {"value": n / best, "unit": "tasks/s", "cores": cores, "kind": "port",
+               "sample": f"all {n} tasks of the step, best of 3 passes, {cores} threads (oracle/c/b9_oracle.c)"}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        algo = ALGO_BYTES_PER_TASK.get(args.handler, 0.0) * n
+        achieved = algo / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": "tasks_per_sec", "value": value, "unit": "tasks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"configs[1]: {n} x {args.chars}-char identity tasks per GPU (1% adversarial escapes), "
+                                   f"resident in HBM", "handler": args.handler, "tasks_per_gpu": n,
+                       "parallelism": f"shard{world}" if world > 1 else "single",
+                       "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; no flush needed"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "b9::drain_kernel<identity>", "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_task": ALGO_BYTES_PER_TASK.get(args.handler), "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "tasks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / args.e2e_steps,
+                    "api": "b9_batch_push + b9_drain with pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    for p in (pin_ids, pin_pl, pin_off, o_ids, o_st, o_has, o_off, o_pl):
+        p.free()
+    dq.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,447 @@
+// libb9gpu.so — host side of the C ABI declared in include/b9gpu.h.
+//
+// One b9_ctx = one GPU: the pending-task ring lives in HBM (payload bytes + SoA slot arrays),
+// pushes DMA the caller's batch straight into it, drains run one persistent kernel over a FIFO
+// window of the ring and DMA the dense result records back. The semantic model of the ring is
+// the reference's FIFO Redis list (pkg/abstractions/taskqueue/client.go:29-96: RPUSH at the tail,
+// LPOP at the head) with `RingBuffer`-style fixed capacity (pkg/abstractions/common/ring_buffer.go).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b9gpu.h"
+#include "drain_kernel.cuh"
+
+using namespace b9;
+
+namespace {
+
+thread_local std::string g_last_error;   // per calling thread, as the header promises
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(B9_EIO, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+uint64_t pow2_ceil(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
+
+struct Segment {             // one push = one contiguous byte range of the payload ring
+    uint64_t first_task;     // logical index of its first task
+    uint32_t n;
+    uint64_t phys_start, bytes;
+    std::vector<uint64_t> rel;   // the batch's offsets (n+1), kept for exact byte accounting
+};
+
+constexpr uint64_t RING_SLACK = 256;   // readable bytes past the ring end (vector loads may over-read)
+constexpr uint64_t SEG_ALIGN  = 256;
+
+}  // namespace
+
+struct b9_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int resident_ctas = 0;             // drain kernel CTAs that fit per SM x SMs
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    std::mutex mu;
+
+    // ---- pending ring (device)
+    uint64_t ring_bytes = 0; uint32_t ring_tasks = 0, slot_mask = 0, max_task_bytes = 0;
+    uint8_t*  d_payload = nullptr;
+    uint64_t* d_off = nullptr; uint64_t* d_hdr = nullptr; uint4* d_ids = nullptr;
+    int64_t*  d_ts = nullptr;  int64_t* d_exp = nullptr;
+    // push staging (device): raw offsets + optional metadata of the batch being ingested
+    uint64_t* d_in_off = nullptr; int64_t* d_in_ts = nullptr; int64_t* d_in_exp = nullptr;
+    uint8_t*  d_in_retries = nullptr; uint8_t* d_in_flags = nullptr;
+    // ring bookkeeping (host)
+    uint64_t head_task = 0, tail_task = 0;     // logical, monotonically increasing
+    uint64_t write_pos = 0;                    // physical byte position of the next segment
+    uint64_t pending_bytes = 0;
+    std::deque<Segment> segs;
+
+    // ---- drain staging (device)
+    uint32_t max_drain_tasks = 0; uint64_t max_result_bytes = 0;
+    uint8_t* d_out_payload = nullptr; uint64_t* d_out_off = nullptr; uint4* d_out_ids = nullptr;
+    uint8_t* d_out_status = nullptr; uint8_t* d_out_has = nullptr;
+    DrainCtl* d_ctl = nullptr; uint64_t* d_tile_state = nullptr;
+    DrainCtl* h_ctl = nullptr;                 // pinned
+    unsigned long long* d_count = nullptr; unsigned long long* h_count = nullptr;
+    // results waiting on the device for b9_drain_fetch
+    bool have_results = false, res_peek = false;
+    uint32_t res_n = 0, res_popped = 0; uint64_t res_bytes = 0, res_in_bytes = 0;
+
+    b9_stats stats{};
+};
+
+namespace {
+
+void free_segments(b9_ctx* c) {
+    while (!c->segs.empty() && c->segs.front().first_task + c->segs.front().n <= c->head_task) c->segs.pop_front();
+    if (c->segs.empty()) c->write_pos = 0;
+}
+
+// where can a segment of `bytes` go? returns false when the ring cannot take it now
+bool place_segment(b9_ctx* c, uint64_t bytes, uint64_t* start) {
+    uint64_t need = (bytes + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1);
+    if (need > c->ring_bytes) return false;
+    if (c->segs.empty()) { *start = 0; return true; }
+    uint64_t oldest = c->segs.front().phys_start;
+    uint64_t wp = c->write_pos;
+    if (wp >= oldest) {                      // live data is [oldest, wp)
+        if (wp + need <= c->ring_bytes) { *start = wp; return true; }
+        if (need <= oldest) { *start = 0; return true; }     // wrap, leaving the tail gap unused
+        return false;
+    }
+    if (wp + need <= oldest) { *start = wp; return true; }   // wrapped already: free is [wp, oldest)
+    return false;
+}
+
+template <int H> cudaError_t launch_drain(const DrainArgs& a, int grid, cudaStream_t s) {
+    drain_kernel<H><<<grid, DRAIN_THREADS, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t b9_abi_version(void) { return B9_ABI_VERSION; }
+
+int b9_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* b9_last_error(const b9_ctx*) { return g_last_error.c_str(); }
+
+static const char* const HANDLER_NAMES[B9_H_COUNT_] = {"identity", "crc32", "vadd_f32", "json_sum"};
+const char* b9_handler_name(int h) { return (h >= 0 && h < B9_H_COUNT_) ? HANDLER_NAMES[h] : nullptr; }
+int b9_handler_id(const char* name) {
+    if (!name) return B9_EINVAL;
+    if (!strcmp(name, "echo")) return B9_H_IDENTITY;
+    for (int h = 0; h < B9_H_COUNT_; ++h) if (!strcmp(name, HANDLER_NAMES[h])) return h;
+    return B9_ENOSYS;
+}
+
+int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
+    if (!out) return fail(B9_EINVAL, "b9_ctx_create: out is NULL");
+    *out = nullptr;
+    b9_opts o{};
+    if (opts) memcpy(&o, opts, std::min<size_t>(sizeof o, opts->struct_size ? opts->struct_size : sizeof o));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B9_ENODEV, "b9_ctx_create: no CUDA device is visible; libb9gpu has no CPU path");
+    }
+    if (o.device < 0 || o.device >= ndev) return fail(B9_EINVAL, "b9_ctx_create: device %d of %d", o.device, ndev);
+    b9_ctx* c = new (std::nothrow) b9_ctx();
+    if (!c) return fail(B9_ENOMEM, "b9_ctx_create: host allocation failed");
+    c->device = o.device;
+    c->ring_bytes = pow2_ceil(o.ring_bytes ? o.ring_bytes : (1ull << 30));
+    c->ring_tasks = (uint32_t)pow2_ceil(o.ring_tasks ? o.ring_tasks : (4u << 20));
+    c->slot_mask = c->ring_tasks - 1;
+    c->max_drain_tasks = o.max_drain_tasks ? o.max_drain_tasks : (2u << 20);
+    if (c->max_drain_tasks >= (1u << 24)) c->max_drain_tasks = (1u << 24) - 1;
+    if (c->max_drain_tasks > c->ring_tasks) c->max_drain_tasks = c->ring_tasks;
+    c->max_result_bytes = o.max_result_bytes ? o.max_result_bytes : (1ull << 30);
+    if (c->max_result_bytes >= (1ull << 38)) c->max_result_bytes = (1ull << 38) - 1;
+    c->max_task_bytes = o.max_task_bytes ? o.max_task_bytes : (1u << 20);
+
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    int rc_ = fail(e_ == cudaErrorMemoryAllocation ? B9_ENOMEM : B9_EIO, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    b9_ctx_destroy(c); return rc_; } } while (0)
+    CUC(cudaSetDevice(c->device));
+    cudaDeviceProp prop{};
+    CUC(cudaGetDeviceProperties(&prop, c->device));
+    c->sm_count = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b)); CUC(cudaEventCreate(&c->ev_c)); CUC(cudaEventCreate(&c->ev_d));
+    const uint32_t rt = c->ring_tasks, md = c->max_drain_tasks;
+    CUC(cudaMalloc(&c->d_payload, c->ring_bytes + RING_SLACK));
+    CUC(cudaMemset(c->d_payload + c->ring_bytes, 0, RING_SLACK));
+    CUC(cudaMalloc(&c->d_off, rt * sizeof(uint64_t)));
+    CUC(cudaMalloc(&c->d_hdr, rt * sizeof(uint64_t)));
+    CUC(cudaMalloc(&c->d_ids, rt * sizeof(uint4)));
+    CUC(cudaMalloc(&c->d_ts, rt * sizeof(int64_t)));
+    CUC(cudaMalloc(&c->d_exp, rt * sizeof(int64_t)));
+    CUC(cudaMalloc(&c->d_in_off, ((size_t)rt + 1) * sizeof(uint64_t)));
+    CUC(cudaMalloc(&c->d_in_ts, rt * sizeof(int64_t)));
+    CUC(cudaMalloc(&c->d_in_exp, rt * sizeof(int64_t)));
+    CUC(cudaMalloc(&c->d_in_retries, rt));
+    CUC(cudaMalloc(&c->d_in_flags, rt));
+    CUC(cudaMalloc(&c->d_out_payload, c->max_result_bytes + RING_SLACK));
+    CUC(cudaMalloc(&c->d_out_off, ((size_t)md + 1) * sizeof(uint64_t)));
+    CUC(cudaMalloc(&c->d_out_ids, (size_t)md * sizeof(uint4)));
+    CUC(cudaMalloc(&c->d_out_status, md));
+    CUC(cudaMalloc(&c->d_out_has, md));
+    CUC(cudaMalloc(&c->d_ctl, sizeof(DrainCtl)));
+    CUC(cudaMalloc(&c->d_tile_state, ((size_t)md / TILE_TASKS + 2) * sizeof(uint64_t)));
+    CUC(cudaMalloc(&c->d_count, sizeof(unsigned long long)));
+    CUC(cudaHostAlloc(&c->h_ctl, sizeof(DrainCtl), cudaHostAllocDefault));
+    CUC(cudaHostAlloc(&c->h_count, sizeof(unsigned long long), cudaHostAllocDefault));
+    int per_sm = 0;
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drain_kernel<0>, DRAIN_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    c->resident_ctas = per_sm * c->sm_count;
+    c->stats.sm_count = (uint32_t)c->sm_count;
+#undef CUC
+    *out = c;
+    return B9_OK;
+}
+
+void b9_ctx_destroy(b9_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_payload); cudaFree(c->d_off); cudaFree(c->d_hdr); cudaFree(c->d_ids); cudaFree(c->d_ts); cudaFree(c->d_exp);
+    cudaFree(c->d_in_off); cudaFree(c->d_in_ts); cudaFree(c->d_in_exp); cudaFree(c->d_in_retries); cudaFree(c->d_in_flags);
+    cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has);
+    cudaFree(c->d_ctl); cudaFree(c->d_tile_state); cudaFree(c->d_count);
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    if (c->h_count) cudaFreeHost(c->h_count);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->ev_c) cudaEventDestroy(c->ev_c);
+    if (c->ev_d) cudaEventDestroy(c->ev_d);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* b9_host_alloc(b9_ctx* c, uint64_t bytes) {
+    if (!c) { fail(B9_EINVAL, "b9_host_alloc: ctx is NULL"); return nullptr; }
+    void* p = nullptr;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { fail(B9_ENOMEM, "cudaHostAlloc(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+void b9_host_free(b9_ctx* c, void* p) {
+    if (!p) return;
+    if (c) cudaSetDevice(c->device);
+    cudaFreeHost(p);
+}
+
+int b9_batch_push(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, const uint64_t* offsets, uint32_t n, const b9_push_meta* meta) {
+    if (!c) return fail(B9_EINVAL, "b9_batch_push: ctx is NULL");
+    if (n == 0) return B9_OK;
+    if (!task_ids || !payload || !offsets) return fail(B9_EINVAL, "b9_batch_push: NULL buffer");
+    // validate the index before anything is copied
+    for (uint32_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i]) return fail(B9_EINVAL, "b9_batch_push: offsets not monotonic at task %u", i);
+        if (offsets[i + 1] - offsets[i] > c->max_task_bytes)
+            return fail(B9_E2BIG, "b9_batch_push: task %u is %llu bytes, max_task_bytes is %u", i,
+                        (unsigned long long)(offsets[i + 1] - offsets[i]), c->max_task_bytes);
+    }
+    const uint64_t bytes = offsets[n] - offsets[0];
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    free_segments(c);
+    if ((uint64_t)n > (uint64_t)c->ring_tasks - (c->tail_task - c->head_task))
+        return fail(B9_ENOSPC, "b9_batch_push: %u tasks do not fit (%llu of %u slots pending)", n,
+                    (unsigned long long)(c->tail_task - c->head_task), c->ring_tasks);
+    uint64_t start = 0;
+    if (!place_segment(c, bytes, &start))
+        return fail(B9_ENOSPC, "b9_batch_push: %llu payload bytes do not fit the ring (%llu pending of %llu)",
+                    (unsigned long long)bytes, (unsigned long long)c->pending_bytes, (unsigned long long)c->ring_bytes);
+    cudaStream_t s = c->stream;
+    CU(cudaEventRecord(c->ev_a, s));
+    if (bytes) CU(cudaMemcpyAsync(c->d_payload + start, payload + offsets[0], bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_in_off, offsets, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    // ids go straight into their ring slots (two pieces when the slot ring wraps)
+    const uint32_t slot0 = (uint32_t)(c->tail_task & c->slot_mask);
+    const uint32_t first = std::min<uint32_t>(n, c->ring_tasks - slot0);
+    CU(cudaMemcpyAsync(c->d_ids + slot0, task_ids, (size_t)first * 16, cudaMemcpyHostToDevice, s));
+    if (first < n) CU(cudaMemcpyAsync(c->d_ids, task_ids + (size_t)first * 16, (size_t)(n - first) * 16, cudaMemcpyHostToDevice, s));
+    const int64_t* ts = nullptr; const int64_t* ex = nullptr; const uint8_t* rt = nullptr; const uint8_t* fl = nullptr;
+    uint64_t meta_bytes = 0;
+    if (meta) {
+        if (meta->timestamp_unix)  { CU(cudaMemcpyAsync(c->d_in_ts, meta->timestamp_unix, (size_t)n * 8, cudaMemcpyHostToDevice, s)); ts = c->d_in_ts; meta_bytes += (uint64_t)n * 8; }
+        if (meta->expires_unix_ns) { CU(cudaMemcpyAsync(c->d_in_exp, meta->expires_unix_ns, (size_t)n * 8, cudaMemcpyHostToDevice, s)); ex = c->d_in_exp; meta_bytes += (uint64_t)n * 8; }
+        if (meta->retries)         { CU(cudaMemcpyAsync(c->d_in_retries, meta->retries, n, cudaMemcpyHostToDevice, s)); rt = c->d_in_retries; meta_bytes += n; }
+        if (meta->flags)           { CU(cudaMemcpyAsync(c->d_in_flags, meta->flags, n, cudaMemcpyHostToDevice, s)); fl = c->d_in_flags; meta_bytes += n; }
+    }
+    CU(cudaEventRecord(c->ev_b, s));
+    ingest_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->d_in_off, n, start, c->tail_task, c->slot_mask, ts, ex, rt, fl,
+                                                  c->d_off, c->d_hdr, c->d_ts, c->d_exp);
+    CU(cudaGetLastError());
+    c->stats.kernel_launches++;
+    CU(cudaStreamSynchronize(s));            // the caller may reuse its buffers as soon as we return
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->stats.last_push_h2d_ms = ms;
+    c->segs.push_back(Segment{c->tail_task, n, start, bytes, std::vector<uint64_t>(offsets, offsets + n + 1)});
+    c->write_pos = start + ((bytes + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
+    c->tail_task += n;
+    c->pending_bytes += bytes;
+    c->stats.tasks_pushed += n;
+    c->stats.bytes_h2d += bytes + ((uint64_t)n + 1) * 8 + (uint64_t)n * 16 + meta_bytes;
+    return B9_OK;
+}
+
+uint64_t b9_depth(b9_ctx* c) {
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return c->tail_task - c->head_task;
+}
+
+uint64_t b9_depth_bytes(b9_ctx* c) {
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return c->pending_bytes;
+}
+
+int64_t b9_expire(b9_ctx* c, int64_t now_unix_ns) {
+    if (!c) return fail(B9_EINVAL, "b9_expire: ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    const uint64_t depth = c->tail_task - c->head_task;
+    if (!depth) return 0;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned long long), c->stream));
+    expire_kernel<<<(uint32_t)((depth + 255) / 256), 256, 0, c->stream>>>(c->d_hdr, c->d_exp, c->slot_mask, c->head_task, (uint32_t)depth, now_unix_ns, c->d_count);
+    CU(cudaGetLastError());
+    c->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(c->h_count, c->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return (int64_t)*c->h_count;
+}
+
+int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
+    if (!c) return fail(B9_EINVAL, "b9_drain_launch: ctx is NULL");
+    if (handler < 0 || handler >= B9_H_COUNT_) return fail(B9_ENOSYS, "b9_drain_launch: unknown handler %d", handler);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    // results of an earlier launch that were never fetched are dropped; their tasks are still
+    // pending (a pop is committed by a successful fetch, never by a launch)
+    c->have_results = false;
+    const uint64_t depth = c->tail_task - c->head_task;
+    const uint32_t n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
+    c->res_n = 0; c->res_popped = 0; c->res_bytes = 0; c->res_in_bytes = 0; c->res_peek = peek != 0;
+    if (n == 0) { c->have_results = true; return 0; }
+    // payload bytes of the window
+    uint64_t in_bytes = 0;
+    {
+        uint64_t lo = c->head_task, hi = c->head_task + n;
+        for (const Segment& sg : c->segs) {
+            uint64_t a = std::max<uint64_t>(lo, sg.first_task), b = std::min<uint64_t>(hi, sg.first_task + sg.n);
+            if (a < b) in_bytes += sg.rel[b - sg.first_task] - sg.rel[a - sg.first_task];
+        }
+    }
+    DrainArgs a{};
+    a.payload = c->d_payload; a.off = c->d_off; a.hdr = c->d_hdr; a.ids = c->d_ids; a.slot_mask = c->slot_mask;
+    a.first_task = c->head_task; a.n_tasks = n; a.n_tiles = (n + TILE_TASKS - 1) / TILE_TASKS;
+    a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_ids = c->d_out_ids;
+    a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.handler = handler;
+    cudaStream_t s = c->stream;
+    CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
+    CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));
+    const int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
+    CU(cudaEventRecord(c->ev_a, s));
+    cudaError_t le;
+    switch (handler) {
+    case B9_H_IDENTITY: le = launch_drain<0>(a, grid, s); break;
+    case B9_H_CRC32:    le = launch_drain<1>(a, grid, s); break;
+    case B9_H_VADD_F32: le = launch_drain<2>(a, grid, s); break;
+    default:            le = launch_drain<3>(a, grid, s); break;
+    }
+    if (le != cudaSuccess) return fail(B9_EIO, "drain kernel launch failed: %s", cudaGetErrorString(le));
+    CU(cudaEventRecord(c->ev_b, s));
+    c->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(DrainCtl), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+    c->stats.last_drain_kernel_ms = ms;
+    c->stats.last_drain_tiles = a.n_tiles;
+    c->stats.drains++;
+    if (c->h_ctl->overflow)
+        return fail(B9_ENOSPC, "b9_drain_launch: results exceed max_result_bytes (%llu); drain fewer tasks or enlarge the staging",
+                    (unsigned long long)c->max_result_bytes);
+    c->res_bytes = c->h_ctl->total >> 24;
+    c->res_n = (uint32_t)(c->h_ctl->total & 0xFFFFFFu);
+    c->res_popped = n;
+    c->res_in_bytes = in_bytes;
+    c->have_results = true;
+    c->stats.last_drain_in_bytes = in_bytes;
+    c->stats.last_drain_out_bytes = c->res_bytes;
+    return (int64_t)c->res_n;
+}
+
+int64_t b9_drain_fetch(b9_ctx* c, b9_results* out) {
+    if (!c || !out) return fail(B9_EINVAL, "b9_drain_fetch: NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->have_results) return fail(B9_EINVAL, "b9_drain_fetch: no drain results are waiting");
+    out->n_results = c->res_n; out->n_popped = c->res_popped; out->n_bytes = c->res_bytes; out->need_bytes = c->res_bytes;
+    if (c->res_n > out->cap_tasks || c->res_bytes > out->cap_bytes)
+        return fail(B9_ENOSPC, "b9_drain_fetch: need %u records / %llu bytes, caller gave %u / %llu", c->res_n,
+                    (unsigned long long)c->res_bytes, out->cap_tasks, (unsigned long long)out->cap_bytes);
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t n = c->res_n;
+    CU(cudaEventRecord(c->ev_c, s));
+    if (n) {
+        if (!out->task_ids || !out->status || !out->has_result || !out->offsets) return fail(B9_EINVAL, "b9_drain_fetch: NULL result array");
+        CU(cudaMemcpyAsync(out->task_ids, c->d_out_ids, n * 16, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(out->status, c->d_out_status, n, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(out->has_result, c->d_out_has, n, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(out->offsets, c->d_out_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        if (c->res_bytes) {
+            if (!out->payload) return fail(B9_EINVAL, "b9_drain_fetch: NULL payload buffer");
+            CU(cudaMemcpyAsync(out->payload, c->d_out_payload, c->res_bytes, cudaMemcpyDeviceToHost, s));
+        }
+    } else if (out->offsets) out->offsets[0] = 0;
+    CU(cudaEventRecord(c->ev_d, s));
+    CU(cudaStreamSynchronize(s));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_c, c->ev_d); c->stats.last_drain_d2h_ms = ms;
+    c->stats.bytes_d2h += c->res_bytes + n * (16 + 1 + 1 + 8) + 8;
+    if (!c->res_peek) {
+        c->head_task += c->res_popped; c->pending_bytes -= c->res_in_bytes; c->stats.tasks_drained += c->res_popped;
+        free_segments(c);
+    }
+    c->have_results = false;
+    return (int64_t)n;
+}
+
+int64_t b9_drain(b9_ctx* c, int handler, uint32_t max_tasks, b9_results* out) {
+    if (!c || !out) return fail(B9_EINVAL, "b9_drain: NULL argument");
+    if (out->cap_tasks < max_tasks) max_tasks = out->cap_tasks;
+    int64_t r = b9_drain_launch(c, handler, max_tasks, /*peek=*/0);
+    if (r < 0) return r;
+    return b9_drain_fetch(c, out);   // on B9_ENOSPC nothing is consumed and the records stay fetchable
+}
+
+int b9_stats_get(b9_ctx* c, b9_stats* out) {
+    if (!c || !out) return fail(B9_EINVAL, "b9_stats_get: NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    *out = c->stats;
+    return B9_OK;
+}
+
+int b9_sync(b9_ctx* c) {
+    if (!c) return fail(B9_EINVAL, "b9_sync: ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return B9_OK;
+}
+
+int b9_task_queue_scale(int64_t queue_length, int64_t tasks_per_container, int64_t max_containers, int64_t max_replicas, int* valid) {
+    if (valid) *valid = 1;
+    if (queue_length == 0) return 0;
+    if (queue_length == -1 || tasks_per_container <= 0) { if (valid) *valid = 0; return 0; }
+    int64_t desired = queue_length / tasks_per_container + (queue_length % tasks_per_container > 0 ? 1 : 0);
+    return (int)std::min<int64_t>(std::min<int64_t>(max_containers, max_replicas), desired);
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+/*
+ * b9gpu — C ABI of the B200-native task fan-out path (libb9gpu.so).
+ *
+ * This is the drop-in boundary for ONE hot path of beam-cloud/beta9: the per-request task
+ * dispatch loop (push a task through the queue, pop it in a runner, deserialise, call the
+ * handler, serialise the result). The reference has no FFI for this path; the seams it does have
+ * are in-process Go interfaces, and each entry point below names the reference interface it
+ * replaces (paths relative to the reference repo). INTEGRATION.md shows the cgo and ctypes stubs
+ * that bind them.
+ *
+ * Conventions
+ *   - plain C, no exceptions across the boundary; `int` returns: 0 = ok, negative = -errno style
+ *     code below; `b9_last_error()` gives text for the calling thread's last failure on a ctx.
+ *   - a `b9_ctx` owns all device and pinned memory of one GPU; callers own the buffers they pass.
+ *     Every call copies what it needs before returning (cgo pointer rules), so Go may free or
+ *     reuse its slices immediately. Buffers obtained from `b9_host_alloc` are page-locked: pass
+ *     those for full PCIe bandwidth (pageable memory works, more slowly).
+ *   - thread safety: all functions may be called concurrently from many OS threads (goroutine
+ *     backed or not); calls on one ctx are serialised internally.
+ *   - a batch is packed SoA: `task_ids` n x 16 raw UUID bytes, `payload` one blob, `offsets`
+ *     n+1 byte offsets into it. A task's payload is the exact `TaskQueuePutRequest.payload`
+ *     bytes (pkg/abstractions/taskqueue/taskqueue.proto:20-23), i.e. what the SDK's
+ *     `json.dumps({"args": args, "kwargs": kwargs})` produced
+ *     (sdk/src/beta9/abstractions/taskqueue.py:284-287).
+ */
+#ifndef B9GPU_H
+#define B9GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B9_ABI_VERSION 1u
+
+/* ---- error codes ------------------------------------------------------------------------ */
+#define B9_OK          0
+#define B9_EINVAL    (-22)   /* bad argument                                                    */
+#define B9_ENOMEM    (-12)   /* host or device allocation failed                                */
+#define B9_ENOSPC    (-28)   /* pending ring full / caller's result buffers too small           */
+#define B9_E2BIG      (-7)   /* one task or one batch exceeds a configured maximum              */
+#define B9_EIO        (-5)   /* CUDA / NCCL runtime error (text in b9_last_error)               */
+#define B9_ENODEV    (-19)   /* no usable CUDA device                                           */
+#define B9_ENOSYS    (-38)   /* handler id unknown                                              */
+
+/* ---- GPU "kernel handlers": the user-function slot (sdk/src/beta9/runner/common.py:297-305)
+ *      for which a device implementation exists. Semantics are those of the Python functions in
+ *      oracle/pyoracle/handlers.py invoked as `handler(*args, **kwargs)`. ------------------- */
+enum b9_handler {
+    B9_H_IDENTITY = 0,  /* def identity(s, /): return s              (configs[0] echo, configs[1])   */
+    B9_H_CRC32    = 1,  /* def crc32(s, /): return zlib.crc32(s.encode())                (configs[2]) */
+    B9_H_VADD_F32 = 2,  /* base64(fp32 a||b) -> base64(a+b)                               (configs[3]) */
+    B9_H_JSON_SUM = 3,  /* def json_sum(obj, /): return sum(obj["values"])                (configs[4]) */
+    B9_H_COUNT_
+};
+
+/* ---- per-task status, reported in b9_results.status ---------------------------------------
+ * COMPLETE/ERROR/RETRY are the runner's TaskStatus values (sdk/src/beta9/type.py TaskStatus,
+ * set at sdk/src/beta9/runner/taskqueue.py:344-361). REJECTED means the reference would have
+ * answered TaskQueuePutResponse{Ok:false} and never created the task
+ * (pkg/abstractions/taskqueue/taskqueue.go:213-218): the batch interface validates on the device,
+ * at drain time. UNSUPPORTED means the payload is valid but outside what the device handler
+ * implements (e.g. a float that needs shortest-repr formatting): the host must route that task
+ * through the reference's own CPU loop. The device never guesses. */
+enum b9_status {
+    B9_ST_COMPLETE    = 0,
+    B9_ST_ERROR       = 1,
+    B9_ST_RETRY       = 2,
+    B9_ST_REJECTED    = 3,
+    B9_ST_UNSUPPORTED = 4
+};
+
+/* ---- per-task flags (b9_push_meta.flags / ring header) ------------------------------------ */
+#define B9_TF_CANCELLED 0x01u  /* task already completed/cancelled/expired: TaskQueuePop skips it
+                                  (taskqueue.go:261-265); the drain compacts it away           */
+
+typedef struct b9_ctx b9_ctx;
+
+typedef struct b9_opts {
+    uint32_t struct_size;        /* sizeof(b9_opts), for forward compatibility                  */
+    int32_t  device;             /* CUDA device ordinal                                         */
+    uint64_t ring_bytes;         /* payload ring capacity in bytes (rounded up to 2^k); 0 = 1 GiB */
+    uint32_t ring_tasks;         /* task-slot ring capacity (rounded up to 2^k);       0 = 4 Mi  */
+    uint32_t max_drain_tasks;    /* most tasks one drain may take (< 2^24);            0 = 2 Mi  */
+    uint64_t max_result_bytes;   /* device result staging per drain;                   0 = 1 GiB */
+    uint32_t max_task_bytes;     /* largest single payload accepted;                   0 = 1 MiB */
+    uint32_t flags;              /* reserved, 0                                                  */
+} b9_opts;
+
+/* optional per-task metadata for a push; NULL pointers mean "all zero" */
+typedef struct b9_push_meta {
+    const int64_t *timestamp_unix;   /* TaskMessage.Timestamp      (pkg/types/task.go:64)       */
+    const int64_t *expires_unix_ns;  /* TaskMessage.Policy.Expires (pkg/types/task.go:121)      */
+    const uint8_t *retries;          /* TaskMessage.Retries        (pkg/types/task.go:63)       */
+    const uint8_t *flags;            /* B9_TF_*                                                  */
+} b9_push_meta;
+
+/* caller-owned result buffers for one drain */
+typedef struct b9_results {
+    uint8_t  *task_ids;     /* [cap_tasks*16] raw UUID of every task that produced a record      */
+    uint8_t  *status;       /* [cap_tasks]    enum b9_status                                     */
+    uint8_t  *has_result;   /* [cap_tasks]    0: runner sends no result bytes (falsy result or
+                                              error, runner/taskqueue.py:378), 1: bytes present  */
+    uint64_t *offsets;      /* [cap_tasks+1]  result i = payload[offsets[i] .. offsets[i+1])     */
+    uint8_t  *payload;      /* [cap_bytes]    TaskQueueCompleteRequest.result bytes
+                                              (taskqueue.proto:47-56), FIFO order                */
+    uint32_t  cap_tasks;
+    uint64_t  cap_bytes;
+    /* filled by the library */
+    uint32_t  n_results;    /* records written                                                   */
+    uint32_t  n_popped;     /* tasks removed from the queue (n_results + compacted-away ones)    */
+    uint64_t  n_bytes;      /* offsets[n_results]                                                */
+    uint64_t  need_bytes;   /* on B9_ENOSPC: payload capacity that would have sufficed           */
+} b9_results;
+
+typedef struct b9_stats {
+    uint64_t tasks_pushed, tasks_drained, bytes_h2d, bytes_d2h;
+    uint64_t kernel_launches;        /* kernels launched by this library since ctx creation      */
+    uint64_t drains;
+    float    last_push_h2d_ms;       /* CUDA-event time of the last push's H2D copies            */
+    float    last_drain_kernel_ms;   /* CUDA-event time around the last drain's kernel(s)        */
+    float    last_drain_d2h_ms;      /* CUDA-event time of the last drain's D2H copies           */
+    uint32_t last_drain_tiles;
+    uint32_t sm_count;
+    uint64_t last_drain_in_bytes;    /* payload bytes of the tasks the last drain consumed       */
+    uint64_t last_drain_out_bytes;   /* result bytes the last drain produced                     */
+} b9_stats;
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+uint32_t    b9_abi_version(void);
+int         b9_device_count(void);
+int         b9_ctx_create(const b9_opts *opts, b9_ctx **out);
+void        b9_ctx_destroy(b9_ctx *ctx);
+const char *b9_last_error(const b9_ctx *ctx);         /* ctx may be NULL for create failures     */
+const char *b9_handler_name(int handler);             /* "identity", "crc32", ...; NULL if unknown */
+int         b9_handler_id(const char *name);          /* inverse; B9_ENOSYS if unknown           */
+
+/* page-locked host memory for callers (so that push/drain DMA straight from/to their buffers) */
+void       *b9_host_alloc(b9_ctx *ctx, uint64_t bytes);
+void        b9_host_free(b9_ctx *ctx, void *p);
+
+/* ---- producer side ---------------------------------------------------------------------------
+ * b9_batch_push replaces, for n tasks at once, `taskQueueClient.Push` = Encode + RPUSH
+ * (pkg/abstractions/taskqueue/client.go:29-41) as reached from `RedisTaskQueue.put`
+ * (pkg/abstractions/taskqueue/taskqueue.go:176-208) -> `Dispatcher.SendAndExecute`
+ * (pkg/task/dispatch.go:75-118) -> `TaskQueueTask.Execute` (taskqueue/task.go:16-47).
+ * Tasks are appended in order (FIFO, like RPUSH). Returns B9_ENOSPC when the ring cannot take the
+ * whole batch (nothing is appended), B9_E2BIG when a task exceeds max_task_bytes. */
+int      b9_batch_push(b9_ctx *ctx, const uint8_t *task_ids, const uint8_t *payload,
+                       const uint64_t *offsets, uint32_t n, const b9_push_meta *meta);
+
+/* Pending tasks = what `TaskRepository.TasksInFlight` / `taskQueueClient.QueueLength` report for
+ * this queue (pkg/repository/task_redis.go:112-119, taskqueue/client.go:99-106); feeds
+ * `taskQueueAutoscalerSampleFunc` (taskqueue/autoscaler.go:18-51) unchanged. */
+uint64_t b9_depth(b9_ctx *ctx);
+uint64_t b9_depth_bytes(b9_ctx *ctx);
+
+/* Marks every pending task whose expires_unix_ns is non-zero and <= now as cancelled — the
+ * unclaimed-task branch of `Dispatcher.monitor` (pkg/task/dispatch.go:173-230). Returns count. */
+int64_t  b9_expire(b9_ctx *ctx, int64_t now_unix_ns);
+
+/* ---- consumer side ---------------------------------------------------------------------------
+ * b9_drain replaces, for up to max_tasks pending tasks in FIFO order, the whole
+ *   TaskQueuePop (taskqueue.go:228-310, client.go:43-96)
+ *   -> runner json.loads + handler + serialize_result
+ *      (sdk/src/beta9/runner/taskqueue.py:185-204,317-404; runner/common.py:297-305,484-489)
+ *   -> TaskQueueComplete's result hand-off (taskqueue.go:312-404)
+ * round trip: one persistent kernel deserialises, runs `handler`, and serialises every ready
+ * task, then the records are copied to `out`. Returns the number of result records (>= 0) or a
+ * negative error. On B9_ENOSPC (caller buffers too small) nothing is consumed, the records stay
+ * on the device and `b9_drain_fetch` can collect them with larger buffers. */
+int64_t  b9_drain(b9_ctx *ctx, int handler, uint32_t max_tasks, b9_results *out);
+
+/* Two-step form: run the kernel only (results stay in device staging), then fetch. `peek` != 0
+ * leaves the tasks in the queue, so the same resident batch can be drained again (used by the
+ * benchmark's device-resident timing and by retry-on-device-failure). */
+int64_t  b9_drain_launch(b9_ctx *ctx, int handler, uint32_t max_tasks, int peek);
+int64_t  b9_drain_fetch(b9_ctx *ctx, b9_results *out);
+
+/* Device-side encode of the queue wire records (the bytes `TaskMessage.Encode` produces,
+ * pkg/types/task.go:79-90) is declared in the "wire" section once implemented. */
+
+int      b9_stats_get(b9_ctx *ctx, b9_stats *out);
+int      b9_sync(b9_ctx *ctx);
+
+/* ---- host-side helpers kept bit-compatible with the reference --------------------------------
+ * `taskQueueScaleFunc` (pkg/abstractions/taskqueue/autoscaler.go:53-79): desired containers for a
+ * queue depth; *valid = 0 when the sample is invalid (queue_length == -1). */
+int      b9_task_queue_scale(int64_t queue_length, int64_t tasks_per_container,
+                             int64_t max_containers, int64_t max_replicas, int *valid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B9GPU_H */

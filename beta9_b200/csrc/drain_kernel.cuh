@@ -15,6 +15,7 @@
 #pragma once
 #include <stdint.h>
 #include "json_device.cuh"
+#include "handlers_device.cuh"
 
 namespace b9 {
 
@@ -150,7 +151,8 @@ __device__ inline uint32_t py_string_len(const uint8_t* __restrict__ p, uint32_t
 }
 
 // Lane 0: classify args[0] for the handler and fill the record. `pr` is the parse of the payload.
-__device__ inline void handler_phase_a(int handler, const uint8_t* __restrict__ p, const Parsed& pr, TaskRec& rec) {
+__device__ inline void handler_phase_a(int handler, const uint8_t* __restrict__ p, const Parsed& pr, TaskRec& rec,
+                                       const uint32_t* __restrict__ crc_table = nullptr) {
     rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
     if (pr.status != ST_OK) { rec.status = pr.status; return; }
     // handler(*args, **kwargs) with a positional-only one-parameter handler
@@ -177,6 +179,34 @@ __device__ inline void handler_phase_a(int handler, const uint8_t* __restrict__ 
         default: rec.status = ST_UNSUPPORTED; return;                       // floats / non-empty containers
         }
     }
+    case 1: {   // crc32: zlib.crc32(s.encode()); a non-str has no .encode -> AttributeError
+        if (pr.a0_kind != AK_STR) { rec.status = 1; return; }
+        uint32_t c = crc32_of_string_token(p, pr.a0_off, pr.a0_off + pr.a0_len, pr.a0_flags, crc_table);
+        if (c == 0) return;                                                 // 0 is falsy
+        rec.value = (long long)c; rec.out_len = dec_len_u64(c); rec.mode = OM_U32_DEC; rec.has = 1;
+        return;
+    }
+    case 2: {   // vadd_f32: base64 -> fp32 a||b -> a+b -> base64
+        if (pr.a0_kind != AK_STR) { rec.status = 1; return; }               // TypeError
+        if (pr.a0_flags & SF_NONPRINT) { rec.status = 1; return; }          // non-ASCII / DEL: ValueError / binascii.Error
+        if (pr.a0_flags & SF_ESC) { rec.status = ST_UNSUPPORTED; return; }  // escaped base64 text: not produced by the SDK
+        int64_t rn = b64_decoded_len(p, pr.a0_off + 1, pr.a0_off + pr.a0_len - 1);
+        if (rn < 0 || (rn % 8)) { rec.status = 1; return; }
+        uint32_t n = (uint32_t)(rn / 8);
+        if (n == 0) return;                                                 // "" is falsy
+        rec.src_off = pr.a0_off + 1; rec.src_len = n; rec.out_len = 2 + b64_encoded_len(4 * n); rec.mode = OM_VADD; rec.has = 1;
+        return;
+    }
+    case 3: {   // json_sum: sum(obj["values"])
+        if (pr.a0_kind != AK_OBJ) { rec.status = 1; return; }               // TypeError, or KeyError for {}
+        long long sum = 0;
+        int st = json_sum_object(p, pr.a0_off, pr.a0_off + pr.a0_len, &sum);
+        if (st) { rec.status = (uint8_t)st; return; }
+        if (sum == 0) return;
+        rec.value = sum; rec.mode = OM_I64_DEC; rec.has = 1;
+        rec.out_len = dec_len_u64((unsigned long long)(sum < 0 ? -sum : sum)) + (sum < 0 ? 1u : 0u);
+        return;
+    }
     default:
         rec.status = ST_UNSUPPORTED; return;
     }
@@ -191,7 +221,9 @@ __global__ void __launch_bounds__(DRAIN_THREADS, 2) drain_kernel(DrainArgs a) {
     __shared__ unsigned long long s_tile;
     __shared__ uint64_t s_base;                     // lb_pack(exclusive bytes, exclusive count) of this tile
 
+    __shared__ uint32_t s_crc_table[HANDLER == 1 ? 256 : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (HANDLER == 1) { s_crc_table[tid & 255] = crc_table_entry(tid & 255); __syncthreads(); }
 
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(&a.ctl->ticket, 1ull);
@@ -202,6 +234,21 @@ __global__ void __launch_bounds__(DRAIN_THREADS, 2) drain_kernel(DrainArgs a) {
         const uint32_t nt = min((uint32_t)TILE_TASKS, a.n_tasks - t0);
 
         // ---------------- phase A: deserialise, run the handler's sizing pass --------------------
+        if (HANDLER != 0) {
+            // v1 of the non-identity handlers: one thread per task, start to finish
+            for (uint32_t k = tid; k < nt; k += DRAIN_THREADS) {
+                const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
+                const uint64_t h = __ldg(a.hdr + slot);
+                TaskRec rec; rec.ready = !(hdr_flags(h) & 1u); rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0;
+                rec.src_off = 0; rec.src_len = 0; rec.value = 0;
+                if (rec.ready) {
+                    const uint8_t* p = a.payload + __ldg(a.off + slot);
+                    Parsed pr = parse_payload(p, hdr_len(h));
+                    handler_phase_a(HANDLER, p, pr, rec, s_crc_table);
+                }
+                s_rec[k] = rec;
+            }
+        } else
         for (uint32_t k = warp; k < nt; k += DRAIN_WARPS) {
             const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
             const uint64_t h = __ldg(a.hdr + slot);
@@ -295,6 +342,24 @@ __global__ void __launch_bounds__(DRAIN_THREADS, 2) drain_kernel(DrainArgs a) {
         if (!fits && tid == 0) a.ctl->overflow = 1u;
 
         // ---------------- phase B: serialise ------------------------------------------------------
+        if (HANDLER != 0) {
+            for (uint32_t k = tid; k < nt; k += DRAIN_THREADS) {
+                const TaskRec rec = s_rec[k];
+                if (!rec.ready) continue;
+                const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
+                const uint32_t j = base_cnt + s_excl_cnt[k];
+                const uint64_t ob = base_bytes + s_excl_bytes[k];
+                a.out_off[j] = ob; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
+                if (!rec.has || !fits) continue;
+                uint8_t* o = a.out_payload + ob;
+                if (rec.mode == OM_VADD) vadd_write(a.payload + __ldg(a.off + slot), rec.src_off, rec.src_len, o);
+                else {
+                    long long v = rec.value; uint32_t l = rec.out_len;
+                    if (v < 0) { *o++ = '-'; --l; v = -v; }
+                    write_dec(o, (unsigned long long)v, l);
+                }
+            }
+        } else
         for (uint32_t k = warp; k < nt; k += DRAIN_WARPS) {
             const TaskRec rec = s_rec[k];
             if (!rec.ready) continue;

@@ -99,7 +99,8 @@ def test_handcrafted_edge_cases(dq):
     assert_matches_oracle(b, r, o, allow_unsupported=len(HANDCRAFTED))
     # the device may decline (UNSUPPORTED) only valid payloads whose arg is a float / non-empty container
     for i in np.flatnonzero(r.status == 4):
-        assert o.status[i] in (0, 4), HANDCRAFTED[i]
+        # ... or a number with an exponent, whose float64 overflow (-> Ok:false) the device does not decide
+        assert o.status[i] in (0, 4) or (o.status[i] == 3 and b"e" in HANDCRAFTED[i].lower()), HANDCRAFTED[i]
 
 
 def test_empty_and_ragged(dq):

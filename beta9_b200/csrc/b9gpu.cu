@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -20,6 +21,7 @@
 
 #include "../../include/b9gpu.h"
 #include "drain_kernel.cuh"
+#include "drain2.cuh"
 
 using namespace b9;
 
@@ -54,7 +56,9 @@ constexpr uint64_t SEG_ALIGN  = 256;
 struct b9_ctx {
     int device = 0;
     int sm_count = 0;
-    int resident_ctas = 0;             // drain kernel CTAs that fit per SM x SMs
+    int resident_ctas = 0;             // drain kernel (v1) CTAs that fit per SM x SMs
+    int drain_version = 2;             // B9_DRAIN_KERNEL=1 selects the first-generation kernel (A/B checks)
+    uint32_t stage_bytes_override = 0; // B9_STAGE_BYTES: force the v2 stage-buffer size
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     std::mutex mu;
@@ -112,6 +116,27 @@ bool place_segment(b9_ctx* c, uint64_t bytes, uint64_t* start) {
 
 template <int H> cudaError_t launch_drain(const DrainArgs& a, int grid, cudaStream_t s) {
     drain_kernel<H><<<grid, DRAIN_THREADS, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// v2: bulk-copy staged tiles. Dynamic shared memory = control block + 2 stage buffers of in_cap (+slack).
+size_t drain2_smem_bytes(uint32_t in_cap) {
+    const size_t ctl = (sizeof(D2Shared) + 127u) & ~(size_t)127u;
+    const size_t stride = ((size_t)in_cap + 64u + 127u) & ~(size_t)127u;
+    return ctl + D2_STAGES * stride;
+}
+template <int H> cudaError_t launch_drain2(DrainArgs a, uint32_t in_cap, int sm_count, cudaStream_t s, int* grid_out) {
+    const size_t smem = drain2_smem_bytes(in_cap);
+    cudaError_t e = cudaFuncSetAttribute(drain2_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drain2_kernel<H>, D2_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    a.n_tiles = (a.n_tasks + D2_THREADS - 1) / D2_THREADS;
+    const int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)(per_sm * sm_count));
+    *grid_out = grid;
+    drain2_kernel<H><<<grid, D2_THREADS, smem, s>>>(a, in_cap);
     return cudaGetLastError();
 }
 
@@ -190,7 +215,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     CUC(cudaMalloc(&c->d_out_status, md));
     CUC(cudaMalloc(&c->d_out_has, md));
     CUC(cudaMalloc(&c->d_ctl, sizeof(DrainCtl)));
-    CUC(cudaMalloc(&c->d_tile_state, ((size_t)md / TILE_TASKS + 2) * sizeof(uint64_t)));
+    CUC(cudaMalloc(&c->d_tile_state, ((size_t)md / D2_THREADS + 2) * sizeof(uint64_t)));
     CUC(cudaMalloc(&c->d_count, sizeof(unsigned long long)));
     CUC(cudaHostAlloc(&c->h_ctl, sizeof(DrainCtl), cudaHostAllocDefault));
     CUC(cudaHostAlloc(&c->h_count, sizeof(unsigned long long), cudaHostAllocDefault));
@@ -199,6 +224,8 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     if (per_sm < 1) per_sm = 1;
     c->resident_ctas = per_sm * c->sm_count;
     c->stats.sm_count = (uint32_t)c->sm_count;
+    if (const char* v = getenv("B9_DRAIN_KERNEL")) c->drain_version = atoi(v) == 1 ? 1 : 2;
+    if (const char* v = getenv("B9_STAGE_BYTES")) c->stage_bytes_override = ((uint32_t)atoi(v) + 1023u) & ~1023u;
 #undef CUC
     *out = c;
     return B9_OK;
@@ -346,12 +373,25 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_ids = c->d_out_ids;
     a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.handler = handler;
     cudaStream_t s = c->stream;
+    const bool v2 = c->drain_version == 2;
+    if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
     CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));
-    const int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
+    int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
+    // stage buffers sized for the window's average task: 64 tasks x 1.25 + 1 KiB, within [8 KiB, 100 KiB]
+    uint32_t in_cap = (uint32_t)std::min<uint64_t>(100u << 10, std::max<uint64_t>(8u << 10, (in_bytes / n) * D2_THREADS * 5 / 4 + 1024));
+    in_cap = (in_cap + 1023u) & ~1023u;
+    if (c->stage_bytes_override) in_cap = c->stage_bytes_override;
     CU(cudaEventRecord(c->ev_a, s));
     cudaError_t le;
-    switch (handler) {
+    if (v2) {
+        switch (handler) {
+        case B9_H_IDENTITY: le = launch_drain2<0>(a, in_cap, c->sm_count, s, &grid); break;
+        case B9_H_CRC32:    le = launch_drain2<1>(a, in_cap, c->sm_count, s, &grid); break;
+        case B9_H_VADD_F32: le = launch_drain2<2>(a, in_cap, c->sm_count, s, &grid); break;
+        default:            le = launch_drain2<3>(a, in_cap, c->sm_count, s, &grid); break;
+        }
+    } else switch (handler) {
     case B9_H_IDENTITY: le = launch_drain<0>(a, grid, s); break;
     case B9_H_CRC32:    le = launch_drain<1>(a, grid, s); break;
     case B9_H_VADD_F32: le = launch_drain<2>(a, grid, s); break;

@@ -1,0 +1,584 @@
+// drain kernel v2 — the production drain.
+//
+// Same contract as v1 (drain_kernel.cuh: persistent CTAs, ticket work stealing, ballot compaction,
+// decoupled look-back, FIFO-dense results) with the data path rebuilt around the B200 memory system:
+//
+//   * a tile's payload bytes are ONE contiguous range of the ring in the common case; warp 0 pulls
+//     it into shared memory with a single bulk async copy (cp.async.bulk / TMA 1-D, completion on
+//     an mbarrier), double buffered so the next tile streams in while this one is processed;
+//   * phase A and B are thread-per-task over the staged bytes (16-byte shared loads, SWAR
+//     classification of the string body, 16-byte global stores): small uniform tasks keep all 32
+//     lanes busy, which a warp-per-task layout cannot (a 284-byte task fills 18 of 32 lanes);
+//   * strings with escapes / non-ASCII (the 1 % "adversarial" share, and most of configs[2]) are
+//     NOT walked by one lane: the warp splits the body into 32 chunks, every lane finds its first
+//     code-unit boundary by a bounded look-behind and transcodes its chunk (esc_* below);
+//   * anything that is not the SDK's canonical frame goes through the sequential validating parser
+//     (json_device.cuh) — correctness first, it is rare.
+//
+// Reference behaviour realised: see drain_kernel.cuh's header (pop, decode, loads, call, result).
+#pragma once
+#include <stdint.h>
+#include "drain_kernel.cuh"
+
+namespace b9 {
+
+constexpr int D2_THREADS = 64;               // threads per CTA == tasks per tile
+constexpr int D2_WARPS   = D2_THREADS / 32;
+constexpr int D2_STAGES  = 2;
+
+// ------------------------------------------------------------------ PTX: mbarrier + bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
+// global -> shared::cta bulk async copy; dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------ per-stage tile metadata
+struct D2Meta {
+    uint64_t goff[D2_THREADS];     // physical ring offset of each task's payload
+    uint32_t soff[D2_THREADS];     // offset inside the stage buffer (when staged)
+    uint32_t len[D2_THREADS];
+    uint8_t  ready[D2_THREADS];
+    unsigned long long tile;
+    uint32_t nt;
+    uint32_t staged;               // 1: payload bytes are (arriving) in shared memory; 0: read from global
+};
+
+// ------------------------------------------------------------------ SWAR classification
+// any byte of the four words outside printable ASCII, or equal to '"' or '\\'?
+// Exactness: a false positive can only occur in a group that also holds a byte >= 0x80, which is
+// "special" anyway (carries out of a byte need a byte >= 0x80 / 0xA0 below them).
+__device__ __forceinline__ bool swar_special16(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    const uint32_t K1 = 0x01010101u, K60 = 0x60606060u, K7F = 0x7F7F7F7Fu, Q = 0x22222222u, S = 0x5C5C5C5Cu, H = 0x80808080u;
+    uint32_t hi = (x | y | z | w) | ((x + K1) | (y + K1) | (z + K1) | (w + K1));          // >= 0x7F
+    uint32_t lo = (x + K60) & (y + K60) & (z + K60) & (w + K60);                          // bit7 clear: < 0x20
+    uint32_t eq = ((x ^ Q) + K7F) & ((y ^ Q) + K7F) & ((z ^ Q) + K7F) & ((w ^ Q) + K7F)   // bit7 clear: == '"'
+                & ((x ^ S) + K7F) & ((y ^ S) + K7F) & ((z ^ S) + K7F) & ((w ^ S) + K7F);  //            == '\\'
+    return ((hi | ~lo | ~eq) & H) != 0;
+}
+__device__ __forceinline__ bool byte_special(uint32_t c) { return c < 0x20u || c >= 0x7Fu || c == '"' || c == '\\'; }
+
+// Thread-per-task: is the payload exactly  {"args": ["<body>"], "kwargs": {}}  with a body of
+// printable ASCII free of '"' and '\\'?  `frame_ok` reports the frame alone.
+__device__ inline bool quick_clean_framed(const uint8_t* __restrict__ p, uint32_t len, bool* frame_ok) {
+    *frame_ok = false;
+    if (len < FRAME_PRE_LEN + FRAME_SUF_LEN) return false;
+    bool ok = true;
+    #pragma unroll
+    for (uint32_t i = 0; i < FRAME_PRE_LEN; ++i) ok &= p[i] == FRAME_PRE[i];
+    const uint8_t* sfx = p + len - FRAME_SUF_LEN;
+    #pragma unroll
+    for (uint32_t i = 0; i < FRAME_SUF_LEN; ++i) ok &= sfx[i] == FRAME_SUF[i];
+    if (!ok) return false;
+    *frame_ok = true;
+    const uint8_t* b0 = p + FRAME_PRE_LEN;
+    const uint8_t* b1 = sfx;
+    const uint8_t* w0 = (const uint8_t*)(((uintptr_t)b0 + 15u) & ~(uintptr_t)15u);
+    const uint8_t* w1 = (const uint8_t*)((uintptr_t)b1 & ~(uintptr_t)15u);
+    bool special = false;
+    if (w0 >= w1) {                                   // short body: bytewise
+        for (const uint8_t* q = b0; q < b1; ++q) special |= byte_special(*q);
+        return !special;
+    }
+    for (const uint8_t* q = b0; q < w0; ++q) special |= byte_special(*q);
+    for (const uint8_t* q = w1; q < b1; ++q) special |= byte_special(*q);
+    for (const uint4* q = (const uint4*)w0; q < (const uint4*)w1; ++q) {
+        uint4 v = *q;
+        special |= swar_special16(v.x, v.y, v.z, v.w);
+    }
+    return !special;
+}
+
+// Thread-per-task copy of n bytes to global memory: 16-byte stores on the destination,
+// 4-byte loads + funnel shift on the (arbitrarily aligned) source.
+__device__ inline void thread_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
+    uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    if (head > n) head = n;
+    for (uint32_t i = 0; i < head; ++i) dst[i] = src[i];
+    dst += head; src += head; n -= head;
+    const uint32_t nvec = n >> 4;
+    if (nvec) {
+        const uint32_t sh = (uint32_t)((uintptr_t)src & 3u), bits = sh * 8;
+        const uint32_t* sw = (const uint32_t*)(src - sh);
+        uint4* dv = (uint4*)dst;
+        uint32_t w0 = sw[0];
+        for (uint32_t v = 0; v < nvec; ++v) {
+            uint32_t w1 = sw[4 * v + 1], w2 = sw[4 * v + 2], w3 = sw[4 * v + 3], w4 = sw[4 * v + 4];  // w4: <= 3 bytes of over-read, inside the buffers' slack
+            uint4 o;
+            o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
+            o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
+            dv[v] = o;
+            w0 = w4;
+        }
+    }
+    const uint32_t done = nvec << 4;
+    for (uint32_t i = done; i < n; ++i) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ chunk-parallel string transcoding
+// body = the bytes between the frame's quotes. A "unit" is what Go's unquote consumes at once: a
+// plain byte, an escape, a \uXXXX (with its low surrogate partner), a UTF-8 sequence.
+__device__ __forceinline__ int hex4(const uint8_t* __restrict__ b) {
+    int h0 = hexval(b[0]), h1 = hexval(b[1]), h2 = hexval(b[2]), h3 = hexval(b[3]);
+    if ((h0 | h1 | h2 | h3) < 0) return -1;
+    return (h0 << 12) | (h1 << 8) | (h2 << 4) | h3;
+}
+__device__ __forceinline__ uint32_t bs_run_before(const uint8_t* __restrict__ b, uint32_t q) {   // backslashes ending at q-1
+    uint32_t r = 0;
+    while (r < q && b[q - 1 - r] == '\\') ++r;
+    return r;
+}
+// is there a "\uDC00..\uDFFF" escape text at position q?
+__device__ __forceinline__ bool low_surrogate_at(const uint8_t* __restrict__ b, uint32_t q, uint32_t n) {
+    if (q + 6 > n || b[q] != '\\' || b[q + 1] != 'u') return false;
+    int r = hex4(b + q + 2);
+    return r >= 0xDC00 && r <= 0xDFFF;
+}
+__device__ __forceinline__ bool high_surrogate_escape_at(const uint8_t* __restrict__ b, uint32_t q, uint32_t n) {
+    if (q + 6 > n || b[q] != '\\' || b[q + 1] != 'u') return false;
+    int r = hex4(b + q + 2);
+    return r >= 0xD800 && r <= 0xDBFF;
+}
+__device__ __forceinline__ uint32_t utf8_valid_len(const uint8_t* __restrict__ b, uint32_t q, uint32_t n) {
+    // length of the valid UTF-8 sequence starting at q (Go utf8.DecodeRune), or 0
+    uint8_t c = b[q]; uint32_t rem = n - q;
+    if (c >= 0xC2 && c <= 0xDF) return (rem >= 2 && (b[q + 1] & 0xC0) == 0x80) ? 2u : 0u;
+    if (c >= 0xE0 && c <= 0xEF) {
+        uint8_t lo = (c == 0xE0) ? 0xA0 : 0x80, hi = (c == 0xED) ? 0x9F : 0xBF;
+        return (rem >= 3 && b[q + 1] >= lo && b[q + 1] <= hi && (b[q + 2] & 0xC0) == 0x80) ? 3u : 0u;
+    }
+    if (c >= 0xF0 && c <= 0xF4) {
+        uint8_t lo = (c == 0xF0) ? 0x90 : 0x80, hi = (c == 0xF4) ? 0x8F : 0xBF;
+        return (rem >= 4 && b[q + 1] >= lo && b[q + 1] <= hi && (b[q + 2] & 0xC0) == 0x80 && (b[q + 3] & 0xC0) == 0x80) ? 4u : 0u;
+    }
+    return 0u;
+}
+
+// First unit boundary at or after `lo`, decided from a bounded neighbourhood of lo. Exact for a
+// body whose escapes are all well-formed; for a malformed body some lane reports !ok and the
+// answer is discarded.
+__device__ inline uint32_t first_unit_start(const uint8_t* __restrict__ b, uint32_t n, uint32_t lo) {
+    if (lo == 0 || lo >= n) return lo;
+    // (1) lo is the character after an escape's backslash
+    if (bs_run_before(b, lo) & 1u) {
+        uint32_t next = lo + 1;
+        if (b[lo] == 'u') {
+            next = lo + 5;
+            if (high_surrogate_escape_at(b, lo - 1, n) && low_surrogate_at(b, next, n)) next += 6;
+        }
+        return next;
+    }
+    // (2) lo is one of the hex digits of a \uXXXX that began 2..5 bytes earlier
+    #pragma unroll
+    for (uint32_t k = 2; k <= 5; ++k) {
+        if (lo >= k) {
+            uint32_t q = lo - k;
+            if (b[q] == '\\' && b[q + 1] == 'u' && !(bs_run_before(b, q) & 1u)) {
+                uint32_t next = q + 6;
+                if (high_surrogate_escape_at(b, q, n) && low_surrogate_at(b, next, n)) next += 6;
+                return next;
+            }
+        }
+    }
+    // (3) lo starts the low-surrogate escape that the high surrogate 6 bytes earlier consumes
+    if (lo >= 6 && low_surrogate_at(b, lo, n) && high_surrogate_escape_at(b, lo - 6, n) && !(bs_run_before(b, lo - 6) & 1u))
+        return lo + 6;
+    // (4) lo is a continuation byte of a valid UTF-8 sequence that began 1..3 bytes earlier
+    if ((b[lo] & 0xC0) == 0x80) {
+        for (uint32_t k = 1; k <= 3 && k <= lo; ++k) {
+            uint8_t c = b[lo - k];
+            if ((c & 0xC0) == 0x80) continue;            // another continuation byte: keep looking back
+            if (c >= 0xC2) { uint32_t L = utf8_valid_len(b, lo - k, n); if (L > k) return lo - k + L; }
+            break;
+        }
+    }
+    return lo;
+}
+
+// One unit at b[i] (i < n): advances i, returns the code point Go's unquote yields; *ok = false on
+// anything that is not a well-formed JSON string body byte (bad escape, raw control byte, raw '"').
+__device__ inline uint32_t next_unit(const uint8_t* __restrict__ b, uint32_t& i, uint32_t n, bool* ok) {
+    uint8_t c = b[i];
+    if (c == '\\') {
+        if (i + 1 >= n) { *ok = false; ++i; return 0; }
+        uint8_t e = b[i + 1];
+        if (e == 'u') {
+            int r = (i + 6 <= n) ? hex4(b + i + 2) : -1;
+            if (r < 0) { *ok = false; i += 2; return 0; }
+            i += 6;
+            if (r >= 0xD800 && r <= 0xDFFF) {
+                if (r <= 0xDBFF && i + 6 <= n && b[i] == '\\' && b[i + 1] == 'u') {
+                    int r1 = hex4(b + i + 2);
+                    if (r1 >= 0xDC00 && r1 <= 0xDFFF) { i += 6; return 0x10000u + (((uint32_t)r - 0xD800u) << 10) + ((uint32_t)r1 - 0xDC00u); }
+                }
+                return 0xFFFDu;
+            }
+            return (uint32_t)r;
+        }
+        i += 2;
+        switch (e) {
+        case '"': case '\\': case '/': return e;
+        case 'b': return 8; case 'f': return 12; case 'n': return 10; case 'r': return 13; case 't': return 9;
+        default: *ok = false; return 0;
+        }
+    }
+    if (c < 0x20 || c == '"') { *ok = false; ++i; return 0; }
+    if (c < 0x80) { ++i; return c; }
+    uint32_t L = utf8_valid_len(b, i, n);
+    if (!L) { ++i; return 0xFFFDu; }
+    uint32_t cp;
+    if (L == 2) cp = ((c & 0x1Fu) << 6) | (b[i + 1] & 0x3Fu);
+    else if (L == 3) cp = ((c & 0x0Fu) << 12) | ((b[i + 1] & 0x3Fu) << 6) | (b[i + 2] & 0x3Fu);
+    else cp = ((c & 0x07u) << 18) | ((b[i + 1] & 0x3Fu) << 12) | ((b[i + 2] & 0x3Fu) << 6) | (b[i + 3] & 0x3Fu);
+    i += L;
+    return cp;
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
+    uint32_t inc = v;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    return inc - v;
+}
+
+// Warp-cooperative: json.dumps length of the framed string body, or ok=false if the body is not a
+// well-formed JSON string ending exactly at the frame's closing quote.
+__device__ inline bool esc_measure(const uint8_t* __restrict__ body, uint32_t n, int lane, uint32_t* out_len) {
+    const uint32_t S = (n + 31u) / 32u;
+    const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
+    bool ok = true;
+    uint32_t mine = 0;
+    if (lo < hi) {
+        uint32_t i = first_unit_start(body, n, lo);
+        while (i < hi && ok) mine += py_escaped_len(next_unit(body, i, n, &ok));
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    *out_len = 2u + warp_sum(mine);
+    return ok;
+}
+
+// Warp-cooperative: write json.dumps(body) to dst (global). Only called after esc_measure said ok.
+__device__ inline void esc_emit(const uint8_t* __restrict__ body, uint32_t n, int lane, uint8_t* __restrict__ dst) {
+    const uint32_t S = (n + 31u) / 32u;
+    const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
+    bool ok = true;
+    uint32_t mine = 0, start = lo;
+    if (lo < hi) {
+        start = first_unit_start(body, n, lo);
+        uint32_t i = start;
+        while (i < hi) mine += py_escaped_len(next_unit(body, i, n, &ok));
+    }
+    const uint32_t at = 1u + warp_excl_scan(mine, lane);
+    if (lane == 0) dst[0] = '"';
+    if (lane == 31) dst[at + mine] = '"';
+    if (lo < hi) {
+        uint8_t* o = dst + at;
+        uint32_t i = start;
+        while (i < hi) o += py_emit(next_unit(body, i, n, &ok), o);
+    }
+}
+
+// ------------------------------------------------------------------ the kernel
+struct D2Shared {
+    D2Meta meta[D2_STAGES];
+    TaskRec rec[D2_THREADS];
+    uint32_t excl_bytes[D2_THREADS], excl_cnt[D2_THREADS];
+    uint32_t warp_bytes[D2_WARPS], warp_cnt[D2_WARPS];
+    uint32_t slow_list[D2_THREADS]; uint32_t n_slow;
+    uint64_t base;
+    unsigned long long next_tile;
+    uint32_t crc_table[256];
+    alignas(8) uint64_t mbar[D2_STAGES];
+};
+
+// warp 0, step 1: start the loads of a tile's slot words (two tasks per lane); nothing is consumed
+// here, so the latency overlaps whatever the warp does until d2_stage_tile.
+struct D2MetaRegs { uint64_t off[2], hdr[2]; };
+__device__ __forceinline__ void d2_load_meta(const DrainArgs& a, unsigned long long tile, int lane, D2MetaRegs& r) {
+    const uint32_t t0 = (uint32_t)tile * D2_THREADS;
+    const uint32_t nt = min((uint32_t)D2_THREADS, a.n_tasks - t0);
+    #pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const uint32_t k = lane + 32 * q;
+        r.off[q] = 0; r.hdr[q] = 0;
+        if (k < nt) {
+            const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
+            r.hdr[q] = __ldg(a.hdr + slot);
+            r.off[q] = __ldg(a.off + slot);
+        }
+    }
+}
+
+// warp 0, step 2: decide how to stage the tile and fire the bulk copies
+__device__ inline void d2_stage_tile(const DrainArgs& a, unsigned long long tile, const D2MetaRegs& r, D2Meta& m, uint8_t* buf,
+                                     uint32_t in_cap, uint64_t* bar, int lane) {
+    const uint32_t t0 = (uint32_t)tile * D2_THREADS;
+    const uint32_t nt = min((uint32_t)D2_THREADS, a.n_tasks - t0);
+    uint64_t off[2], end[2]; uint32_t len[2]; bool valid[2];
+    #pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const uint32_t k = lane + 32 * q;
+        valid[q] = k < nt;
+        off[q] = r.off[q]; len[q] = valid[q] ? hdr_len(r.hdr[q]) : 0u;
+        if (valid[q]) { m.goff[k] = off[q]; m.len[k] = len[q]; m.ready[k] = !(hdr_flags(r.hdr[q]) & 1u); }
+        end[q] = off[q] + len[q];
+    }
+    // contiguous?  task k starts where task k-1 ended
+    uint64_t prev0 = __shfl_up_sync(0xffffffffu, end[0], 1);
+    uint64_t prev1 = __shfl_up_sync(0xffffffffu, end[1], 1);
+    const uint64_t end0_last = __shfl_sync(0xffffffffu, end[0], 31);
+    if (lane == 0) { prev0 = off[0]; prev1 = end0_last; }
+    bool contig = (!valid[0] || off[0] == prev0) && (!valid[1] || off[1] == prev1);
+    contig = __all_sync(0xffffffffu, contig);
+    const uint64_t gs = __shfl_sync(0xffffffffu, off[0], 0);
+    const uint32_t last = nt - 1;
+    const uint64_t ge0 = __shfl_sync(0xffffffffu, end[0], last & 31), ge1 = __shfl_sync(0xffffffffu, end[1], last & 31);
+    const uint64_t ge = (last < 32) ? ge0 : ge1;
+    uint32_t staged = 0;
+    if (contig) {
+        const uint64_t as = gs & ~15ull;
+        const uint64_t bytes = ((ge + 15ull) & ~15ull) - as;
+        if (bytes <= in_cap) {
+            staged = 1;
+            #pragma unroll
+            for (int q = 0; q < 2; ++q) if (valid[q]) m.soff[lane + 32 * q] = (uint32_t)(off[q] - as);
+            if (lane == 0) {
+                mbar_expect_tx(bar, (uint32_t)bytes);
+                if (bytes) bulk_g2s(buf, a.payload + as, (uint32_t)bytes, bar);
+            }
+        }
+    } else {
+        // scattered tile (it spans pushes): one copy per task, each widened to 16-byte boundaries
+        uint32_t asz[2];
+        #pragma unroll
+        for (int q = 0; q < 2; ++q) asz[q] = (valid[q] && len[q]) ? (uint32_t)(((end[q] + 15ull) & ~15ull) - (off[q] & ~15ull)) : 0u;
+        const uint32_t ex0 = warp_excl_scan(asz[0], lane);
+        const uint32_t tot0 = __shfl_sync(0xffffffffu, ex0 + asz[0], 31);
+        const uint32_t ex1 = tot0 + warp_excl_scan(asz[1], lane);
+        const uint32_t total = __shfl_sync(0xffffffffu, ex1 + asz[1], 31);
+        if (total <= in_cap) {
+            staged = 1;
+            if (lane == 0) mbar_expect_tx(bar, total);
+            __syncwarp();
+            if (valid[0]) { m.soff[lane] = ex0 + (uint32_t)(off[0] & 15ull); if (asz[0]) bulk_g2s(buf + ex0, a.payload + (off[0] & ~15ull), asz[0], bar); }
+            if (valid[1]) { m.soff[lane + 32] = ex1 + (uint32_t)(off[1] & 15ull); if (asz[1]) bulk_g2s(buf + ex1, a.payload + (off[1] & ~15ull), asz[1], bar); }
+        }
+    }
+    if (lane == 0) { m.tile = tile; m.nt = nt; m.staged = staged; }
+}
+
+template <int HANDLER>
+__global__ void __launch_bounds__(D2_THREADS, 4) drain2_kernel(DrainArgs a, uint32_t in_cap) {
+    extern __shared__ __align__(128) uint8_t d2_smem[];
+    D2Shared& S = *reinterpret_cast<D2Shared*>(d2_smem);
+    uint8_t* const bufs = d2_smem + ((sizeof(D2Shared) + 127u) & ~127u);
+    const uint32_t buf_stride = (in_cap + 64u + 127u) & ~127u;           // 64 bytes of readable slack behind each stage
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) { mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (HANDLER == 1) for (int i = tid; i < 256; i += D2_THREADS) S.crc_table[i] = crc_table_entry(i);
+    __syncthreads();
+
+    uint32_t stage = 0, parity_bits = 0;   // bit s: phase parity of stage s's mbarrier
+    // warp 0 runs a three-deep software pipeline so that no global latency sits between two
+    // block barriers: ticket(i+3) is being claimed while the slot words of tile i+2 are in flight
+    // and the payload bytes of tile i+1 stream into the other stage.
+    unsigned long long t_meta = ~0ull;     // tile whose slot words are in `mregs`
+    unsigned long long t_raw = ~0ull;      // lane 0: ticket claimed for the tile after t_meta
+    D2MetaRegs mregs; mregs.off[0] = mregs.off[1] = mregs.hdr[0] = mregs.hdr[1] = 0;
+    if (warp == 0) {
+        unsigned long long t0 = 0, t1 = 0;
+        if (lane == 0) { t0 = atomicAdd(&a.ctl->ticket, 1ull); t1 = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
+        t0 = __shfl_sync(0xffffffffu, t0, 0); t1 = __shfl_sync(0xffffffffu, t1, 0);
+        if (t0 < a.n_tiles) { D2MetaRegs r0; d2_load_meta(a, t0, lane, r0); d2_stage_tile(a, t0, r0, S.meta[0], bufs, in_cap, &S.mbar[0], lane); }
+        else if (lane == 0) S.meta[0].tile = t0;
+        t_meta = t1;
+        if (t_meta < a.n_tiles) d2_load_meta(a, t_meta, lane, mregs);
+    }
+    __syncthreads();
+
+    for (;;) {
+        D2Meta& M = S.meta[stage];
+        const unsigned long long tile = M.tile;
+        if (tile >= a.n_tiles) break;
+        if (warp == 0) {
+            // stage tile i+1 (its slot words were requested one iteration ago) ...
+            if (t_meta < a.n_tiles) d2_stage_tile(a, t_meta, mregs, S.meta[stage ^ 1], bufs + (size_t)(stage ^ 1) * buf_stride, in_cap, &S.mbar[stage ^ 1], lane);
+            else if (lane == 0) S.meta[stage ^ 1].tile = t_meta;
+            // ... request the slot words of tile i+2, claim the ticket of tile i+3
+            t_meta = __shfl_sync(0xffffffffu, t_raw, 0);
+            if (t_meta < a.n_tiles) d2_load_meta(a, t_meta, lane, mregs);
+            if (lane == 0) t_raw = atomicAdd(&a.ctl->ticket, 1ull);
+        }
+        const uint32_t nt = M.nt;
+        const uint32_t t0 = (uint32_t)tile * D2_THREADS;
+        const bool staged = M.staged != 0;
+        const uint8_t* const sbuf = bufs + (size_t)stage * buf_stride;
+        if (staged) { mbar_wait(&S.mbar[stage], (parity_bits >> stage) & 1u); parity_bits ^= 1u << stage; }
+        if (tid == 0) S.n_slow = 0;
+        __syncthreads();
+
+        // ---------------- phase A (thread per task) -------------------------------------------------
+        {
+            TaskRec rec; rec.ready = 0; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
+            if (tid < (int)nt) {
+                rec.ready = M.ready[tid];
+                if (rec.ready) {
+                    const uint32_t len = M.len[tid];
+                    const uint8_t* p = staged ? sbuf + M.soff[tid] : a.payload + M.goff[tid];
+                    if (HANDLER == 0) {
+                        bool frame_ok;
+                        if (quick_clean_framed(p, len, &frame_ok)) {
+                            const uint32_t tok = len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
+                            if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
+                        } else {
+                            rec.mode = frame_ok ? OM_STR_PAR : OM_NONE;         // decided in the cooperative pass
+                            S.slow_list[atomicAdd(&S.n_slow, 1u)] = (uint32_t)tid;
+                        }
+                    } else {
+                        Parsed pr = parse_payload(p, len);
+                        handler_phase_a(HANDLER, p, pr, rec, S.crc_table);
+                    }
+                }
+            }
+            S.rec[tid] = rec;
+        }
+        __syncthreads();
+        // ---------------- phase A, cooperative pass over the tasks the quick look could not settle --
+        if (HANDLER == 0) {
+            const uint32_t ns = S.n_slow;
+            for (uint32_t s = warp; s < ns; s += D2_WARPS) {
+                const uint32_t k = S.slow_list[s];
+                const uint32_t len = M.len[k];
+                const uint8_t* p = staged ? sbuf + M.soff[k] : a.payload + M.goff[k];
+                TaskRec rec = S.rec[k];
+                bool done = false;
+                if (rec.mode == OM_STR_PAR) {                                     // canonical frame, body needs transcoding
+                    uint32_t ol;
+                    const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
+                    if (esc_measure(p + FRAME_PRE_LEN, n, lane, &ol)) {
+                        rec.has = 1; rec.src_off = FRAME_PRE_LEN; rec.src_len = n; rec.out_len = ol; done = true;   // n > 0 here
+                    }
+                }
+                if (!done) {
+                    if (lane == 0) { Parsed pr = parse_payload(p, len); handler_phase_a(0, p, pr, rec, nullptr); rec.ready = 1; }
+                }
+                if (lane == 0) S.rec[k] = rec;
+            }
+            __syncthreads();
+        }
+
+        // ---------------- compaction + sizes --------------------------------------------------------
+        uint32_t my_bytes = 0, my_cnt = 0;
+        if (tid < (int)nt) { my_bytes = S.rec[tid].out_len; my_cnt = S.rec[tid].ready ? 1u : 0u; }
+        const uint32_t ready_mask = __ballot_sync(0xffffffffu, my_cnt);
+        const uint32_t ex_b = warp_excl_scan(my_bytes, lane);
+        if (lane == 31) { S.warp_bytes[warp] = ex_b + my_bytes; S.warp_cnt[warp] = __popc(ready_mask); }
+        __syncthreads();
+        uint32_t wb = 0, wc = 0, tb = 0, tc = 0;
+        #pragma unroll
+        for (int w = 0; w < D2_WARPS; ++w) { uint32_t b = S.warp_bytes[w], c = S.warp_cnt[w]; if (w < warp) { wb += b; wc += c; } tb += b; tc += c; }
+        S.excl_bytes[tid] = wb + ex_b;
+        S.excl_cnt[tid] = wc + __popc(ready_mask & ((1u << lane) - 1u));
+
+        // ---------------- decoupled look-back -------------------------------------------------------
+        if (warp == 0) {
+            const uint64_t agg = lb_pack(tb, tc);
+            uint64_t excl = 0;
+            if (tile == 0) {
+                if (lane == 0) st_volatile_u64(a.tile_state + 0, LB_INC | agg);
+            } else {
+                if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_AGG | agg);
+                long long look = (long long)tile - 1;
+                for (;;) {
+                    const long long idx = look - lane;
+                    uint64_t w = (idx >= 0) ? ld_volatile_u64(a.tile_state + idx) : LB_INC;
+                    while (__any_sync(0xffffffffu, (w & LB_STATUS) == 0)) { if ((w & LB_STATUS) == 0) w = ld_volatile_u64(a.tile_state + idx); }
+                    const uint32_t inc_mask = __ballot_sync(0xffffffffu, (w & LB_STATUS) == LB_INC);
+                    uint64_t v = lb_value(w);
+                    if (inc_mask) { const int first = __ffs(inc_mask) - 1; if (lane > first) v = 0; }
+                    #pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                    excl += v;
+                    if (inc_mask) break;
+                    look -= 32;
+                }
+                if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_INC | (excl + agg));
+            }
+            if (lane == 0) {
+                S.base = excl;
+                if (tile == a.n_tiles - 1) {
+                    const uint64_t tot = excl + agg;
+                    a.ctl->total = tot;
+                    a.out_off[(uint32_t)(tot & 0xFFFFFFu)] = tot >> 24;
+                }
+            }
+        }
+        __syncthreads();
+        const uint64_t base_bytes = S.base >> 24;
+        const uint32_t base_cnt = (uint32_t)(S.base & 0xFFFFFFu);
+        const bool fits = base_bytes + tb <= a.out_cap;
+        if (!fits && tid == 0) a.ctl->overflow = 1u;
+
+        // ---------------- phase B (thread per task) -------------------------------------------------
+        if (tid < (int)nt) {
+            const TaskRec rec = S.rec[tid];
+            if (rec.ready) {
+                const uint32_t slot = (uint32_t)((a.first_task + t0 + tid) & a.slot_mask);
+                const uint32_t j = base_cnt + S.excl_cnt[tid];
+                const uint64_t ob = base_bytes + S.excl_bytes[tid];
+                a.out_off[j] = ob; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
+                if (rec.has && fits) {
+                    const uint8_t* p = staged ? sbuf + M.soff[tid] : a.payload + M.goff[tid];
+                    uint8_t* o = a.out_payload + ob;
+                    if (rec.mode == OM_COPY) thread_copy(o, p + rec.src_off, rec.src_len);
+                    else if (rec.mode == OM_VADD) vadd_write(p, rec.src_off, rec.src_len, o);
+                    else if (rec.mode == OM_U32_DEC || rec.mode == OM_I64_DEC) {
+                        long long v = rec.value; uint32_t l = rec.out_len;
+                        if (v < 0) { *o++ = '-'; --l; v = -v; }
+                        write_dec(o, (unsigned long long)v, l);
+                    } else if (rec.mode == OM_STR_ESC) {                          // string the sequential parser sized (non-canonical frame)
+                        uint32_t i = rec.src_off + 1, end = rec.src_off + rec.src_len - 1;
+                        *o++ = '"';
+                        while (i < end) o += py_emit(next_cp(p, i, end), o);
+                        *o = '"';
+                    }
+                }
+            }
+        }
+        // ---------------- phase B, cooperative: transcode the escaped strings -----------------------
+        if (HANDLER == 0 && fits) {
+            const uint32_t ns = S.n_slow;
+            for (uint32_t s = warp; s < ns; s += D2_WARPS) {
+                const uint32_t k = S.slow_list[s];
+                const TaskRec rec = S.rec[k];
+                if (rec.mode != OM_STR_PAR || !rec.has) continue;
+                const uint8_t* p = staged ? sbuf + M.soff[k] : a.payload + M.goff[k];
+                esc_emit(p + rec.src_off, rec.src_len, lane, a.out_payload + base_bytes + S.excl_bytes[k]);
+            }
+        }
+        __syncthreads();            // stage buffer, records and metadata are free again
+        stage ^= 1u;
+    }
+}
+
+}  // namespace b9

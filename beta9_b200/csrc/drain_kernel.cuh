@@ -65,7 +65,8 @@ struct DrainArgs {
 };
 
 // what phase A leaves for phase B, per task of the tile
-enum OutMode : uint8_t { OM_NONE = 0, OM_COPY, OM_STR_ESC, OM_U32_DEC, OM_I64_DEC, OM_VADD };
+enum OutMode : uint8_t { OM_NONE = 0, OM_COPY, OM_STR_ESC /* one thread walks the token */, OM_U32_DEC, OM_I64_DEC, OM_VADD,
+                         OM_STR_PAR /* warp transcodes the framed body in 32 chunks (drain2) */ };
 struct TaskRec {
     uint32_t src_off;    // OM_COPY / OM_STR_ESC / OM_VADD: byte offset inside the payload
     uint32_t src_len;

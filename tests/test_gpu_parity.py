@@ -51,7 +51,7 @@ def assert_matches_oracle(batch, r, o, allow_unsupported=0):
 
 def test_golden_fixtures(dq):
     g = G.load()
-    for handler in ["identity"]:
+    for handler in HANDLERS:
         for name, cases in g["groups"].items():
             b = G.group_batch(cases)
             r = run_gpu(dq, b, handler)
@@ -91,16 +91,58 @@ def test_identity_on_other_configs(dq):
         assert_matches_oracle(b, r, o, allow_unsupported=b.n if b.name == "json_sum" else 0)
 
 
-def test_handcrafted_edge_cases(dq):
+@pytest.mark.parametrize("handler", HANDLERS)
+def test_handcrafted_edge_cases(dq, handler):
     from tests.test_oracle_c_vs_py import HANDCRAFTED
     b = synth.from_payloads(HANDCRAFTED)
-    r = run_gpu(dq, b, "identity")
-    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "identity")
+    r = run_gpu(dq, b, handler)
+    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, handler)
     assert_matches_oracle(b, r, o, allow_unsupported=len(HANDCRAFTED))
     # the device may decline (UNSUPPORTED) only valid payloads whose arg is a float / non-empty container
     for i in np.flatnonzero(r.status == 4):
         # ... or a number with an exponent, whose float64 overflow (-> Ok:false) the device does not decide
         assert o.status[i] in (0, 4) or (o.status[i] == 3 and b"e" in HANDCRAFTED[i].lower()), HANDCRAFTED[i]
+
+
+def test_crc32_zipf(dq):
+    b = synth.crc_batch(50_000)                   # BASELINE configs[2] at a size the oracle does in seconds
+    r = run_gpu(dq, b, "crc32")
+    assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "crc32", nthreads=16))
+    b = synth.strings_batch(20_000, 256, adversarial_frac=0.3, seed=5)     # non-ASCII / escapes under the CRC
+    r = run_gpu(dq, b, "crc32")
+    assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "crc32", nthreads=16))
+
+
+def test_vadd_f32(dq):
+    b = synth.vadd_batch(100_000)                 # BASELINE configs[3] payload shape
+    r = run_gpu(dq, b, "vadd_f32")
+    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "vadd_f32", nthreads=16)
+    assert_matches_oracle(b, r, o)
+    # float handler bodies within 1e-6 rel (north_star); here they are bit-equal, check the decoded values too
+    import base64
+    for i in (0, 1, b.n - 1):
+        got = np.frombuffer(base64.b64decode(r.result(i)[1:-1]), "<f4")
+        want = np.frombuffer(base64.b64decode(o.result(i)[1:-1]), "<f4")
+        assert np.allclose(got, want, rtol=1e-6, atol=0)
+    for fpv in (1, 3, 5, 7):                      # every base64 padding phase
+        b = synth.vadd_batch(500, floats_per_vec=fpv, seed=fpv)
+        r = run_gpu(dq, b, "vadd_f32")
+        assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "vadd_f32"))
+
+
+def test_json_sum(dq):
+    b = synth.json_batch(20_000)                  # BASELINE configs[4] payload shape
+    r = run_gpu(dq, b, "json_sum")
+    assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "json_sum", nthreads=16))
+
+
+def test_wrong_handler_for_payload(dq):
+    # every handler over every config's payloads: type errors must come out as ERROR exactly like the oracle
+    for b in (synth.strings_batch(2000, 64, adversarial_frac=0.2), synth.vadd_batch(1000), synth.json_batch(200)):
+        for h in HANDLERS:
+            r = run_gpu(dq, b, h)
+            o = coracle.run_batch(b.task_ids, b.payload, b.offsets, h)
+            assert_matches_oracle(b, r, o, allow_unsupported=b.n if (h == "identity" and b.name == "json_sum") else 0)
 
 
 def test_empty_and_ragged(dq):

@@ -210,8 +210,8 @@ def main():
     pin_ids.array[:] = batch.task_ids.reshape(-1); pin_pl.array[:] = batch.payload
     pin_off.view(np.uint64, n + 1)[:] = batch.offsets
     cap_bytes = out_bytes + 4096
-    o_ids = dq.pinned(n * 16); o_st = dq.pinned(n); o_has = dq.pinned(n); o_off = dq.pinned((n + 1) * 8); o_pl = dq.pinned(cap_bytes)
-    resbuf = L.Results(o_ids.ptr, o_st.ptr, o_has.ptr, o_off.ptr, o_pl.ptr, n, cap_bytes, 0, 0, 0, 0)
+    o_ids = dq.pinned(n * 16); o_st = dq.pinned(n); o_has = dq.pinned(n); o_off = dq.pinned(n * 8); o_len = dq.pinned(n * 4); o_pl = dq.pinned(cap_bytes)
+    resbuf = L.Results(o_ids.ptr, o_st.ptr, o_has.ptr, o_off.ptr, o_len.ptr, o_pl.ptr, n, cap_bytes, 0, 0, 0, 0)
     lib = L.load()
     hid = {"identity": 0, "crc32": 1, "vadd_f32": 2, "json_sum": 3}[args.handler]
 
@@ -238,7 +238,9 @@ def main():
     h2d = (s1.bytes_h2d - s0.bytes_h2d) // args.e2e_steps
     d2h = (s1.bytes_d2h - s0.bytes_d2h) // args.e2e_steps
     # the records that came back are the real ones
-    assert bytes(o_pl.array[:8]) == res.payload[:8].tobytes()
+    e_off = o_off.view(np.uint64, n); e_len = o_len.view(np.uint32, n)
+    for i in (0, n // 2, n - 1):
+        assert bytes(o_pl.array[int(e_off[i]):int(e_off[i]) + int(e_len[i])]) == res.result(i)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
@@ -252,7 +254,7 @@ def main():
             dt = time.perf_counter() - c0
             best = dt if best is None else min(best, dt)
         # while we are here: the device answers are the oracle's answers
-        assert np.array_equal(o.payload, res.payload) and np.array_equal(o.status, res.status)
+        assert np.array_equal(o.payload, res.fifo_payload()) and np.array_equal(o.status, res.status)
         cpu = {"value": n / best, "unit": "tasks/s", "cores": cores, "kind": "port",
                "sample": f"all {n} tasks of the step, best of 3 passes, {cores} threads (oracle/c/b9_oracle.c)"}
 
@@ -282,7 +284,7 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    for p in (pin_ids, pin_pl, pin_off, o_ids, o_st, o_has, o_off, o_pl):
+    for p in (pin_ids, pin_pl, pin_off, o_ids, o_st, o_has, o_off, o_len, o_pl):
         p.free()
     dq.close()
     if dist is not None:

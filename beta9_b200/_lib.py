@@ -27,7 +27,7 @@ class PushMeta(C.Structure):
 
 class Results(C.Structure):
     _fields_ = [("task_ids", C.c_void_p), ("status", C.c_void_p), ("has_result", C.c_void_p),
-                ("offsets", C.c_void_p), ("payload", C.c_void_p), ("cap_tasks", C.c_uint32),
+                ("offsets", C.c_void_p), ("lengths", C.c_void_p), ("payload", C.c_void_p), ("cap_tasks", C.c_uint32),
                 ("cap_bytes", C.c_uint64), ("n_results", C.c_uint32), ("n_popped", C.c_uint32),
                 ("n_bytes", C.c_uint64), ("need_bytes", C.c_uint64)]
 

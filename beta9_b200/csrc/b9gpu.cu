@@ -80,7 +80,8 @@ struct b9_ctx {
     // ---- drain staging (device)
     uint32_t max_drain_tasks = 0; uint64_t max_result_bytes = 0;
     uint8_t* d_out_payload = nullptr; uint64_t* d_out_off = nullptr; uint4* d_out_ids = nullptr;
-    uint8_t* d_out_status = nullptr; uint8_t* d_out_has = nullptr;
+    uint8_t* d_out_status = nullptr; uint8_t* d_out_has = nullptr; uint32_t* d_out_len = nullptr;
+    uint64_t cancelled_pending = 0;            // pending tasks carrying B9_TF_CANCELLED (pushed so, or expired)
     DrainCtl* d_ctl = nullptr; uint64_t* d_tile_state = nullptr;
     DrainCtl* h_ctl = nullptr;                 // pinned
     unsigned long long* d_count = nullptr; unsigned long long* h_count = nullptr;
@@ -214,6 +215,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     CUC(cudaMalloc(&c->d_out_ids, (size_t)md * sizeof(uint4)));
     CUC(cudaMalloc(&c->d_out_status, md));
     CUC(cudaMalloc(&c->d_out_has, md));
+    CUC(cudaMalloc(&c->d_out_len, (size_t)md * sizeof(uint32_t)));
     CUC(cudaMalloc(&c->d_ctl, sizeof(DrainCtl)));
     CUC(cudaMalloc(&c->d_tile_state, ((size_t)md / D2_THREADS + 2) * sizeof(uint64_t)));
     CUC(cudaMalloc(&c->d_count, sizeof(unsigned long long)));
@@ -237,7 +239,7 @@ void b9_ctx_destroy(b9_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_payload); cudaFree(c->d_off); cudaFree(c->d_hdr); cudaFree(c->d_ids); cudaFree(c->d_ts); cudaFree(c->d_exp);
     cudaFree(c->d_in_off); cudaFree(c->d_in_ts); cudaFree(c->d_in_exp); cudaFree(c->d_in_retries); cudaFree(c->d_in_flags);
-    cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has);
+    cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len);
     cudaFree(c->d_ctl); cudaFree(c->d_tile_state); cudaFree(c->d_count);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_count) cudaFreeHost(c->h_count);
@@ -276,6 +278,8 @@ int b9_batch_push(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, co
                         (unsigned long long)(offsets[i + 1] - offsets[i]), c->max_task_bytes);
     }
     const uint64_t bytes = offsets[n] - offsets[0];
+    uint64_t n_cancelled = 0;
+    if (meta && meta->flags) for (uint32_t i = 0; i < n; ++i) n_cancelled += (meta->flags[i] & B9_TF_CANCELLED) ? 1 : 0;
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     free_segments(c);
@@ -314,6 +318,7 @@ int b9_batch_push(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, co
     c->write_pos = start + ((bytes + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
     c->tail_task += n;
     c->pending_bytes += bytes;
+    c->cancelled_pending += n_cancelled;
     c->stats.tasks_pushed += n;
     c->stats.bytes_h2d += bytes + ((uint64_t)n + 1) * 8 + (uint64_t)n * 16 + meta_bytes;
     return B9_OK;
@@ -343,6 +348,7 @@ int64_t b9_expire(b9_ctx* c, int64_t now_unix_ns) {
     c->stats.kernel_launches++;
     CU(cudaMemcpyAsync(c->h_count, c->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->cancelled_pending += *c->h_count;
     return (int64_t)*c->h_count;
 }
 
@@ -371,7 +377,8 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     a.payload = c->d_payload; a.off = c->d_off; a.hdr = c->d_hdr; a.ids = c->d_ids; a.slot_mask = c->slot_mask;
     a.first_task = c->head_task; a.n_tasks = n; a.n_tiles = (n + TILE_TASKS - 1) / TILE_TASKS;
     a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_ids = c->d_out_ids;
-    a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.handler = handler;
+    a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.handler = handler;
+    a.count_mode = c->cancelled_pending ? 1u : 0u;
     cudaStream_t s = c->stream;
     const bool v2 = c->drain_version == 2;
     if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;
@@ -409,8 +416,8 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     if (c->h_ctl->overflow)
         return fail(B9_ENOSPC, "b9_drain_launch: results exceed max_result_bytes (%llu); drain fewer tasks or enlarge the staging",
                     (unsigned long long)c->max_result_bytes);
-    c->res_bytes = c->h_ctl->total >> 24;
-    c->res_n = (uint32_t)(c->h_ctl->total & 0xFFFFFFu);
+    if (v2) { c->res_bytes = c->h_ctl->bytes; c->res_n = c->h_ctl->total_cnt; }
+    else { c->res_bytes = c->h_ctl->total >> 24; c->res_n = (uint32_t)(c->h_ctl->total & 0xFFFFFFu); }
     c->res_popped = n;
     c->res_in_bytes = in_bytes;
     c->have_results = true;
@@ -432,22 +439,24 @@ int64_t b9_drain_fetch(b9_ctx* c, b9_results* out) {
     const size_t n = c->res_n;
     CU(cudaEventRecord(c->ev_c, s));
     if (n) {
-        if (!out->task_ids || !out->status || !out->has_result || !out->offsets) return fail(B9_EINVAL, "b9_drain_fetch: NULL result array");
+        if (!out->task_ids || !out->status || !out->has_result || !out->offsets || !out->lengths) return fail(B9_EINVAL, "b9_drain_fetch: NULL result array");
+        CU(cudaMemcpyAsync(out->lengths, c->d_out_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(out->task_ids, c->d_out_ids, n * 16, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(out->status, c->d_out_status, n, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(out->has_result, c->d_out_has, n, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(out->offsets, c->d_out_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(out->offsets, c->d_out_off, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         if (c->res_bytes) {
             if (!out->payload) return fail(B9_EINVAL, "b9_drain_fetch: NULL payload buffer");
             CU(cudaMemcpyAsync(out->payload, c->d_out_payload, c->res_bytes, cudaMemcpyDeviceToHost, s));
         }
-    } else if (out->offsets) out->offsets[0] = 0;
+    }
     CU(cudaEventRecord(c->ev_d, s));
     CU(cudaStreamSynchronize(s));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev_c, c->ev_d); c->stats.last_drain_d2h_ms = ms;
-    c->stats.bytes_d2h += c->res_bytes + n * (16 + 1 + 1 + 8) + 8;
+    c->stats.bytes_d2h += c->res_bytes + n * (16 + 1 + 1 + 8 + 4);
     if (!c->res_peek) {
         c->head_task += c->res_popped; c->pending_bytes -= c->res_in_bytes; c->stats.tasks_drained += c->res_popped;
+        c->cancelled_pending -= std::min<uint64_t>(c->cancelled_pending, (uint64_t)(c->res_popped - c->res_n));
         free_segments(c);
     }
     c->have_results = false;

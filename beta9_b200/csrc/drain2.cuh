@@ -1,7 +1,15 @@
 // drain kernel v2 — the production drain.
 //
-// Same contract as v1 (drain_kernel.cuh: persistent CTAs, ticket work stealing, ballot compaction,
-// decoupled look-back, FIFO-dense results) with the data path rebuilt around the B200 memory system:
+// Persistent CTAs, ticket work stealing and ballot compaction as in v1 (drain_kernel.cuh), with the
+// data path rebuilt around the B200 memory system and the inter-CTA ordering chain removed:
+//
+//   * result RECORDS (id, status, has, offset, length) are FIFO-dense: record j belongs to the j-th
+//     ready task. When no pending task is cancelled (the host knows) j is plain arithmetic on the
+//     ticket; otherwise the per-tile ready counts — known from the slot words alone, long before
+//     the tile is processed — go through a decoupled look-back;
+//   * result BYTES are placed by ONE atomicAdd per tile on a byte cursor: dense, but in completion
+//     order. (v1 chained the byte prefix through an in-order look-back; ncu showed the whole grid
+//     falling into lockstep behind it, 32 tiles resolved per L2 round trip — profiles/r1_v2a_*.)
 //
 //   * a tile's payload bytes are ONE contiguous range of the ring in the common case; warp 0 pulls
 //     it into shared memory with a single bulk async copy (cp.async.bulk / TMA 1-D, completion on
@@ -56,6 +64,8 @@ struct D2Meta {
     unsigned long long tile;
     uint32_t nt;
     uint32_t staged;               // 1: payload bytes are (arriving) in shared memory; 0: read from global
+    uint32_t base_cnt;             // records of all earlier tiles (index of this tile's first record)
+    uint32_t ready_cnt;            // ready tasks in this tile
 };
 
 // ------------------------------------------------------------------ SWAR classification
@@ -301,11 +311,10 @@ __device__ inline void esc_emit(const uint8_t* __restrict__ body, uint32_t n, in
 struct D2Shared {
     D2Meta meta[D2_STAGES];
     TaskRec rec[D2_THREADS];
-    uint32_t excl_bytes[D2_THREADS], excl_cnt[D2_THREADS];
+    uint32_t excl_bytes[D2_THREADS];
     uint32_t warp_bytes[D2_WARPS], warp_cnt[D2_WARPS];
     uint32_t slow_list[D2_THREADS]; uint32_t n_slow;
-    uint64_t base;
-    unsigned long long next_tile;
+    unsigned long long base;
     uint32_t crc_table[256];
     alignas(8) uint64_t mbar[D2_STAGES];
 };
@@ -383,7 +392,37 @@ __device__ inline void d2_stage_tile(const DrainArgs& a, unsigned long long tile
             if (valid[1]) { m.soff[lane + 32] = ex1 + (uint32_t)(off[1] & 15ull); if (asz[1]) bulk_g2s(buf + ex1, a.payload + (off[1] & ~15ull), asz[1], bar); }
         }
     }
-    if (lane == 0) { m.tile = tile; m.nt = nt; m.staged = staged; }
+    // ---- record indices: ready counts are known from the slot words alone
+    const uint32_t rc = __popc(__ballot_sync(0xffffffffu, valid[0] && !(hdr_flags(r.hdr[0]) & 1u)))
+                      + __popc(__ballot_sync(0xffffffffu, valid[1] && !(hdr_flags(r.hdr[1]) & 1u)));
+    uint32_t base_cnt = t0;                                   // nothing cancelled anywhere: pure arithmetic
+    if (a.count_mode) {                                       // some pending task is cancelled: chain the counts
+        uint64_t excl = 0;
+        if (tile == 0) { if (lane == 0) st_volatile_u64(a.tile_state + 0, LB_INC | rc); }
+        else {
+            if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_AGG | rc);
+            long long look = (long long)tile - 1;
+            for (;;) {
+                const long long idx = look - lane;
+                uint64_t w = (idx >= 0) ? ld_volatile_u64(a.tile_state + idx) : LB_INC;
+                while (__any_sync(0xffffffffu, (w & LB_STATUS) == 0)) { if ((w & LB_STATUS) == 0) w = ld_volatile_u64(a.tile_state + idx); }
+                const uint32_t inc_mask = __ballot_sync(0xffffffffu, (w & LB_STATUS) == LB_INC);
+                uint64_t v = lb_value(w);
+                if (inc_mask) { const int first = __ffs(inc_mask) - 1; if (lane > first) v = 0; }
+                #pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_INC | (excl + rc));
+        }
+        base_cnt = (uint32_t)excl;
+    }
+    if (lane == 0) {
+        m.tile = tile; m.nt = nt; m.staged = staged; m.base_cnt = base_cnt; m.ready_cnt = rc;
+        if (tile == a.n_tiles - 1) a.ctl->total_cnt = base_cnt + rc;
+    }
 }
 
 template <int HANDLER>
@@ -401,7 +440,8 @@ __global__ void __launch_bounds__(D2_THREADS, 4) drain2_kernel(DrainArgs a, uint
     uint32_t stage = 0, parity_bits = 0;   // bit s: phase parity of stage s's mbarrier
     // warp 0 runs a three-deep software pipeline so that no global latency sits between two
     // block barriers: ticket(i+3) is being claimed while the slot words of tile i+2 are in flight
-    // and the payload bytes of tile i+1 stream into the other stage.
+    // and the payload bytes of tile i+1 stream into the other stage. Holding tickets ahead is
+    // harmless now that no CTA waits on another CTA's unprocessed tile.
     unsigned long long t_meta = ~0ull;     // tile whose slot words are in `mregs`
     unsigned long long t_raw = ~0ull;      // lane 0: ticket claimed for the tile after t_meta
     D2MetaRegs mregs; mregs.off[0] = mregs.off[1] = mregs.hdr[0] = mregs.hdr[1] = 0;
@@ -487,55 +527,23 @@ __global__ void __launch_bounds__(D2_THREADS, 4) drain2_kernel(DrainArgs a, uint
             __syncthreads();
         }
 
-        // ---------------- compaction + sizes --------------------------------------------------------
+        // ---------------- compaction (ballot) + sizes (scan) + one cursor add per tile ---------------
         uint32_t my_bytes = 0, my_cnt = 0;
         if (tid < (int)nt) { my_bytes = S.rec[tid].out_len; my_cnt = S.rec[tid].ready ? 1u : 0u; }
         const uint32_t ready_mask = __ballot_sync(0xffffffffu, my_cnt);
         const uint32_t ex_b = warp_excl_scan(my_bytes, lane);
         if (lane == 31) { S.warp_bytes[warp] = ex_b + my_bytes; S.warp_cnt[warp] = __popc(ready_mask); }
         __syncthreads();
-        uint32_t wb = 0, wc = 0, tb = 0, tc = 0;
+        uint32_t wb = 0, wc = 0, tb = 0;
         #pragma unroll
-        for (int w = 0; w < D2_WARPS; ++w) { uint32_t b = S.warp_bytes[w], c = S.warp_cnt[w]; if (w < warp) { wb += b; wc += c; } tb += b; tc += c; }
-        S.excl_bytes[tid] = wb + ex_b;
-        S.excl_cnt[tid] = wc + __popc(ready_mask & ((1u << lane) - 1u));
-
-        // ---------------- decoupled look-back -------------------------------------------------------
-        if (warp == 0) {
-            const uint64_t agg = lb_pack(tb, tc);
-            uint64_t excl = 0;
-            if (tile == 0) {
-                if (lane == 0) st_volatile_u64(a.tile_state + 0, LB_INC | agg);
-            } else {
-                if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_AGG | agg);
-                long long look = (long long)tile - 1;
-                for (;;) {
-                    const long long idx = look - lane;
-                    uint64_t w = (idx >= 0) ? ld_volatile_u64(a.tile_state + idx) : LB_INC;
-                    while (__any_sync(0xffffffffu, (w & LB_STATUS) == 0)) { if ((w & LB_STATUS) == 0) w = ld_volatile_u64(a.tile_state + idx); }
-                    const uint32_t inc_mask = __ballot_sync(0xffffffffu, (w & LB_STATUS) == LB_INC);
-                    uint64_t v = lb_value(w);
-                    if (inc_mask) { const int first = __ffs(inc_mask) - 1; if (lane > first) v = 0; }
-                    #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    excl += v;
-                    if (inc_mask) break;
-                    look -= 32;
-                }
-                if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_INC | (excl + agg));
-            }
-            if (lane == 0) {
-                S.base = excl;
-                if (tile == a.n_tiles - 1) {
-                    const uint64_t tot = excl + agg;
-                    a.ctl->total = tot;
-                    a.out_off[(uint32_t)(tot & 0xFFFFFFu)] = tot >> 24;
-                }
-            }
-        }
+        for (int w = 0; w < D2_WARPS; ++w) { uint32_t b = S.warp_bytes[w], c = S.warp_cnt[w]; if (w < warp) { wb += b; wc += c; } tb += b; }
+        const uint32_t my_excl_bytes = wb + ex_b;
+        const uint32_t my_excl_cnt = wc + __popc(ready_mask & ((1u << lane) - 1u));
+        S.excl_bytes[tid] = my_excl_bytes;                    // the cooperative pass needs other tasks' offsets
+        if (tid == 0) S.base = tb ? atomicAdd(&a.ctl->bytes, (unsigned long long)tb) : 0ull;
         __syncthreads();
-        const uint64_t base_bytes = S.base >> 24;
-        const uint32_t base_cnt = (uint32_t)(S.base & 0xFFFFFFu);
+        const uint64_t base_bytes = S.base;
+        const uint32_t base_cnt = M.base_cnt;
         const bool fits = base_bytes + tb <= a.out_cap;
         if (!fits && tid == 0) a.ctl->overflow = 1u;
 
@@ -544,9 +552,9 @@ __global__ void __launch_bounds__(D2_THREADS, 4) drain2_kernel(DrainArgs a, uint
             const TaskRec rec = S.rec[tid];
             if (rec.ready) {
                 const uint32_t slot = (uint32_t)((a.first_task + t0 + tid) & a.slot_mask);
-                const uint32_t j = base_cnt + S.excl_cnt[tid];
-                const uint64_t ob = base_bytes + S.excl_bytes[tid];
-                a.out_off[j] = ob; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
+                const uint32_t j = base_cnt + my_excl_cnt;
+                const uint64_t ob = base_bytes + my_excl_bytes;
+                a.out_off[j] = ob; a.out_len[j] = rec.out_len; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
                 if (rec.has && fits) {
                     const uint8_t* p = staged ? sbuf + M.soff[tid] : a.payload + M.goff[tid];
                     uint8_t* o = a.out_payload + ob;

@@ -37,9 +37,10 @@ __device__ __forceinline__ uint64_t lb_value(uint64_t w) { return w & ~LB_STATUS
 
 struct DrainCtl {
     unsigned long long ticket;      // next tile to hand out
-    unsigned long long total;       // lb_pack(result bytes, result count) of the whole window
+    unsigned long long total;       // v1: lb_pack(result bytes, result count) of the whole window
+    unsigned long long bytes;       // v2: result-byte cursor (one atomicAdd per tile); final value = total bytes
     unsigned int overflow;          // result staging too small
-    unsigned int pad;
+    unsigned int total_cnt;         // v2: result records of the whole window
 };
 
 struct DrainArgs {
@@ -54,7 +55,8 @@ struct DrainArgs {
     uint32_t n_tiles;
     // outputs
     uint8_t*  out_payload; uint64_t out_cap;
-    uint64_t* out_off;              // [n_tasks + 1]
+    uint64_t* out_off;              // [n_tasks + 1]  start of each record's bytes
+    uint32_t* out_len;              // [n_tasks]      length of each record's bytes
     uint4*    out_ids;              // [n_tasks]
     uint8_t*  out_status;           // [n_tasks]
     uint8_t*  out_has;              // [n_tasks]
@@ -62,6 +64,7 @@ struct DrainArgs {
     DrainCtl* ctl;
     uint64_t* tile_state;           // [n_tiles], zeroed before launch
     int handler;
+    uint32_t count_mode;            // v2: 0 = no pending task is cancelled (record index = task index), 1 = chain the ready counts
 };
 
 // what phase A leaves for phase B, per task of the tile
@@ -190,7 +193,13 @@ __device__ inline void handler_phase_a(int handler, const uint8_t* __restrict__ 
     case 2: {   // vadd_f32: base64 -> fp32 a||b -> a+b -> base64
         if (pr.a0_kind != AK_STR) { rec.status = 1; return; }               // TypeError
         if (pr.a0_flags & SF_NONPRINT) { rec.status = 1; return; }          // non-ASCII / DEL: ValueError / binascii.Error
-        if (pr.a0_flags & SF_ESC) { rec.status = ST_UNSUPPORTED; return; }  // escaped base64 text: not produced by the SDK
+        if (pr.a0_flags & SF_ESC) {
+            // escaped text: any decoded character outside the base64 alphabet is an error for sure;
+            // a fully valid escaped base64 string (only "\/" can do that) is not produced by the SDK
+            uint32_t i = pr.a0_off + 1, end = pr.a0_off + pr.a0_len - 1;
+            while (i < end) { uint32_t cp = next_cp(p, i, end); if (cp >= 0x80 || (b64_val((uint8_t)cp) < 0 && cp != '=')) { rec.status = 1; return; } }
+            rec.status = ST_UNSUPPORTED; return;
+        }
         int64_t rn = b64_decoded_len(p, pr.a0_off + 1, pr.a0_off + pr.a0_len - 1);
         if (rn < 0 || (rn % 8)) { rec.status = 1; return; }
         uint32_t n = (uint32_t)(rn / 8);
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(DRAIN_THREADS, 2) drain_kernel(DrainArgs a) {
                 const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
                 const uint32_t j = base_cnt + s_excl_cnt[k];
                 const uint64_t ob = base_bytes + s_excl_bytes[k];
-                a.out_off[j] = ob; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
+                a.out_off[j] = ob; a.out_len[j] = rec.out_len; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
                 if (!rec.has || !fits) continue;
                 uint8_t* o = a.out_payload + ob;
                 if (rec.mode == OM_VADD) vadd_write(a.payload + __ldg(a.off + slot), rec.src_off, rec.src_len, o);
@@ -369,6 +378,7 @@ __global__ void __launch_bounds__(DRAIN_THREADS, 2) drain_kernel(DrainArgs a) {
             const uint64_t ob = base_bytes + s_excl_bytes[k];
             if (lane == 0) {
                 a.out_off[j] = ob;
+                a.out_len[j] = rec.out_len;
                 a.out_ids[j] = __ldg(a.ids + slot);
                 a.out_status[j] = rec.status;
                 a.out_has[j] = rec.has;

@@ -27,6 +27,7 @@ constexpr uint32_t SF_ESC      = 1u << 0;  // string contains a backslash escape
 constexpr uint32_t SF_NONPRINT = 1u << 1;  // string contains a byte >= 0x7F
 constexpr uint32_t SF_NUM_EXP  = 1u << 2;  // a number with exponent or > 300 digits (may overflow float64)
 constexpr uint32_t SF_DEEP     = 1u << 3;  // nesting deeper than the device stack
+constexpr uint32_t SF_F64_OVER = 1u << 4;  // a number literal that strconv.ParseFloat rejects with ErrRange
 
 constexpr int ST_OK = 0, ST_REJECTED = 3, ST_UNSUPPORTED = 4;
 
@@ -103,6 +104,56 @@ __device__ inline int64_t scan_number(const uint8_t* __restrict__ p, uint32_t i,
     return i;
 }
 
+
+// ---- does a number literal overflow float64 (strconv.ParseFloat ErrRange -> Unmarshal error)? ----
+// 2^1024 - 2^970, the smallest decimal that rounds (half-even) to +Inf: 309 digits.
+__device__ __constant__ char F64_OVERFLOW_THRESHOLD[310] = {'1','7','9','7','6','9','3','1','3','4','8','6','2','3','1','5','8','0','7','9','3','7','2','8','9','7','1','4','0','5','3','0','3','4','1','5','0','7','9','9','3','4','1','3','2','7','1','0','0','3','7','8','2','6','9','3','6','1','7','3','7','7','8','9','8','0','4','4','4','9','6','8','2','9','2','7','6','4','7','5','0','9','4','6','6','4','9','0','1','7','9','7','7','5','8','7','2','0','7','0','9','6','3','3','0','2','8','6','4','1','6','6','9','2','8','8','7','9','1','0','9','4','6','5','5','5','5','4','7','8','5','1','9','4','0','4','0','2','6','3','0','6','5','7','4','8','8','6','7','1','5','0','5','8','2','0','6','8','1','9','0','8','9','0','2','0','0','0','7','0','8','3','8','3','6','7','6','2','7','3','8','5','4','8','4','5','8','1','7','7','1','1','5','3','1','7','6','4','4','7','5','7','3','0','2','7','0','0','6','9','8','5','5','5','7','1','3','6','6','9','5','9','6','2','2','8','4','2','9','1','4','8','1','9','8','6','0','8','3','4','9','3','6','4','7','5','2','9','2','7','1','9','0','7','4','1','6','8','4','4','4','3','6','5','5','1','0','7','0','4','3','4','2','7','1','1','5','5','9','6','9','9','5','0','8','0','9','3','0','4','2','8','8','0','1','7','7','9','0','4','1','7','4','4','9','7','7','9','2', 0};
+
+// p[s..e) is a syntactically valid JSON number. Exact: compares the literal's significant digits
+// against the threshold above when its magnitude is 10^308..10^309, otherwise decides by magnitude.
+__device__ inline bool number_overflows_f64(const uint8_t* __restrict__ p, uint32_t s, uint32_t e) {
+    uint32_t i = s;
+    if (p[i] == '-') ++i;
+    // significant digits = integer digits then fraction digits, leading zeros stripped
+    uint32_t int_s = i;
+    while (i < e && is_digit(p[i])) ++i;
+    uint32_t int_e = i, frac_s = i, frac_e = i;
+    if (i < e && p[i] == '.') { ++i; frac_s = i; while (i < e && is_digit(p[i])) ++i; frac_e = i; }
+    long long ex = 0;
+    if (i < e && (p[i] == 'e' || p[i] == 'E')) {
+        ++i; bool neg = false;
+        if (p[i] == '+') ++i; else if (p[i] == '-') { neg = true; ++i; }
+        while (i < e) { if (ex < 100000000) ex = ex * 10 + (p[i] - '0'); ++i; }
+        if (neg) ex = -ex;
+    }
+    // position of the first non-zero digit
+    long long mag;                   // value = 0.d1d2.. x 10^mag
+    uint32_t k = int_s;
+    while (k < int_e && p[k] == '0') ++k;
+    uint32_t first_in_frac = 0; bool in_frac = false;
+    if (k < int_e) mag = (long long)(int_e - k) + ex;
+    else {
+        uint32_t z = frac_s;
+        while (z < frac_e && p[z] == '0') ++z;
+        if (z >= frac_e) return false;                     // the value is zero
+        mag = -(long long)(z - frac_s) + ex;
+        in_frac = true; first_in_frac = z;
+    }
+    if (mag <= 308) return false;
+    if (mag >= 310) return true;
+    // mag == 309: digit-wise compare against the 309-digit threshold (missing digits are zeros)
+    uint32_t a = in_frac ? first_in_frac : k;              // walks the literal's digits, skipping '.'
+    bool in_int = !in_frac;
+    for (uint32_t t = 0; t < 309; ++t) {
+        char d = '0';
+        if (in_int) { if (a < int_e) d = (char)p[a++]; else { in_int = false; a = frac_s; if (a < frac_e) d = (char)p[a++]; } }
+        else if (a < frac_e) d = (char)p[a++];
+        char th = F64_OVERFLOW_THRESHOLD[t];
+        if (d != th) return d > th;
+    }
+    return true;                                           // >= threshold in the first 309 digits
+}
+
 __device__ inline int64_t scan_literal(const uint8_t* __restrict__ p, uint32_t i, uint32_t n) {
     uint8_t c = p[i];
     if (c == 't') { if (i + 4 <= n && p[i + 1] == 'r' && p[i + 2] == 'u' && p[i + 3] == 'e') return i + 4; return -1; }
@@ -138,7 +189,10 @@ __device__ inline int64_t skip_value(const uint8_t* __restrict__ p, uint32_t i, 
         } else if (c == '"') {
             int64_t e = scan_string(p, i, n, flags); if (e < 0) return -1; i = (uint32_t)e;
         } else if (c == '-' || is_digit(c)) {
-            int64_t e = scan_number(p, i, n, flags, nullptr); if (e < 0) return -1; i = (uint32_t)e;
+            uint32_t nf = 0;
+            int64_t e = scan_number(p, i, n, nf, nullptr); if (e < 0) return -1;
+            if ((nf & SF_NUM_EXP) && number_overflows_f64(p, i, (uint32_t)e)) nf |= SF_F64_OVER;
+            flags |= nf; i = (uint32_t)e;
         } else {
             int64_t e = scan_literal(p, i, n); if (e < 0) return -1; i = (uint32_t)e;
         }
@@ -294,9 +348,11 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
                     if (i >= n) B9_REJECT();
                     uint32_t es = i, ef = 0; uint8_t c = p[i]; bool simple = false;
                     int64_t ee;
-                    if (c == '-' || is_digit(c)) ee = scan_number(p, i, n, ef, &simple);
-                    else ee = skip_value(p, i, n, ef);
-                    sub_flags |= ef & (SF_NUM_EXP | SF_DEEP);
+                    if (c == '-' || is_digit(c)) {
+                        ee = scan_number(p, i, n, ef, &simple);
+                        if (ee >= 0 && (ef & SF_NUM_EXP) && number_overflows_f64(p, i, (uint32_t)ee)) ef |= SF_F64_OVER;
+                    } else ee = skip_value(p, i, n, ef);
+                    sub_flags |= ef & (SF_F64_OVER | SF_DEEP);
                     if (ee < 0) B9_REJECT();
                     i = (uint32_t)ee;
                     if (cnt == 0) {
@@ -326,7 +382,7 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
             if (p[i] == '{') {
                 uint32_t vs = i, ef = 0;
                 int64_t ee = skip_value(p, i, n, ef);
-                sub_flags |= ef & (SF_NUM_EXP | SF_DEEP);
+                sub_flags |= ef & (SF_F64_OVER | SF_DEEP);
                 if (ee < 0) B9_REJECT();
                 i = (uint32_t)ee;
                 if (!only_ws(p, vs + 1, i - 1)) r.kwargs_nonempty = 1;   // a non-nil map is merged into
@@ -349,7 +405,7 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
     while (i < n && is_ws(p[i])) ++i;
     if (i != n) B9_REJECT();
 #undef B9_REJECT
-    if (sub_flags & SF_NUM_EXP) r.status = ST_UNSUPPORTED;   // might be a float64 overflow -> Ok:false; not decided here
+    if (sub_flags & SF_F64_OVER) r.status = ST_REJECTED;     // "number out of range": Unmarshal error -> Ok:false
     return r;
 }
 

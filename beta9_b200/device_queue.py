@@ -25,8 +25,9 @@ class DrainResult:
     task_ids: np.ndarray     # uint8 [n,16]
     status: np.ndarray       # uint8 [n]
     has_result: np.ndarray   # uint8 [n]
-    offsets: np.ndarray      # uint64 [n+1]
-    payload: np.ndarray      # uint8 [n_bytes]
+    offsets: np.ndarray      # uint64 [n]   start of record i's bytes in `payload`
+    lengths: np.ndarray      # uint32 [n]
+    payload: np.ndarray      # uint8 [n_bytes]  dense; byte order = tile completion order, use offsets
     n_popped: int
 
     @property
@@ -36,7 +37,19 @@ class DrainResult:
     def result(self, i: int) -> Optional[bytes]:
         if not self.has_result[i]:
             return None
-        return self.payload[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes()
+        o = int(self.offsets[i])
+        return self.payload[o:o + int(self.lengths[i])].tobytes()
+
+    def fifo_payload(self) -> np.ndarray:
+        """The result bytes re-laid in record order (what `offsets[n+1]`-style consumers expect)."""
+        if self.n == 0:
+            return np.empty(0, np.uint8)
+        ln = self.lengths.astype(np.int64)
+        ends = np.cumsum(ln)
+        idx = np.arange(int(ends[-1]), dtype=np.int64)
+        rec = np.repeat(np.arange(self.n, dtype=np.int64), ln)
+        src = self.offsets.astype(np.int64)[rec] + (idx - (ends - ln)[rec])
+        return self.payload[src]
 
     def records(self) -> List[Tuple[bytes, str, Optional[bytes]]]:
         return [(self.task_ids[i].tobytes(), STATUS_NAMES[int(self.status[i])], self.result(i)) for i in range(self.n)]
@@ -143,16 +156,17 @@ class DeviceQueue:
         if cap_bytes is None:
             cap_bytes = int(st.last_drain_out_bytes)
         if n is None:
-            n = int(st.last_drain_tiles) * 128
+            n = int(st.last_drain_tiles) * 128      # an upper bound for either kernel generation
         ids = np.empty((max(n, 1), 16), np.uint8)
         status = np.empty(max(n, 1), np.uint8)
         has = np.empty(max(n, 1), np.uint8)
-        off = np.zeros(max(n, 1) + 1, np.uint64)
+        off = np.zeros(max(n, 1), np.uint64)
+        ln = np.zeros(max(n, 1), np.uint32)
         pl = np.empty(max(cap_bytes, 1), np.uint8)
-        r = L.Results(ids.ctypes.data, status.ctypes.data, has.ctypes.data, off.ctypes.data, pl.ctypes.data,
+        r = L.Results(ids.ctypes.data, status.ctypes.data, has.ctypes.data, off.ctypes.data, ln.ctypes.data, pl.ctypes.data,
                       max(n, 1), max(cap_bytes, 1), 0, 0, 0, 0)
         got = self._check(self._lib.b9_drain_fetch(self._ctx, C.byref(r)))
-        return DrainResult(ids[:got], status[:got], has[:got], off[:got + 1], pl[:int(r.n_bytes)], int(r.n_popped))
+        return DrainResult(ids[:got], status[:got], has[:got], off[:got], ln[:got], pl[:int(r.n_bytes)], int(r.n_popped))
 
     def drain_into(self, handler: str, max_tasks: int, res: "L.Results") -> int:
         """b9_drain straight into caller-owned (ideally pinned) buffers described by `res`."""

@@ -102,15 +102,18 @@ typedef struct b9_results {
     uint8_t  *status;       /* [cap_tasks]    enum b9_status                                     */
     uint8_t  *has_result;   /* [cap_tasks]    0: runner sends no result bytes (falsy result or
                                               error, runner/taskqueue.py:378), 1: bytes present  */
-    uint64_t *offsets;      /* [cap_tasks+1]  result i = payload[offsets[i] .. offsets[i+1])     */
+    uint64_t *offsets;      /* [cap_tasks]    result i = payload[offsets[i] .. offsets[i]+lengths[i]) */
+    uint32_t *lengths;      /* [cap_tasks]                                                       */
     uint8_t  *payload;      /* [cap_bytes]    TaskQueueCompleteRequest.result bytes
-                                              (taskqueue.proto:47-56), FIFO order                */
+                                              (taskqueue.proto:47-56). Dense (n_bytes in total),
+                                              records are FIFO-ordered but their bytes are laid out
+                                              in tile-completion order: always go through offsets */
     uint32_t  cap_tasks;
     uint64_t  cap_bytes;
     /* filled by the library */
     uint32_t  n_results;    /* records written                                                   */
     uint32_t  n_popped;     /* tasks removed from the queue (n_results + compacted-away ones)    */
-    uint64_t  n_bytes;      /* offsets[n_results]                                                */
+    uint64_t  n_bytes;      /* total result bytes written to payload                             */
     uint64_t  need_bytes;   /* on B9_ENOSPC: payload capacity that would have sufficed           */
 } b9_results;
 

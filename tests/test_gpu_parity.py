@@ -39,11 +39,13 @@ def assert_matches_oracle(batch, r, o, allow_unsupported=0):
     ok = ~unsup & (o.status != 4)
     assert np.array_equal(r.status[ok], o.status[ok]), np.flatnonzero(ok & (r.status != o.status))[:10]
     assert np.array_equal(r.has_result[ok], o.has[ok])
-    rl = np.diff(r.offsets).astype(np.int64)
+    rl = r.lengths.astype(np.int64)
     ol = np.diff(o.offsets).astype(np.int64)
     assert np.array_equal(rl[ok], ol[ok]), np.flatnonzero(ok & (rl != ol))[:10]
+    # the blob is dense and every record lies inside it
+    assert int(rl.sum()) == r.payload.size and (r.n == 0 or int((r.offsets.astype(np.int64) + rl).max()) <= r.payload.size)
     if not unsup.any() and not (o.status == 4).any():
-        assert np.array_equal(r.payload, o.payload)
+        assert np.array_equal(r.fifo_payload(), o.payload)      # bit-for-bit, every record
     else:
         for i in np.flatnonzero(ok):
             assert r.result(i) == o.result(i), i

@@ -82,32 +82,54 @@ __device__ __forceinline__ bool swar_special16(uint32_t x, uint32_t y, uint32_t 
 }
 __device__ __forceinline__ bool byte_special(uint32_t c) { return c < 0x20u || c >= 0x7Fu || c == '"' || c == '\\'; }
 
+// 4 bytes at an arbitrary address: two aligned words + funnel shift
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* __restrict__ p) {
+    const uint32_t a = (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t* w = (const uint32_t*)(p - a);
+    return __funnelshift_r(w[0], w[1], a * 8u);
+}
+// per-byte 0xFF where the byte's index (0..15 across the four words) is >= lo and < hi
+__device__ __forceinline__ uint32_t byte_range_mask(uint32_t word, uint32_t lo, uint32_t hi) {
+    const uint32_t idx = 0x03020100u + 0x04040404u * word;
+    return __vcmpgeu4(idx, lo * 0x01010101u) & __vcmpltu4(idx, hi * 0x01010101u);
+}
+
 // Thread-per-task: is the payload exactly  {"args": ["<body>"], "kwargs": {}}  with a body of
 // printable ASCII free of '"' and '\\'?  `frame_ok` reports the frame alone.
-__device__ inline bool quick_clean_framed(const uint8_t* __restrict__ p, uint32_t len, bool* frame_ok) {
+__device__ __forceinline__ bool quick_clean_framed(const uint8_t* __restrict__ p, uint32_t len, bool* frame_ok) {
     *frame_ok = false;
     if (len < FRAME_PRE_LEN + FRAME_SUF_LEN) return false;
-    bool ok = true;
-    #pragma unroll
-    for (uint32_t i = 0; i < FRAME_PRE_LEN; ++i) ok &= p[i] == FRAME_PRE[i];
-    const uint8_t* sfx = p + len - FRAME_SUF_LEN;
-    #pragma unroll
-    for (uint32_t i = 0; i < FRAME_SUF_LEN; ++i) ok &= sfx[i] == FRAME_SUF[i];
+    // frame: 11 + 17 bytes compared as 32-bit words ("{\"ar" "gs\":" " [\""  /  "\"], " "\"kwa" "rgs\"" ": {}" "}")
+    const uint8_t* q = p + len - FRAME_SUF_LEN;
+    bool ok = ld_u32_unaligned(p) == 0x7261227Bu && ld_u32_unaligned(p + 4) == 0x3A227367u
+           && (ld_u32_unaligned(p + 8) & 0x00FFFFFFu) == 0x00225B20u
+           && ld_u32_unaligned(q) == 0x202C5D22u && ld_u32_unaligned(q + 4) == 0x61776B22u
+           && ld_u32_unaligned(q + 8) == 0x22736772u && ld_u32_unaligned(q + 12) == 0x7D7B203Au && q[16] == '}';
     if (!ok) return false;
     *frame_ok = true;
+    // body = [b0, b1): aligned 16-byte groups; bytes of the first/last group that lie outside the
+    // body are replaced by 'a' before the SWAR test
     const uint8_t* b0 = p + FRAME_PRE_LEN;
-    const uint8_t* b1 = sfx;
-    const uint8_t* w0 = (const uint8_t*)(((uintptr_t)b0 + 15u) & ~(uintptr_t)15u);
-    const uint8_t* w1 = (const uint8_t*)((uintptr_t)b1 & ~(uintptr_t)15u);
+    const uint8_t* b1 = q;
+    if (b0 == b1) return true;
+    // (pointer - integer keeps the address space the compiler inferred; an integer round trip loses it)
+    const uint8_t* g0 = b0 - ((uintptr_t)b0 & 15u);
+    const uint8_t* g1 = b1 + ((16u - ((uintptr_t)b1 & 15u)) & 15u);
+    const uint32_t lead = (uint32_t)(b0 - g0);                  // bytes to ignore at the front of the first group
+    const uint32_t tail_keep = 16u - (uint32_t)(g1 - b1);       // bytes to keep in the last group
+    const uint32_t A = 0x61616161u;
     bool special = false;
-    if (w0 >= w1) {                                   // short body: bytewise
-        for (const uint8_t* q = b0; q < b1; ++q) special |= byte_special(*q);
-        return !special;
-    }
-    for (const uint8_t* q = b0; q < w0; ++q) special |= byte_special(*q);
-    for (const uint8_t* q = w1; q < b1; ++q) special |= byte_special(*q);
-    for (const uint4* q = (const uint4*)w0; q < (const uint4*)w1; ++q) {
-        uint4 v = *q;
+    for (const uint8_t* g = g0; g < g1; g += 16) {
+        uint4 v = *(const uint4*)g;
+        const bool first = g == g0, last = g + 16 == g1;
+        if (first | last) {
+            const uint32_t lo = first ? lead : 0u, hi = last ? tail_keep : 16u;
+            uint32_t m;
+            m = byte_range_mask(0, lo, hi); v.x = (v.x & m) | (A & ~m);
+            m = byte_range_mask(1, lo, hi); v.y = (v.y & m) | (A & ~m);
+            m = byte_range_mask(2, lo, hi); v.z = (v.z & m) | (A & ~m);
+            m = byte_range_mask(3, lo, hi); v.w = (v.w & m) | (A & ~m);
+        }
         special |= swar_special16(v.x, v.y, v.z, v.w);
     }
     return !special;
@@ -115,7 +137,7 @@ __device__ inline bool quick_clean_framed(const uint8_t* __restrict__ p, uint32_
 
 // Thread-per-task copy of n bytes to global memory: 16-byte stores on the destination,
 // 4-byte loads + funnel shift on the (arbitrarily aligned) source.
-__device__ inline void thread_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
+__device__ __forceinline__ void thread_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
     uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
     if (head > n) head = n;
     for (uint32_t i = 0; i < head; ++i) dst[i] = src[i];
@@ -270,24 +292,14 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
     return inc - v;
 }
 
-// Warp-cooperative: json.dumps length of the framed string body, or ok=false if the body is not a
-// well-formed JSON string ending exactly at the frame's closing quote.
-__device__ inline bool esc_measure(const uint8_t* __restrict__ body, uint32_t n, int lane, uint32_t* out_len) {
-    const uint32_t S = (n + 31u) / 32u;
-    const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
-    bool ok = true;
-    uint32_t mine = 0;
-    if (lo < hi) {
-        uint32_t i = first_unit_start(body, n, lo);
-        while (i < hi && ok) mine += py_escaped_len(next_unit(body, i, n, &ok));
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    *out_len = 2u + warp_sum(mine);
-    return ok;
-}
+__device__ __forceinline__ bool plain_byte(uint32_t c) { return c >= 0x20u && c < 0x7Fu && c != '"' && c != '\\'; }
 
-// Warp-cooperative: write json.dumps(body) to dst (global). Only called after esc_measure said ok.
-__device__ inline void esc_emit(const uint8_t* __restrict__ body, uint32_t n, int lane, uint8_t* __restrict__ dst) {
+// Warp-cooperative: json.dumps length of the framed string body, or false if the body is not a
+// well-formed JSON string ending exactly at the frame's closing quote. Every lane walks its chunk
+// as  (run of plain bytes)* (one escape / UTF-8 unit)  so that the branchy unit decoder runs once
+// per round for the whole warp. `lane_info` (optional, shared memory, 32 words) keeps each lane's
+// first-unit offset and output length for esc_emit.
+__device__ __forceinline__ bool esc_measure(const uint8_t* __restrict__ body, uint32_t n, int lane, uint32_t* out_len, uint32_t* lane_info) {
     const uint32_t S = (n + 31u) / 32u;
     const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
     bool ok = true;
@@ -295,7 +307,34 @@ __device__ inline void esc_emit(const uint8_t* __restrict__ body, uint32_t n, in
     if (lo < hi) {
         start = first_unit_start(body, n, lo);
         uint32_t i = start;
-        while (i < hi) mine += py_escaped_len(next_unit(body, i, n, &ok));
+        while (i < hi) {
+            while (i < hi && plain_byte(body[i])) { ++i; ++mine; }
+            if (i >= hi) break;
+            mine += py_escaped_len(next_unit(body, i, n, &ok));
+            if (!ok) break;
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    *out_len = 2u + warp_sum(mine);
+    if (lane_info) lane_info[lane] = mine | ((start - lo) << 24);     // chunk output < 2^24 bytes for any accepted payload
+    return ok;
+}
+
+// Warp-cooperative: write json.dumps(body) to dst (global). Only called after esc_measure said ok.
+__device__ __forceinline__ void esc_emit(const uint8_t* __restrict__ body, uint32_t n, int lane, uint8_t* __restrict__ dst, const uint32_t* lane_info) {
+    const uint32_t S = (n + 31u) / 32u;
+    const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
+    bool ok = true;
+    uint32_t mine = 0, start = lo;
+    if (lane_info) { const uint32_t w = lane_info[lane]; mine = w & 0xFFFFFFu; start = lo + (w >> 24); }
+    else if (lo < hi) {
+        start = first_unit_start(body, n, lo);
+        uint32_t i = start;
+        while (i < hi) {
+            while (i < hi && plain_byte(body[i])) { ++i; ++mine; }
+            if (i >= hi) break;
+            mine += py_escaped_len(next_unit(body, i, n, &ok));
+        }
     }
     const uint32_t at = 1u + warp_excl_scan(mine, lane);
     if (lane == 0) dst[0] = '"';
@@ -303,20 +342,27 @@ __device__ inline void esc_emit(const uint8_t* __restrict__ body, uint32_t n, in
     if (lo < hi) {
         uint8_t* o = dst + at;
         uint32_t i = start;
-        while (i < hi) o += py_emit(next_unit(body, i, n, &ok), o);
+        while (i < hi) {
+            while (i < hi) { const uint32_t c = body[i]; if (!plain_byte(c)) break; *o++ = (uint8_t)c; ++i; }
+            if (i >= hi) break;
+            o += py_emit(next_unit(body, i, n, &ok), o);
+        }
     }
 }
 
 // ------------------------------------------------------------------ the kernel
+constexpr int D2_ESC_SLOTS = 8;          // escaped strings per tile whose per-lane sizes are kept for phase B
+template <int HANDLER>
 struct D2Shared {
-    D2Meta meta[D2_STAGES];
+    D2Meta meta;
     TaskRec rec[D2_THREADS];
-    uint32_t excl_bytes[D2_THREADS];
-    uint32_t warp_bytes[D2_WARPS], warp_cnt[D2_WARPS];
+    uint32_t excl_bytes[D2_THREADS];     // exclusive prefix of out_len inside the tile
+    uint32_t excl_cnt[D2_THREADS];       // exclusive prefix of ready inside the tile
     uint32_t slow_list[D2_THREADS]; uint32_t n_slow;
+    uint32_t esc_info[D2_ESC_SLOTS][32];
     unsigned long long base;
-    uint32_t crc_table[256];
-    alignas(8) uint64_t mbar[D2_STAGES];
+    uint32_t crc_table[HANDLER == 1 ? 256 : 1];
+    alignas(8) uint64_t mbar;
 };
 
 // warp 0, step 1: start the loads of a tile's slot words (two tasks per lane); nothing is consumed
@@ -425,167 +471,169 @@ __device__ inline void d2_stage_tile(const DrainArgs& a, unsigned long long tile
     }
 }
 
+// ---- per-task bodies, inlined once for shared-memory payloads (LDS) and once for global ones ----
 template <int HANDLER>
-__global__ void __launch_bounds__(D2_THREADS, 4) drain2_kernel(DrainArgs a, uint32_t in_cap) {
+__device__ __forceinline__ void d2_phase_a_task(const uint8_t* __restrict__ p, uint32_t len, TaskRec& rec, bool* slow,
+                                                const uint32_t* crc_table) {
+    if (HANDLER == 0) {
+        bool frame_ok;
+        if (quick_clean_framed(p, len, &frame_ok)) {
+            const uint32_t tok = len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
+            if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
+        } else {
+            rec.mode = frame_ok ? OM_STR_PAR : OM_NONE;         // settled in the cooperative pass
+            *slow = true;
+        }
+    } else {
+        Parsed pr = parse_payload(p, len);
+        handler_phase_a(HANDLER, p, pr, rec, crc_table);
+    }
+}
+
+__device__ __forceinline__ void d2_phase_b_task(const uint8_t* __restrict__ p, const TaskRec& rec, uint8_t* __restrict__ o) {
+    if (rec.mode == OM_COPY) thread_copy(o, p + rec.src_off, rec.src_len);
+    else if (rec.mode == OM_VADD) vadd_write(p, rec.src_off, rec.src_len, o);
+    else if (rec.mode == OM_U32_DEC || rec.mode == OM_I64_DEC) {
+        long long v = rec.value; uint32_t l = rec.out_len;
+        if (v < 0) { *o++ = '-'; --l; v = -v; }
+        write_dec(o, (unsigned long long)v, l);
+    } else if (rec.mode == OM_STR_ESC) {                          // string the sequential parser sized (non-canonical frame)
+        uint32_t i = rec.src_off + 1, end = rec.src_off + rec.src_len - 1;
+        *o++ = '"';
+        while (i < end) o += py_emit(next_cp(p, i, end), o);
+        *o = '"';
+    }
+}
+
+template <int HANDLER>
+__global__ void __launch_bounds__(D2_THREADS, 8) drain2_kernel(DrainArgs a, uint32_t in_cap) {
     extern __shared__ __align__(128) uint8_t d2_smem[];
-    D2Shared& S = *reinterpret_cast<D2Shared*>(d2_smem);
-    uint8_t* const bufs = d2_smem + ((sizeof(D2Shared) + 127u) & ~127u);
-    const uint32_t buf_stride = (in_cap + 64u + 127u) & ~127u;           // 64 bytes of readable slack behind each stage
+    using Sh = D2Shared<HANDLER>;
+    Sh& S = *reinterpret_cast<Sh*>(d2_smem);
+    uint8_t* const sbuf = d2_smem + ((sizeof(Sh) + 127u) & ~127u);      // the stage buffer (+64 bytes of readable slack)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    if (tid == 0) { mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.n_slow = 0; }
     if (HANDLER == 1) for (int i = tid; i < 256; i += D2_THREADS) S.crc_table[i] = crc_table_entry(i);
-    __syncthreads();
 
-    uint32_t stage = 0, parity_bits = 0;   // bit s: phase parity of stage s's mbarrier
-    // warp 0 runs a three-deep software pipeline so that no global latency sits between two
-    // block barriers: ticket(i+3) is being claimed while the slot words of tile i+2 are in flight
-    // and the payload bytes of tile i+1 stream into the other stage. Holding tickets ahead is
-    // harmless now that no CTA waits on another CTA's unprocessed tile.
-    unsigned long long t_meta = ~0ull;     // tile whose slot words are in `mregs`
-    unsigned long long t_raw = ~0ull;      // lane 0: ticket claimed for the tile after t_meta
+    // warp 0 keeps two tickets ahead of the tile being processed: the slot words of the next tile are
+    // already in registers when its turn comes (no global latency between the end of one tile and the
+    // bulk copy of the next), and the ticket after that is in flight. Holding tickets is harmless: no
+    // CTA waits on another CTA's unprocessed tile (the byte cursor is an atomic, not a chain).
+    unsigned long long t_cur = ~0ull;      // tile to process next; its slot words are in `mregs`
+    unsigned long long t_raw = ~0ull;      // lane 0: ticket claimed for the tile after t_cur
     D2MetaRegs mregs; mregs.off[0] = mregs.off[1] = mregs.hdr[0] = mregs.hdr[1] = 0;
     if (warp == 0) {
-        unsigned long long t0 = 0, t1 = 0;
-        if (lane == 0) { t0 = atomicAdd(&a.ctl->ticket, 1ull); t1 = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
-        t0 = __shfl_sync(0xffffffffu, t0, 0); t1 = __shfl_sync(0xffffffffu, t1, 0);
-        if (t0 < a.n_tiles) { D2MetaRegs r0; d2_load_meta(a, t0, lane, r0); d2_stage_tile(a, t0, r0, S.meta[0], bufs, in_cap, &S.mbar[0], lane); }
-        else if (lane == 0) S.meta[0].tile = t0;
-        t_meta = t1;
-        if (t_meta < a.n_tiles) d2_load_meta(a, t_meta, lane, mregs);
+        if (lane == 0) { t_cur = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
+        t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
+        if (t_cur < a.n_tiles) d2_load_meta(a, t_cur, lane, mregs);
     }
     __syncthreads();
+    uint32_t parity = 0;
+    D2Meta& M = S.meta;
 
     for (;;) {
-        D2Meta& M = S.meta[stage];
-        const unsigned long long tile = M.tile;
-        if (tile >= a.n_tiles) break;
         if (warp == 0) {
-            // stage tile i+1 (its slot words were requested one iteration ago) ...
-            if (t_meta < a.n_tiles) d2_stage_tile(a, t_meta, mregs, S.meta[stage ^ 1], bufs + (size_t)(stage ^ 1) * buf_stride, in_cap, &S.mbar[stage ^ 1], lane);
-            else if (lane == 0) S.meta[stage ^ 1].tile = t_meta;
-            // ... request the slot words of tile i+2, claim the ticket of tile i+3
-            t_meta = __shfl_sync(0xffffffffu, t_raw, 0);
-            if (t_meta < a.n_tiles) d2_load_meta(a, t_meta, lane, mregs);
+            if (t_cur < a.n_tiles) d2_stage_tile(a, t_cur, mregs, M, sbuf, in_cap, &S.mbar, lane);
+            else if (lane == 0) M.tile = t_cur;
+            t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
+            if (t_cur < a.n_tiles) d2_load_meta(a, t_cur, lane, mregs);
             if (lane == 0) t_raw = atomicAdd(&a.ctl->ticket, 1ull);
         }
+        __syncthreads();                                                   // [1] tile metadata visible
+        const unsigned long long tile = M.tile;
+        if (tile >= a.n_tiles) break;
         const uint32_t nt = M.nt;
         const uint32_t t0 = (uint32_t)tile * D2_THREADS;
         const bool staged = M.staged != 0;
-        const uint8_t* const sbuf = bufs + (size_t)stage * buf_stride;
-        if (staged) { mbar_wait(&S.mbar[stage], (parity_bits >> stage) & 1u); parity_bits ^= 1u << stage; }
-        if (tid == 0) S.n_slow = 0;
-        __syncthreads();
+        if (staged) { mbar_wait(&S.mbar, parity); parity ^= 1u; }
 
         // ---------------- phase A (thread per task) -------------------------------------------------
-        {
-            TaskRec rec; rec.ready = 0; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
-            if (tid < (int)nt) {
-                rec.ready = M.ready[tid];
-                if (rec.ready) {
-                    const uint32_t len = M.len[tid];
-                    const uint8_t* p = staged ? sbuf + M.soff[tid] : a.payload + M.goff[tid];
-                    if (HANDLER == 0) {
-                        bool frame_ok;
-                        if (quick_clean_framed(p, len, &frame_ok)) {
-                            const uint32_t tok = len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
-                            if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
-                        } else {
-                            rec.mode = frame_ok ? OM_STR_PAR : OM_NONE;         // decided in the cooperative pass
-                            S.slow_list[atomicAdd(&S.n_slow, 1u)] = (uint32_t)tid;
-                        }
-                    } else {
-                        Parsed pr = parse_payload(p, len);
-                        handler_phase_a(HANDLER, p, pr, rec, S.crc_table);
-                    }
-                }
-            }
-            S.rec[tid] = rec;
+        TaskRec rec; rec.ready = 0; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
+        if (tid < (int)nt && M.ready[tid]) {
+            rec.ready = 1;
+            bool slow = false;
+            if (staged) d2_phase_a_task<HANDLER>(sbuf + M.soff[tid], M.len[tid], rec, &slow, S.crc_table);
+            else        d2_phase_a_task<HANDLER>(a.payload + M.goff[tid], M.len[tid], rec, &slow, S.crc_table);
+            if (slow) S.slow_list[atomicAdd(&S.n_slow, 1u)] = (uint32_t)tid;
         }
-        __syncthreads();
+        S.rec[tid] = rec;
+        __syncthreads();                                                   // [2] records + slow list complete
         // ---------------- phase A, cooperative pass over the tasks the quick look could not settle --
-        if (HANDLER == 0) {
-            const uint32_t ns = S.n_slow;
+        const uint32_t ns = (HANDLER == 0) ? S.n_slow : 0u;
+        if (ns) {
             for (uint32_t s = warp; s < ns; s += D2_WARPS) {
                 const uint32_t k = S.slow_list[s];
                 const uint32_t len = M.len[k];
-                const uint8_t* p = staged ? sbuf + M.soff[k] : a.payload + M.goff[k];
-                TaskRec rec = S.rec[k];
+                TaskRec r2 = S.rec[k];
                 bool done = false;
-                if (rec.mode == OM_STR_PAR) {                                     // canonical frame, body needs transcoding
+                if (r2.mode == OM_STR_PAR) {                               // canonical frame, body needs transcoding
                     uint32_t ol;
                     const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
-                    if (esc_measure(p + FRAME_PRE_LEN, n, lane, &ol)) {
-                        rec.has = 1; rec.src_off = FRAME_PRE_LEN; rec.src_len = n; rec.out_len = ol; done = true;   // n > 0 here
-                    }
+                    uint32_t* info = s < D2_ESC_SLOTS ? S.esc_info[s] : nullptr;
+                    const bool ok = staged ? esc_measure(sbuf + M.soff[k] + FRAME_PRE_LEN, n, lane, &ol, info)
+                                           : esc_measure(a.payload + M.goff[k] + FRAME_PRE_LEN, n, lane, &ol, info);
+                    if (ok) { r2.has = 1; r2.src_off = FRAME_PRE_LEN; r2.src_len = n; r2.out_len = ol; done = true; }
                 }
-                if (!done) {
-                    if (lane == 0) { Parsed pr = parse_payload(p, len); handler_phase_a(0, p, pr, rec, nullptr); rec.ready = 1; }
+                if (!done && lane == 0) {
+                    const uint8_t* p = staged ? (const uint8_t*)(sbuf + M.soff[k]) : a.payload + M.goff[k];
+                    Parsed pr = parse_payload(p, len);
+                    handler_phase_a(0, p, pr, r2, nullptr);
+                    r2.ready = 1;
                 }
-                if (lane == 0) S.rec[k] = rec;
+                if (lane == 0) S.rec[k] = r2;
             }
-            __syncthreads();
+            __syncthreads();                                               // [3] slow tasks sized
         }
 
-        // ---------------- compaction (ballot) + sizes (scan) + one cursor add per tile ---------------
-        uint32_t my_bytes = 0, my_cnt = 0;
-        if (tid < (int)nt) { my_bytes = S.rec[tid].out_len; my_cnt = S.rec[tid].ready ? 1u : 0u; }
-        const uint32_t ready_mask = __ballot_sync(0xffffffffu, my_cnt);
-        const uint32_t ex_b = warp_excl_scan(my_bytes, lane);
-        if (lane == 31) { S.warp_bytes[warp] = ex_b + my_bytes; S.warp_cnt[warp] = __popc(ready_mask); }
-        __syncthreads();
-        uint32_t wb = 0, wc = 0, tb = 0;
-        #pragma unroll
-        for (int w = 0; w < D2_WARPS; ++w) { uint32_t b = S.warp_bytes[w], c = S.warp_cnt[w]; if (w < warp) { wb += b; wc += c; } tb += b; }
-        const uint32_t my_excl_bytes = wb + ex_b;
-        const uint32_t my_excl_cnt = wc + __popc(ready_mask & ((1u << lane) - 1u));
-        S.excl_bytes[tid] = my_excl_bytes;                    // the cooperative pass needs other tasks' offsets
-        if (tid == 0) S.base = tb ? atomicAdd(&a.ctl->bytes, (unsigned long long)tb) : 0ull;
-        __syncthreads();
-        const uint64_t base_bytes = S.base;
+        // ---------------- compaction (ballot) + sizes (scan) + ONE cursor add, all in warp 0 ---------
+        if (warp == 0) {
+            const uint32_t l0 = S.rec[lane].out_len, l1 = S.rec[lane + 32].out_len;
+            const uint32_t m0 = __ballot_sync(0xffffffffu, S.rec[lane].ready), m1 = __ballot_sync(0xffffffffu, S.rec[lane + 32].ready);
+            const uint32_t e0 = warp_excl_scan(l0, lane);
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, e0 + l0, 31);
+            const uint32_t e1 = tot0 + warp_excl_scan(l1, lane);
+            const uint32_t tb = __shfl_sync(0xffffffffu, e1 + l1, 31);
+            S.excl_bytes[lane] = e0; S.excl_bytes[lane + 32] = e1;
+            const uint32_t below = (1u << lane) - 1u;
+            S.excl_cnt[lane] = __popc(m0 & below); S.excl_cnt[lane + 32] = __popc(m0) + __popc(m1 & below);
+            if (lane == 0) {
+                const unsigned long long base = tb ? atomicAdd(&a.ctl->bytes, (unsigned long long)tb) : 0ull;
+                S.base = base;
+                if (base + tb > a.out_cap) { a.ctl->overflow = 1u; S.base = ~0ull; }
+                S.n_slow = 0;                                              // for the next tile (read again only after [1])
+            }
+        }
+        __syncthreads();                                                   // [4] offsets known
+        const unsigned long long base_bytes = S.base;
+        const bool fits = base_bytes != ~0ull;
         const uint32_t base_cnt = M.base_cnt;
-        const bool fits = base_bytes + tb <= a.out_cap;
-        if (!fits && tid == 0) a.ctl->overflow = 1u;
 
         // ---------------- phase B (thread per task) -------------------------------------------------
-        if (tid < (int)nt) {
-            const TaskRec rec = S.rec[tid];
-            if (rec.ready) {
-                const uint32_t slot = (uint32_t)((a.first_task + t0 + tid) & a.slot_mask);
-                const uint32_t j = base_cnt + my_excl_cnt;
-                const uint64_t ob = base_bytes + my_excl_bytes;
-                a.out_off[j] = ob; a.out_len[j] = rec.out_len; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
-                if (rec.has && fits) {
-                    const uint8_t* p = staged ? sbuf + M.soff[tid] : a.payload + M.goff[tid];
-                    uint8_t* o = a.out_payload + ob;
-                    if (rec.mode == OM_COPY) thread_copy(o, p + rec.src_off, rec.src_len);
-                    else if (rec.mode == OM_VADD) vadd_write(p, rec.src_off, rec.src_len, o);
-                    else if (rec.mode == OM_U32_DEC || rec.mode == OM_I64_DEC) {
-                        long long v = rec.value; uint32_t l = rec.out_len;
-                        if (v < 0) { *o++ = '-'; --l; v = -v; }
-                        write_dec(o, (unsigned long long)v, l);
-                    } else if (rec.mode == OM_STR_ESC) {                          // string the sequential parser sized (non-canonical frame)
-                        uint32_t i = rec.src_off + 1, end = rec.src_off + rec.src_len - 1;
-                        *o++ = '"';
-                        while (i < end) o += py_emit(next_cp(p, i, end), o);
-                        *o = '"';
-                    }
-                }
+        if (rec.ready) {
+            rec = S.rec[tid];                                              // the cooperative pass may have rewritten it
+            const uint32_t slot = (uint32_t)((a.first_task + t0 + tid) & a.slot_mask);
+            const uint32_t j = base_cnt + S.excl_cnt[tid];
+            const uint64_t ob = base_bytes + S.excl_bytes[tid];
+            a.out_off[j] = fits ? ob : 0; a.out_len[j] = rec.out_len; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
+            if (rec.has && fits && rec.mode != OM_STR_PAR) {
+                if (staged) d2_phase_b_task(sbuf + M.soff[tid], rec, a.out_payload + ob);
+                else        d2_phase_b_task(a.payload + M.goff[tid], rec, a.out_payload + ob);
             }
         }
         // ---------------- phase B, cooperative: transcode the escaped strings -----------------------
-        if (HANDLER == 0 && fits) {
-            const uint32_t ns = S.n_slow;
+        if (ns && fits) {
             for (uint32_t s = warp; s < ns; s += D2_WARPS) {
                 const uint32_t k = S.slow_list[s];
-                const TaskRec rec = S.rec[k];
-                if (rec.mode != OM_STR_PAR || !rec.has) continue;
-                const uint8_t* p = staged ? sbuf + M.soff[k] : a.payload + M.goff[k];
-                esc_emit(p + rec.src_off, rec.src_len, lane, a.out_payload + base_bytes + S.excl_bytes[k]);
+                const TaskRec r2 = S.rec[k];
+                if (r2.mode != OM_STR_PAR || !r2.has) continue;
+                const uint32_t* info = s < D2_ESC_SLOTS ? S.esc_info[s] : nullptr;
+                uint8_t* o = a.out_payload + base_bytes + S.excl_bytes[k];
+                if (staged) esc_emit(sbuf + M.soff[k] + r2.src_off, r2.src_len, lane, o, info);
+                else        esc_emit(a.payload + M.goff[k] + r2.src_off, r2.src_len, lane, o, info);
             }
         }
-        __syncthreads();            // stage buffer, records and metadata are free again
-        stage ^= 1u;
+        __syncthreads();                                                   // [5] stage buffer, records, metadata free again
     }
 }
 

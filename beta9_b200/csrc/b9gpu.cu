@@ -124,20 +124,20 @@ template <int H> cudaError_t launch_drain(const DrainArgs& a, int grid, cudaStre
 template <int H> size_t drain2_smem_bytes(uint32_t in_cap) {
     const size_t ctl = (sizeof(D2Shared<H>) + 127u) & ~(size_t)127u;
     const size_t stride = ((size_t)in_cap + 64u + 127u) & ~(size_t)127u;
-    return ctl + stride;
+    return ctl + D2_STAGES * stride;
 }
 template <int H> cudaError_t launch_drain2(DrainArgs a, uint32_t in_cap, int sm_count, cudaStream_t s, int* grid_out) {
     const size_t smem = drain2_smem_bytes<H>(in_cap);
     cudaError_t e = cudaFuncSetAttribute(drain2_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drain2_kernel<H>, D2_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drain2_kernel<H>, D2Cfg<H>::THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     a.n_tiles = (a.n_tasks + D2_THREADS - 1) / D2_THREADS;
     const int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)(per_sm * sm_count));
     *grid_out = grid;
-    drain2_kernel<H><<<grid, D2_THREADS, smem, s>>>(a, in_cap);
+    drain2_kernel<H><<<grid, D2Cfg<H>::THREADS, smem, s>>>(a, in_cap);
     return cudaGetLastError();
 }
 
@@ -385,9 +385,9 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
     CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));
     int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
-    // one stage buffer per CTA, sized for the window's average tile: 64 tasks x 1.1 + 2 KiB, within [4 KiB, 200 KiB].
+    // two stage buffers per CTA, each sized for the window's average tile: 64 tasks x 1.1 + 2 KiB, within [4 KiB, 100 KiB].
     // Tiles that do not fit are processed straight from global memory (same code, slower loads).
-    uint32_t in_cap = (uint32_t)std::min<uint64_t>(200u << 10, std::max<uint64_t>(4u << 10, (in_bytes * D2_THREADS / n) * 11 / 10 + 2048));
+    uint32_t in_cap = (uint32_t)std::min<uint64_t>(100u << 10, std::max<uint64_t>(4u << 10, (in_bytes * D2_THREADS / n) * 11 / 10 + 2048));
     in_cap = (in_cap + 511u) & ~511u;
     if (c->stage_bytes_override) in_cap = c->stage_bytes_override;
     CU(cudaEventRecord(c->ev_a, s));

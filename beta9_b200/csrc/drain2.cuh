@@ -30,9 +30,13 @@
 
 namespace b9 {
 
-constexpr int D2_THREADS = 64;               // threads per CTA == tasks per tile
-constexpr int D2_WARPS   = D2_THREADS / 32;
+constexpr int D2_TASKS   = 64;               // tasks per tile
+constexpr int D2_THREADS = D2_TASKS;         // (host code sizes tiles with this name)
 constexpr int D2_STAGES  = 2;
+// G threads share one task (G = 4 for the identity kernel: a 284-byte payload is 18 sixteen-byte
+// groups, 4-5 per thread; four times the warps per byte of staged payload hide the latencies that a
+// thread-per-task layout, capped at ~16 warps/SM by its shared-memory footprint, cannot).
+template <int HANDLER> struct D2Cfg { static constexpr int G = (HANDLER == 0) ? 4 : 1; static constexpr int THREADS = D2_TASKS * G; };
 
 // ------------------------------------------------------------------ PTX: mbarrier + bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -57,10 +61,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // ------------------------------------------------------------------ per-stage tile metadata
 struct D2Meta {
-    uint64_t goff[D2_THREADS];     // physical ring offset of each task's payload
-    uint32_t soff[D2_THREADS];     // offset inside the stage buffer (when staged)
-    uint32_t len[D2_THREADS];
-    uint8_t  ready[D2_THREADS];
+    uint64_t goff[D2_TASKS];     // physical ring offset of each task's payload
+    uint32_t soff[D2_TASKS];     // offset inside the stage buffer (when staged)
+    uint32_t len[D2_TASKS];
+    uint8_t  ready[D2_TASKS];
     unsigned long long tile;
     uint32_t nt;
     uint32_t staged;               // 1: payload bytes are (arriving) in shared memory; 0: read from global
@@ -94,71 +98,77 @@ __device__ __forceinline__ uint32_t byte_range_mask(uint32_t word, uint32_t lo, 
     return __vcmpgeu4(idx, lo * 0x01010101u) & __vcmpltu4(idx, hi * 0x01010101u);
 }
 
-// Thread-per-task: is the payload exactly  {"args": ["<body>"], "kwargs": {}}  with a body of
-// printable ASCII free of '"' and '\\'?  `frame_ok` reports the frame alone.
-__device__ __forceinline__ bool quick_clean_framed(const uint8_t* __restrict__ p, uint32_t len, bool* frame_ok) {
-    *frame_ok = false;
-    if (len < FRAME_PRE_LEN + FRAME_SUF_LEN) return false;
-    // frame: 11 + 17 bytes compared as 32-bit words ("{\"ar" "gs\":" " [\""  /  "\"], " "\"kwa" "rgs\"" ": {}" "}")
-    const uint8_t* q = p + len - FRAME_SUF_LEN;
-    bool ok = ld_u32_unaligned(p) == 0x7261227Bu && ld_u32_unaligned(p + 4) == 0x3A227367u
-           && (ld_u32_unaligned(p + 8) & 0x00FFFFFFu) == 0x00225B20u
-           && ld_u32_unaligned(q) == 0x202C5D22u && ld_u32_unaligned(q + 4) == 0x61776B22u
-           && ld_u32_unaligned(q + 8) == 0x22736772u && ld_u32_unaligned(q + 12) == 0x7D7B203Au && q[16] == '}';
-    if (!ok) return false;
-    *frame_ok = true;
-    // body = [b0, b1): aligned 16-byte groups; bytes of the first/last group that lie outside the
-    // body are replaced by 'a' before the SWAR test
-    const uint8_t* b0 = p + FRAME_PRE_LEN;
-    const uint8_t* b1 = q;
-    if (b0 == b1) return true;
-    // (pointer - integer keeps the address space the compiler inferred; an integer round trip loses it)
-    const uint8_t* g0 = b0 - ((uintptr_t)b0 & 15u);
-    const uint8_t* g1 = b1 + ((16u - ((uintptr_t)b1 & 15u)) & 15u);
-    const uint32_t lead = (uint32_t)(b0 - g0);                  // bytes to ignore at the front of the first group
-    const uint32_t tail_keep = 16u - (uint32_t)(g1 - b1);       // bytes to keep in the last group
-    const uint32_t A = 0x61616161u;
-    bool special = false;
-    for (const uint8_t* g = g0; g < g1; g += 16) {
-        uint4 v = *(const uint4*)g;
-        const bool first = g == g0, last = g + 16 == g1;
-        if (first | last) {
-            const uint32_t lo = first ? lead : 0u, hi = last ? tail_keep : 16u;
-            uint32_t m;
-            m = byte_range_mask(0, lo, hi); v.x = (v.x & m) | (A & ~m);
-            m = byte_range_mask(1, lo, hi); v.y = (v.y & m) | (A & ~m);
-            m = byte_range_mask(2, lo, hi); v.z = (v.z & m) | (A & ~m);
-            m = byte_range_mask(3, lo, hi); v.w = (v.w & m) | (A & ~m);
+// G threads per task (sub = 0..G-1, adjacent lanes): is the payload exactly
+//   {"args": ["<body>"], "kwargs": {}}
+// with a body of printable ASCII free of '"' and '\\'?  Returns bit0 = frame matches, bit1 = body
+// clean, identical on all G lanes. Must be called by all 32 lanes of the warp (`active` masks the
+// loads of lanes whose task does not exist).
+template <int G>
+__device__ __forceinline__ uint32_t quick_clean_framed(const uint8_t* __restrict__ p, uint32_t len, int sub, bool active) {
+    uint32_t bad_frame = 0, special = 0;
+    if (active && len >= FRAME_PRE_LEN + FRAME_SUF_LEN) {
+        // frame: 11 + 17 bytes compared as 32-bit words ("{\"ar" "gs\":" " [\""  /  "\"], " "\"kwa" "rgs\"" ": {}" "}")
+        const uint8_t* q = p + len - FRAME_SUF_LEN;
+        if (0 % G == sub) bad_frame |= ld_u32_unaligned(p) != 0x7261227Bu;
+        if (1 % G == sub) bad_frame |= ld_u32_unaligned(p + 4) != 0x3A227367u;
+        if (2 % G == sub) bad_frame |= (ld_u32_unaligned(p + 8) & 0x00FFFFFFu) != 0x00225B20u;
+        if (3 % G == sub) bad_frame |= ld_u32_unaligned(q) != 0x202C5D22u;
+        if (4 % G == sub) bad_frame |= ld_u32_unaligned(q + 4) != 0x61776B22u;
+        if (5 % G == sub) bad_frame |= ld_u32_unaligned(q + 8) != 0x22736772u;
+        if (6 % G == sub) bad_frame |= ld_u32_unaligned(q + 12) != 0x7D7B203Au;
+        if (7 % G == sub) bad_frame |= q[16] != '}';
+        // body = [b0, b1): aligned 16-byte groups, group i handled by lane i % G; bytes of the first /
+        // last group outside the body are replaced by 'a' before the SWAR test. (A garbage frame makes
+        // the answer irrelevant, but the loads stay inside the payload: len >= 28.)
+        const uint8_t* b0 = p + FRAME_PRE_LEN;
+        const uint8_t* b1 = q;
+        // (pointer - integer keeps the address space the compiler inferred; an integer round trip loses it)
+        const uint8_t* g0 = b0 - ((uintptr_t)b0 & 15u);
+        const uint8_t* g1 = b1 + ((16u - ((uintptr_t)b1 & 15u)) & 15u);
+        const uint32_t lead = (uint32_t)(b0 - g0);                  // bytes to ignore at the front of the first group
+        const uint32_t tail_keep = 16u - (uint32_t)(g1 - b1);       // bytes to keep in the last group
+        const uint32_t A = 0x61616161u;
+        for (const uint8_t* g = g0 + 16 * sub; g < g1; g += 16 * G) {
+            uint4 v = *(const uint4*)g;
+            const bool first = g == g0, last = g + 16 == g1;
+            if (first | last) {
+                const uint32_t lo = first ? lead : 0u, hi = last ? tail_keep : 16u;
+                uint32_t m;
+                m = byte_range_mask(0, lo, hi); v.x = (v.x & m) | (A & ~m);
+                m = byte_range_mask(1, lo, hi); v.y = (v.y & m) | (A & ~m);
+                m = byte_range_mask(2, lo, hi); v.z = (v.z & m) | (A & ~m);
+                m = byte_range_mask(3, lo, hi); v.w = (v.w & m) | (A & ~m);
+            }
+            special |= swar_special16(v.x, v.y, v.z, v.w) ? 1u : 0u;
         }
-        special |= swar_special16(v.x, v.y, v.z, v.w);
-    }
-    return !special;
+    } else bad_frame = 1;
+    uint32_t bits = bad_frame | (special << 1);
+    #pragma unroll
+    for (int d = 1; d < G; d <<= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, d);
+    return (bits & 1u ? 0u : 1u) | (bits & 2u ? 0u : 2u);
 }
 
-// Thread-per-task copy of n bytes to global memory: 16-byte stores on the destination,
-// 4-byte loads + funnel shift on the (arbitrarily aligned) source.
-__device__ __forceinline__ void thread_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
+// Copy of n bytes to global memory by the G threads of a task: 16-byte stores on the destination
+// (vector v by lane v % G), 4-byte loads + funnel shift on the (arbitrarily aligned) source.
+template <int G>
+__device__ __forceinline__ void group_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int sub) {
     uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
     if (head > n) head = n;
-    for (uint32_t i = 0; i < head; ++i) dst[i] = src[i];
+    if (sub == 0) for (uint32_t i = 0; i < head; ++i) dst[i] = src[i];
     dst += head; src += head; n -= head;
     const uint32_t nvec = n >> 4;
-    if (nvec) {
-        const uint32_t sh = (uint32_t)((uintptr_t)src & 3u), bits = sh * 8;
-        const uint32_t* sw = (const uint32_t*)(src - sh);
-        uint4* dv = (uint4*)dst;
-        uint32_t w0 = sw[0];
-        for (uint32_t v = 0; v < nvec; ++v) {
-            uint32_t w1 = sw[4 * v + 1], w2 = sw[4 * v + 2], w3 = sw[4 * v + 3], w4 = sw[4 * v + 4];  // w4: <= 3 bytes of over-read, inside the buffers' slack
-            uint4 o;
-            o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
-            o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
-            dv[v] = o;
-            w0 = w4;
-        }
+    const uint32_t sh = (uint32_t)((uintptr_t)src & 3u), bits = sh * 8;
+    const uint32_t* sw = (const uint32_t*)(src - sh);
+    uint4* dv = (uint4*)dst;
+    for (uint32_t v = sub; v < nvec; v += G) {
+        const uint32_t* s4 = sw + 4 * v;
+        const uint32_t w0 = s4[0], w1 = s4[1], w2 = s4[2], w3 = s4[3], w4 = s4[4];   // w4: <= 3 bytes of over-read, inside the buffers' slack
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
+        o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
+        dv[v] = o;
     }
-    const uint32_t done = nvec << 4;
-    for (uint32_t i = done; i < n; ++i) dst[i] = src[i];
+    if (sub == G - 1) { const uint32_t done = nvec << 4; for (uint32_t i = done; i < n; ++i) dst[i] = src[i]; }
 }
 
 // ------------------------------------------------------------------ chunk-parallel string transcoding
@@ -203,7 +213,7 @@ __device__ __forceinline__ uint32_t utf8_valid_len(const uint8_t* __restrict__ b
 // First unit boundary at or after `lo`, decided from a bounded neighbourhood of lo. Exact for a
 // body whose escapes are all well-formed; for a malformed body some lane reports !ok and the
 // answer is discarded.
-__device__ inline uint32_t first_unit_start(const uint8_t* __restrict__ b, uint32_t n, uint32_t lo) {
+__device__ __noinline__ uint32_t first_unit_start(const uint8_t* __restrict__ b, uint32_t n, uint32_t lo) {
     if (lo == 0 || lo >= n) return lo;
     // (1) lo is the character after an escape's backslash
     if (bs_run_before(b, lo) & 1u) {
@@ -243,7 +253,7 @@ __device__ inline uint32_t first_unit_start(const uint8_t* __restrict__ b, uint3
 
 // One unit at b[i] (i < n): advances i, returns the code point Go's unquote yields; *ok = false on
 // anything that is not a well-formed JSON string body byte (bad escape, raw control byte, raw '"').
-__device__ inline uint32_t next_unit(const uint8_t* __restrict__ b, uint32_t& i, uint32_t n, bool* ok) {
+__device__ __noinline__ uint32_t next_unit(const uint8_t* __restrict__ b, uint32_t& i, uint32_t n, bool* ok) {
     uint8_t c = b[i];
     if (c == '\\') {
         if (i + 1 >= n) { *ok = false; ++i; return 0; }
@@ -354,23 +364,23 @@ __device__ __forceinline__ void esc_emit(const uint8_t* __restrict__ body, uint3
 constexpr int D2_ESC_SLOTS = 8;          // escaped strings per tile whose per-lane sizes are kept for phase B
 template <int HANDLER>
 struct D2Shared {
-    D2Meta meta;
-    TaskRec rec[D2_THREADS];
-    uint32_t excl_bytes[D2_THREADS];     // exclusive prefix of out_len inside the tile
-    uint32_t excl_cnt[D2_THREADS];       // exclusive prefix of ready inside the tile
-    uint32_t slow_list[D2_THREADS]; uint32_t n_slow;
+    D2Meta meta[D2_STAGES];
+    TaskRec rec[D2_TASKS];
+    uint32_t excl_bytes[D2_TASKS];       // exclusive prefix of out_len inside the tile
+    uint32_t excl_cnt[D2_TASKS];         // exclusive prefix of ready inside the tile
+    uint32_t slow_list[D2_TASKS]; uint32_t n_slow;
     uint32_t esc_info[D2_ESC_SLOTS][32];
     unsigned long long base;
     uint32_t crc_table[HANDLER == 1 ? 256 : 1];
-    alignas(8) uint64_t mbar;
+    alignas(8) uint64_t mbar[D2_STAGES];
 };
 
 // warp 0, step 1: start the loads of a tile's slot words (two tasks per lane); nothing is consumed
 // here, so the latency overlaps whatever the warp does until d2_stage_tile.
 struct D2MetaRegs { uint64_t off[2], hdr[2]; };
 __device__ __forceinline__ void d2_load_meta(const DrainArgs& a, unsigned long long tile, int lane, D2MetaRegs& r) {
-    const uint32_t t0 = (uint32_t)tile * D2_THREADS;
-    const uint32_t nt = min((uint32_t)D2_THREADS, a.n_tasks - t0);
+    const uint32_t t0 = (uint32_t)tile * D2_TASKS;
+    const uint32_t nt = min((uint32_t)D2_TASKS, a.n_tasks - t0);
     #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const uint32_t k = lane + 32 * q;
@@ -386,8 +396,8 @@ __device__ __forceinline__ void d2_load_meta(const DrainArgs& a, unsigned long l
 // warp 0, step 2: decide how to stage the tile and fire the bulk copies
 __device__ inline void d2_stage_tile(const DrainArgs& a, unsigned long long tile, const D2MetaRegs& r, D2Meta& m, uint8_t* buf,
                                      uint32_t in_cap, uint64_t* bar, int lane) {
-    const uint32_t t0 = (uint32_t)tile * D2_THREADS;
-    const uint32_t nt = min((uint32_t)D2_THREADS, a.n_tasks - t0);
+    const uint32_t t0 = (uint32_t)tile * D2_TASKS;
+    const uint32_t nt = min((uint32_t)D2_TASKS, a.n_tasks - t0);
     uint64_t off[2], end[2]; uint32_t len[2]; bool valid[2];
     #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -473,26 +483,8 @@ __device__ inline void d2_stage_tile(const DrainArgs& a, unsigned long long tile
 
 // ---- per-task bodies, inlined once for shared-memory payloads (LDS) and once for global ones ----
 template <int HANDLER>
-__device__ __forceinline__ void d2_phase_a_task(const uint8_t* __restrict__ p, uint32_t len, TaskRec& rec, bool* slow,
-                                                const uint32_t* crc_table) {
-    if (HANDLER == 0) {
-        bool frame_ok;
-        if (quick_clean_framed(p, len, &frame_ok)) {
-            const uint32_t tok = len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
-            if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
-        } else {
-            rec.mode = frame_ok ? OM_STR_PAR : OM_NONE;         // settled in the cooperative pass
-            *slow = true;
-        }
-    } else {
-        Parsed pr = parse_payload(p, len);
-        handler_phase_a(HANDLER, p, pr, rec, crc_table);
-    }
-}
-
 __device__ __forceinline__ void d2_phase_b_task(const uint8_t* __restrict__ p, const TaskRec& rec, uint8_t* __restrict__ o) {
-    if (rec.mode == OM_COPY) thread_copy(o, p + rec.src_off, rec.src_len);
-    else if (rec.mode == OM_VADD) vadd_write(p, rec.src_off, rec.src_len, o);
+    if (rec.mode == OM_VADD) vadd_write(p, rec.src_off, rec.src_len, o);
     else if (rec.mode == OM_U32_DEC || rec.mode == OM_I64_DEC) {
         long long v = rec.value; uint32_t l = rec.out_len;
         if (v < 0) { *o++ = '-'; --l; v = -v; }
@@ -505,85 +497,114 @@ __device__ __forceinline__ void d2_phase_b_task(const uint8_t* __restrict__ p, c
     }
 }
 
+// the sequential validating parser + handler sizing, out of line: rare for identity, and it keeps the
+// hot loops' registers and instruction-cache footprint small
 template <int HANDLER>
-__global__ void __launch_bounds__(D2_THREADS, 8) drain2_kernel(DrainArgs a, uint32_t in_cap) {
+__device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, TaskRec& rec, const uint32_t* crc_table) {
+    Parsed pr = parse_payload(p, len);
+    handler_phase_a(HANDLER, p, pr, rec, crc_table);
+}
+
+template <int HANDLER>
+__global__ void __launch_bounds__(D2Cfg<HANDLER>::THREADS, (HANDLER == 0) ? 4 : 8) drain2_kernel(DrainArgs a, uint32_t in_cap) {
+    constexpr int G = D2Cfg<HANDLER>::G, THREADS = D2Cfg<HANDLER>::THREADS, WARPS = THREADS / 32;
     extern __shared__ __align__(128) uint8_t d2_smem[];
     using Sh = D2Shared<HANDLER>;
     Sh& S = *reinterpret_cast<Sh*>(d2_smem);
-    uint8_t* const sbuf = d2_smem + ((sizeof(Sh) + 127u) & ~127u);      // the stage buffer (+64 bytes of readable slack)
+    uint8_t* const bufs = d2_smem + ((sizeof(Sh) + 127u) & ~127u);
+    const uint32_t buf_stride = (in_cap + 64u + 127u) & ~127u;             // 64 bytes of readable slack behind each stage
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = tid / G, sub = tid % G;                                  // my task inside the tile, my share of it
 
-    if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.n_slow = 0; }
-    if (HANDLER == 1) for (int i = tid; i < 256; i += D2_THREADS) S.crc_table[i] = crc_table_entry(i);
+    if (tid == 0) { mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.n_slow = 0; }
+    if (HANDLER == 1) for (int i = tid; i < 256; i += THREADS) S.crc_table[i] = crc_table_entry(i);
 
-    // warp 0 keeps two tickets ahead of the tile being processed: the slot words of the next tile are
-    // already in registers when its turn comes (no global latency between the end of one tile and the
-    // bulk copy of the next), and the ticket after that is in flight. Holding tickets is harmless: no
+    // warp 0 runs a three-deep software pipeline so that no global latency sits between two block
+    // barriers: ticket(i+3) is being claimed while the slot words of tile i+2 are in flight and the
+    // payload bytes of tile i+1 stream into the other stage. Holding tickets ahead is harmless: no
     // CTA waits on another CTA's unprocessed tile (the byte cursor is an atomic, not a chain).
-    unsigned long long t_cur = ~0ull;      // tile to process next; its slot words are in `mregs`
-    unsigned long long t_raw = ~0ull;      // lane 0: ticket claimed for the tile after t_cur
+    unsigned long long t_meta = ~0ull;     // tile whose slot words are in `mregs`
+    unsigned long long t_raw = ~0ull;      // lane 0: ticket claimed for the tile after t_meta
     D2MetaRegs mregs; mregs.off[0] = mregs.off[1] = mregs.hdr[0] = mregs.hdr[1] = 0;
     if (warp == 0) {
-        if (lane == 0) { t_cur = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
-        t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
-        if (t_cur < a.n_tiles) d2_load_meta(a, t_cur, lane, mregs);
+        unsigned long long t0 = 0, t1 = 0;
+        if (lane == 0) { t0 = atomicAdd(&a.ctl->ticket, 1ull); t1 = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
+        t0 = __shfl_sync(0xffffffffu, t0, 0); t1 = __shfl_sync(0xffffffffu, t1, 0);
+        if (t0 < a.n_tiles) { D2MetaRegs r0; d2_load_meta(a, t0, lane, r0); d2_stage_tile(a, t0, r0, S.meta[0], bufs, in_cap, &S.mbar[0], lane); }
+        else if (lane == 0) S.meta[0].tile = t0;
+        t_meta = t1;
+        if (t_meta < a.n_tiles) d2_load_meta(a, t_meta, lane, mregs);
     }
     __syncthreads();
-    uint32_t parity = 0;
-    D2Meta& M = S.meta;
+    uint32_t stage = 0, parity_bits = 0;   // bit s: phase parity of stage s's mbarrier
 
     for (;;) {
-        if (warp == 0) {
-            if (t_cur < a.n_tiles) d2_stage_tile(a, t_cur, mregs, M, sbuf, in_cap, &S.mbar, lane);
-            else if (lane == 0) M.tile = t_cur;
-            t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
-            if (t_cur < a.n_tiles) d2_load_meta(a, t_cur, lane, mregs);
-            if (lane == 0) t_raw = atomicAdd(&a.ctl->ticket, 1ull);
-        }
-        __syncthreads();                                                   // [1] tile metadata visible
+        D2Meta& M = S.meta[stage];
         const unsigned long long tile = M.tile;
         if (tile >= a.n_tiles) break;
-        const uint32_t nt = M.nt;
-        const uint32_t t0 = (uint32_t)tile * D2_THREADS;
-        const bool staged = M.staged != 0;
-        if (staged) { mbar_wait(&S.mbar, parity); parity ^= 1u; }
-
-        // ---------------- phase A (thread per task) -------------------------------------------------
-        TaskRec rec; rec.ready = 0; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
-        if (tid < (int)nt && M.ready[tid]) {
-            rec.ready = 1;
-            bool slow = false;
-            if (staged) d2_phase_a_task<HANDLER>(sbuf + M.soff[tid], M.len[tid], rec, &slow, S.crc_table);
-            else        d2_phase_a_task<HANDLER>(a.payload + M.goff[tid], M.len[tid], rec, &slow, S.crc_table);
-            if (slow) S.slow_list[atomicAdd(&S.n_slow, 1u)] = (uint32_t)tid;
+        if (warp == 0) {
+            // stage tile i+1 (its slot words were requested one iteration ago) ...
+            if (t_meta < a.n_tiles) d2_stage_tile(a, t_meta, mregs, S.meta[stage ^ 1], bufs + (size_t)(stage ^ 1) * buf_stride, in_cap, &S.mbar[stage ^ 1], lane);
+            else if (lane == 0) S.meta[stage ^ 1].tile = t_meta;
+            // ... request the slot words of tile i+2, claim the ticket of tile i+3
+            t_meta = __shfl_sync(0xffffffffu, t_raw, 0);
+            if (t_meta < a.n_tiles) d2_load_meta(a, t_meta, lane, mregs);
+            if (lane == 0) t_raw = atomicAdd(&a.ctl->ticket, 1ull);
         }
-        S.rec[tid] = rec;
-        __syncthreads();                                                   // [2] records + slow list complete
+        const uint32_t nt = M.nt;
+        const uint32_t t0 = (uint32_t)tile * D2_TASKS;
+        const bool staged = M.staged != 0;
+        const uint8_t* const sbuf = bufs + (size_t)stage * buf_stride;
+        if (staged) { mbar_wait(&S.mbar[stage], (parity_bits >> stage) & 1u); parity_bits ^= 1u << stage; }
+
+        // ---------------- phase A: G threads per task ------------------------------------------------
+        const bool mine = k < (int)nt && M.ready[k];
+        const uint32_t my_len = mine ? M.len[k] : 0u;
+        TaskRec rec; rec.ready = mine; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
+        if (HANDLER == 0) {
+            uint32_t q;
+            if (staged) q = quick_clean_framed<G>(sbuf + (mine ? M.soff[k] : 0u), my_len, sub, mine);
+            else        q = quick_clean_framed<G>(a.payload + (mine ? M.goff[k] : 0ull), my_len, sub, mine);
+            if (mine) {
+                if (q == 3u) {
+                    const uint32_t tok = my_len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
+                    if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
+                } else {
+                    rec.mode = (q & 1u) ? OM_STR_PAR : OM_NONE;          // settled in the cooperative pass
+                    if (sub == 0) S.slow_list[atomicAdd(&S.n_slow, 1u)] = (uint32_t)k;
+                }
+            }
+        } else if (mine) {
+            const uint8_t* p = staged ? (const uint8_t*)(sbuf + M.soff[k]) : a.payload + M.goff[k];
+            d2_parse_and_size<HANDLER>(p, my_len, rec, S.crc_table);
+        }
+        if (sub == 0 && k < D2_TASKS) S.rec[k] = rec;
+        __syncthreads();                                                   // [1] records + slow list complete
         // ---------------- phase A, cooperative pass over the tasks the quick look could not settle --
         const uint32_t ns = (HANDLER == 0) ? S.n_slow : 0u;
         if (ns) {
-            for (uint32_t s = warp; s < ns; s += D2_WARPS) {
-                const uint32_t k = S.slow_list[s];
-                const uint32_t len = M.len[k];
-                TaskRec r2 = S.rec[k];
+            for (uint32_t s = warp; s < ns; s += WARPS) {
+                const uint32_t ks = S.slow_list[s];
+                const uint32_t len = M.len[ks];
+                TaskRec r2 = S.rec[ks];
                 bool done = false;
                 if (r2.mode == OM_STR_PAR) {                               // canonical frame, body needs transcoding
                     uint32_t ol;
                     const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
                     uint32_t* info = s < D2_ESC_SLOTS ? S.esc_info[s] : nullptr;
-                    const bool ok = staged ? esc_measure(sbuf + M.soff[k] + FRAME_PRE_LEN, n, lane, &ol, info)
-                                           : esc_measure(a.payload + M.goff[k] + FRAME_PRE_LEN, n, lane, &ol, info);
+                    const bool ok = staged ? esc_measure(sbuf + M.soff[ks] + FRAME_PRE_LEN, n, lane, &ol, info)
+                                           : esc_measure(a.payload + M.goff[ks] + FRAME_PRE_LEN, n, lane, &ol, info);
                     if (ok) { r2.has = 1; r2.src_off = FRAME_PRE_LEN; r2.src_len = n; r2.out_len = ol; done = true; }
                 }
                 if (!done && lane == 0) {
-                    const uint8_t* p = staged ? (const uint8_t*)(sbuf + M.soff[k]) : a.payload + M.goff[k];
-                    Parsed pr = parse_payload(p, len);
-                    handler_phase_a(0, p, pr, r2, nullptr);
+                    const uint8_t* p = staged ? (const uint8_t*)(sbuf + M.soff[ks]) : a.payload + M.goff[ks];
+                    r2.mode = OM_NONE; r2.has = 0; r2.out_len = 0;
+                    d2_parse_and_size<0>(p, len, r2, nullptr);
                     r2.ready = 1;
                 }
-                if (lane == 0) S.rec[k] = r2;
+                if (lane == 0) S.rec[ks] = r2;
             }
-            __syncthreads();                                               // [3] slow tasks sized
+            __syncthreads();                                               // [2] slow tasks sized
         }
 
         // ---------------- compaction (ballot) + sizes (scan) + ONE cursor add, all in warp 0 ---------
@@ -601,39 +622,47 @@ __global__ void __launch_bounds__(D2_THREADS, 8) drain2_kernel(DrainArgs a, uint
                 const unsigned long long base = tb ? atomicAdd(&a.ctl->bytes, (unsigned long long)tb) : 0ull;
                 S.base = base;
                 if (base + tb > a.out_cap) { a.ctl->overflow = 1u; S.base = ~0ull; }
-                S.n_slow = 0;                                              // for the next tile (read again only after [1])
+                S.n_slow = 0;                                              // for the next tile (touched again only after [4])
             }
         }
-        __syncthreads();                                                   // [4] offsets known
+        __syncthreads();                                                   // [3] offsets known
         const unsigned long long base_bytes = S.base;
         const bool fits = base_bytes != ~0ull;
         const uint32_t base_cnt = M.base_cnt;
 
-        // ---------------- phase B (thread per task) -------------------------------------------------
-        if (rec.ready) {
-            rec = S.rec[tid];                                              // the cooperative pass may have rewritten it
-            const uint32_t slot = (uint32_t)((a.first_task + t0 + tid) & a.slot_mask);
-            const uint32_t j = base_cnt + S.excl_cnt[tid];
-            const uint64_t ob = base_bytes + S.excl_bytes[tid];
-            a.out_off[j] = fits ? ob : 0; a.out_len[j] = rec.out_len; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
-            if (rec.has && fits && rec.mode != OM_STR_PAR) {
-                if (staged) d2_phase_b_task(sbuf + M.soff[tid], rec, a.out_payload + ob);
-                else        d2_phase_b_task(a.payload + M.goff[tid], rec, a.out_payload + ob);
+        // ---------------- phase B: G threads per task ------------------------------------------------
+        if (mine) {
+            if (ns) rec = S.rec[k];                                        // the cooperative pass may have rewritten it
+            const uint64_t ob = base_bytes + S.excl_bytes[k];
+            if (sub == 0) {
+                const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
+                const uint32_t j = base_cnt + S.excl_cnt[k];
+                a.out_off[j] = fits ? ob : 0; a.out_len[j] = rec.out_len; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
+            }
+            if (rec.has && fits) {
+                if (rec.mode == OM_COPY) {
+                    if (staged) group_copy<G>(a.out_payload + ob, sbuf + M.soff[k] + rec.src_off, rec.src_len, sub);
+                    else        group_copy<G>(a.out_payload + ob, a.payload + M.goff[k] + rec.src_off, rec.src_len, sub);
+                } else if (sub == 0 && rec.mode != OM_STR_PAR) {
+                    const uint8_t* p = staged ? (const uint8_t*)(sbuf + M.soff[k]) : a.payload + M.goff[k];
+                    d2_phase_b_task<HANDLER>(p, rec, a.out_payload + ob);
+                }
             }
         }
         // ---------------- phase B, cooperative: transcode the escaped strings -----------------------
         if (ns && fits) {
-            for (uint32_t s = warp; s < ns; s += D2_WARPS) {
-                const uint32_t k = S.slow_list[s];
-                const TaskRec r2 = S.rec[k];
+            for (uint32_t s = warp; s < ns; s += WARPS) {
+                const uint32_t ks = S.slow_list[s];
+                const TaskRec r2 = S.rec[ks];
                 if (r2.mode != OM_STR_PAR || !r2.has) continue;
                 const uint32_t* info = s < D2_ESC_SLOTS ? S.esc_info[s] : nullptr;
-                uint8_t* o = a.out_payload + base_bytes + S.excl_bytes[k];
-                if (staged) esc_emit(sbuf + M.soff[k] + r2.src_off, r2.src_len, lane, o, info);
-                else        esc_emit(a.payload + M.goff[k] + r2.src_off, r2.src_len, lane, o, info);
+                uint8_t* o = a.out_payload + base_bytes + S.excl_bytes[ks];
+                if (staged) esc_emit(sbuf + M.soff[ks] + r2.src_off, r2.src_len, lane, o, info);
+                else        esc_emit(a.payload + M.goff[ks] + r2.src_off, r2.src_len, lane, o, info);
             }
         }
-        __syncthreads();                                                   // [5] stage buffer, records, metadata free again
+        __syncthreads();                                                   // [4] stage buffer, records, metadata free again
+        stage ^= 1u;
     }
 }
 

@@ -385,7 +385,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
     CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));
     int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
-    // two stage buffers per CTA, each sized for the window's average tile: 64 tasks x 1.1 + 2 KiB, within [4 KiB, 100 KiB].
+    // one stage buffer per CTA, sized for the window's average tile: 64 tasks x 1.1 + 2 KiB, within [4 KiB, 100 KiB].
     // Tiles that do not fit are processed straight from global memory (same code, slower loads).
     uint32_t in_cap = (uint32_t)std::min<uint64_t>(100u << 10, std::max<uint64_t>(4u << 10, (in_bytes * D2_THREADS / n) * 11 / 10 + 2048));
     in_cap = (in_cap + 511u) & ~511u;

@@ -32,11 +32,12 @@ namespace b9 {
 
 constexpr int D2_TASKS   = 64;               // tasks per tile
 constexpr int D2_THREADS = D2_TASKS;         // (host code sizes tiles with this name)
-constexpr int D2_STAGES  = 2;
-// G threads share one task (G = 4 for the identity kernel: a 284-byte payload is 18 sixteen-byte
-// groups, 4-5 per thread; four times the warps per byte of staged payload hide the latencies that a
-// thread-per-task layout, capped at ~16 warps/SM by its shared-memory footprint, cannot).
-template <int HANDLER> struct D2Cfg { static constexpr int G = (HANDLER == 0) ? 4 : 1; static constexpr int THREADS = D2_TASKS * G; };
+constexpr int D2_STAGES  = 1;
+// G threads share one task. Shared memory caps the TASKS resident on an SM (~900 for 284-byte
+// payloads, one stage); thread-per-task would stop at ~16-25 warps/SM, too few to cover the
+// shared-memory, atomic and barrier latencies (profiles/r1_v2c_*). G = 2 doubles the warps for the
+// same bytes; G = 4 with two stages was slower (8-warp CTAs idling at block barriers, r1_v2d_*).
+template <int HANDLER> struct D2Cfg { static constexpr int G = (HANDLER == 0) ? 2 : 1; static constexpr int THREADS = D2_TASKS * G; };
 
 // ------------------------------------------------------------------ PTX: mbarrier + bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,13 +149,34 @@ __device__ __forceinline__ uint32_t quick_clean_framed(const uint8_t* __restrict
     return (bits & 1u ? 0u : 1u) | (bits & 2u ? 0u : 2u);
 }
 
+// up to 15 bytes, destination alignment known to allow the 1/2/4/8-byte ladder used by the callers
+__device__ __forceinline__ void copy_small_up(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
+    // dst + n is 16-byte aligned (head of a copy): ascending sizes keep every store naturally aligned
+    uint32_t i = 0;
+    if (n & 1u) { dst[0] = src[0]; i = 1; }
+    if (n & 2u) { *(uint16_t*)(dst + i) = (uint16_t)(src[i] | (src[i + 1] << 8)); i += 2; }
+    if (n & 4u) { *(uint32_t*)(dst + i) = ld_u32_unaligned(src + i); i += 4; }
+    if (n & 8u) { *(uint2*)(dst + i) = make_uint2(ld_u32_unaligned(src + i), ld_u32_unaligned(src + i + 4)); }
+}
+__device__ __forceinline__ void copy_small_down(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
+    // dst is 16-byte aligned (tail of a copy): descending sizes
+    uint32_t i = 0;
+    if (n & 8u) { *(uint2*)(dst) = make_uint2(ld_u32_unaligned(src), ld_u32_unaligned(src + 4)); i = 8; }
+    if (n & 4u) { *(uint32_t*)(dst + i) = ld_u32_unaligned(src + i); i += 4; }
+    if (n & 2u) { *(uint16_t*)(dst + i) = (uint16_t)(src[i] | (src[i + 1] << 8)); i += 2; }
+    if (n & 1u) dst[i] = src[i];
+}
+
 // Copy of n bytes to global memory by the G threads of a task: 16-byte stores on the destination
 // (vector v by lane v % G), 4-byte loads + funnel shift on the (arbitrarily aligned) source.
 template <int G>
 __device__ __forceinline__ void group_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int sub) {
     uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
-    if (head > n) head = n;
-    if (sub == 0) for (uint32_t i = 0; i < head; ++i) dst[i] = src[i];
+    if (head > n) {                                              // tiny copy that never reaches an aligned vector
+        if (sub == 0) for (uint32_t i = 0; i < n; ++i) dst[i] = src[i];
+        return;
+    }
+    if (sub == 0) copy_small_up(dst, src, head);
     dst += head; src += head; n -= head;
     const uint32_t nvec = n >> 4;
     const uint32_t sh = (uint32_t)((uintptr_t)src & 3u), bits = sh * 8;
@@ -168,7 +190,7 @@ __device__ __forceinline__ void group_copy(uint8_t* __restrict__ dst, const uint
         o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
         dv[v] = o;
     }
-    if (sub == G - 1) { const uint32_t done = nvec << 4; for (uint32_t i = done; i < n; ++i) dst[i] = src[i]; }
+    if (sub == G - 1) { const uint32_t done = nvec << 4; copy_small_down(dst + done, src + done, n - done); }
 }
 
 // ------------------------------------------------------------------ chunk-parallel string transcoding
@@ -506,7 +528,7 @@ __device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, T
 }
 
 template <int HANDLER>
-__global__ void __launch_bounds__(D2Cfg<HANDLER>::THREADS, (HANDLER == 0) ? 4 : 8) drain2_kernel(DrainArgs a, uint32_t in_cap) {
+__global__ void __launch_bounds__(D2Cfg<HANDLER>::THREADS, 8) drain2_kernel(DrainArgs a, uint32_t in_cap) {
     constexpr int G = D2Cfg<HANDLER>::G, THREADS = D2Cfg<HANDLER>::THREADS, WARPS = THREADS / 32;
     extern __shared__ __align__(128) uint8_t d2_smem[];
     using Sh = D2Shared<HANDLER>;
@@ -516,46 +538,42 @@ __global__ void __launch_bounds__(D2Cfg<HANDLER>::THREADS, (HANDLER == 0) ? 4 : 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = tid / G, sub = tid % G;                                  // my task inside the tile, my share of it
 
-    if (tid == 0) { mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.n_slow = 0; }
+    if (tid == 0) { mbar_init(&S.mbar[0], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.n_slow = 0; }
     if (HANDLER == 1) for (int i = tid; i < 256; i += THREADS) S.crc_table[i] = crc_table_entry(i);
 
-    // warp 0 runs a three-deep software pipeline so that no global latency sits between two block
-    // barriers: ticket(i+3) is being claimed while the slot words of tile i+2 are in flight and the
-    // payload bytes of tile i+1 stream into the other stage. Holding tickets ahead is harmless: no
+    // warp 0 keeps two tickets ahead of the tile being processed: the slot words of the next tile are
+    // already in registers when its turn comes (no global latency between the end of one tile and the
+    // bulk copy of the next), and the ticket after that is in flight. Holding tickets is harmless: no
     // CTA waits on another CTA's unprocessed tile (the byte cursor is an atomic, not a chain).
-    unsigned long long t_meta = ~0ull;     // tile whose slot words are in `mregs`
-    unsigned long long t_raw = ~0ull;      // lane 0: ticket claimed for the tile after t_meta
+    unsigned long long t_cur = ~0ull;      // tile to process next; its slot words are in `mregs`
+    unsigned long long t_raw = ~0ull;      // lane 0: ticket claimed for the tile after t_cur
     D2MetaRegs mregs; mregs.off[0] = mregs.off[1] = mregs.hdr[0] = mregs.hdr[1] = 0;
     if (warp == 0) {
-        unsigned long long t0 = 0, t1 = 0;
-        if (lane == 0) { t0 = atomicAdd(&a.ctl->ticket, 1ull); t1 = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
-        t0 = __shfl_sync(0xffffffffu, t0, 0); t1 = __shfl_sync(0xffffffffu, t1, 0);
-        if (t0 < a.n_tiles) { D2MetaRegs r0; d2_load_meta(a, t0, lane, r0); d2_stage_tile(a, t0, r0, S.meta[0], bufs, in_cap, &S.mbar[0], lane); }
-        else if (lane == 0) S.meta[0].tile = t0;
-        t_meta = t1;
-        if (t_meta < a.n_tiles) d2_load_meta(a, t_meta, lane, mregs);
+        if (lane == 0) { t_cur = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
+        t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
+        if (t_cur < a.n_tiles) d2_load_meta(a, t_cur, lane, mregs);
     }
     __syncthreads();
-    uint32_t stage = 0, parity_bits = 0;   // bit s: phase parity of stage s's mbarrier
+    uint32_t parity = 0;
+    const uint32_t stage = 0;
+    D2Meta& M = S.meta[0];
 
     for (;;) {
-        D2Meta& M = S.meta[stage];
-        const unsigned long long tile = M.tile;
-        if (tile >= a.n_tiles) break;
         if (warp == 0) {
-            // stage tile i+1 (its slot words were requested one iteration ago) ...
-            if (t_meta < a.n_tiles) d2_stage_tile(a, t_meta, mregs, S.meta[stage ^ 1], bufs + (size_t)(stage ^ 1) * buf_stride, in_cap, &S.mbar[stage ^ 1], lane);
-            else if (lane == 0) S.meta[stage ^ 1].tile = t_meta;
-            // ... request the slot words of tile i+2, claim the ticket of tile i+3
-            t_meta = __shfl_sync(0xffffffffu, t_raw, 0);
-            if (t_meta < a.n_tiles) d2_load_meta(a, t_meta, lane, mregs);
+            if (t_cur < a.n_tiles) d2_stage_tile(a, t_cur, mregs, M, bufs, in_cap, &S.mbar[0], lane);
+            else if (lane == 0) M.tile = t_cur;
+            t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
+            if (t_cur < a.n_tiles) d2_load_meta(a, t_cur, lane, mregs);
             if (lane == 0) t_raw = atomicAdd(&a.ctl->ticket, 1ull);
         }
+        __syncthreads();                                                   // [0] tile metadata visible
+        const unsigned long long tile = M.tile;
+        if (tile >= a.n_tiles) break;
         const uint32_t nt = M.nt;
         const uint32_t t0 = (uint32_t)tile * D2_TASKS;
         const bool staged = M.staged != 0;
         const uint8_t* const sbuf = bufs + (size_t)stage * buf_stride;
-        if (staged) { mbar_wait(&S.mbar[stage], (parity_bits >> stage) & 1u); parity_bits ^= 1u << stage; }
+        if (staged) { mbar_wait(&S.mbar[0], parity); parity ^= 1u; }
 
         // ---------------- phase A: G threads per task ------------------------------------------------
         const bool mine = k < (int)nt && M.ready[k];
@@ -662,7 +680,6 @@ __global__ void __launch_bounds__(D2Cfg<HANDLER>::THREADS, (HANDLER == 0) ? 4 : 
             }
         }
         __syncthreads();                                                   // [4] stage buffer, records, metadata free again
-        stage ^= 1u;
     }
 }
 

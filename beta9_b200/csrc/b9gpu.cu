@@ -120,24 +120,31 @@ template <int H> cudaError_t launch_drain(const DrainArgs& a, int grid, cudaStre
     return cudaGetLastError();
 }
 
-// v2: bulk-copy staged tiles. Dynamic shared memory = control block + 2 stage buffers of in_cap (+slack).
-template <int H> size_t drain2_smem_bytes(uint32_t in_cap) {
-    const size_t ctl = (sizeof(D2Shared<H>) + 127u) & ~(size_t)127u;
-    const size_t stride = ((size_t)in_cap + 64u + 127u) & ~(size_t)127u;
-    return ctl + D2_STAGES * stride;
+// v2 (warp-autonomous): every warp owns a slice of dynamic shared memory = control block + one stage buffer.
+template <int H> uint32_t drain3_warp_stride(uint32_t in_cap) {
+    const size_t ctl = (sizeof(D3Warp<D3Cfg<H>::T>) + 127u) & ~(size_t)127u;
+    return (uint32_t)(ctl + (((size_t)in_cap + 64u + 127u) & ~(size_t)127u));
 }
-template <int H> cudaError_t launch_drain2(DrainArgs a, uint32_t in_cap, int sm_count, cudaStream_t s, int* grid_out) {
-    const size_t smem = drain2_smem_bytes<H>(in_cap);
-    cudaError_t e = cudaFuncSetAttribute(drain2_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes, uint32_t cap_override, int sm_count, cudaStream_t s, int* grid_out) {
+    constexpr int T = D3Cfg<H>::T;
+    // stage buffer per warp sized for the window's average warp-tile: T tasks x 1.1 + 768 B, within [1 KiB, 48 KiB].
+    // Tiles that do not fit are processed straight from global memory (same code, generic loads).
+    uint32_t in_cap = (uint32_t)std::min<uint64_t>(48u << 10, std::max<uint64_t>(1u << 10, avg_task_bytes * T * 11 / 10 + 768));
+    in_cap = (in_cap + 127u) & ~127u;
+    if (cap_override) in_cap = cap_override;
+    const uint32_t stride = drain3_warp_stride<H>(in_cap);
+    const size_t smem = (size_t)stride * D3_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(drain3_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drain2_kernel<H>, D2Cfg<H>::THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drain3_kernel<H>, D3_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    a.n_tiles = (a.n_tasks + D2_THREADS - 1) / D2_THREADS;
-    const int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)(per_sm * sm_count));
+    a.n_tiles = (a.n_tasks + T - 1) / T;
+    const uint32_t ctas_needed = (a.n_tiles + D3_WARPS - 1) / D3_WARPS;
+    const int grid = (int)std::min<uint32_t>(ctas_needed, (uint32_t)(per_sm * sm_count));
     *grid_out = grid;
-    drain2_kernel<H><<<grid, D2Cfg<H>::THREADS, smem, s>>>(a, in_cap);
+    drain3_kernel<H><<<grid, D3_WARPS * 32, smem, s>>>(a, in_cap, stride);
     return cudaGetLastError();
 }
 
@@ -381,23 +388,18 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     a.count_mode = c->cancelled_pending ? 1u : 0u;
     cudaStream_t s = c->stream;
     const bool v2 = c->drain_version == 2;
-    if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;
+    if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;     // upper bound over the handlers' warp-tile sizes (state array memset)
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
     CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));
     int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
-    // one stage buffer per CTA, sized for the window's average tile: 64 tasks x 1.1 + 2 KiB, within [4 KiB, 100 KiB].
-    // Tiles that do not fit are processed straight from global memory (same code, slower loads).
-    uint32_t in_cap = (uint32_t)std::min<uint64_t>(100u << 10, std::max<uint64_t>(4u << 10, (in_bytes * D2_THREADS / n) * 11 / 10 + 2048));
-    in_cap = (in_cap + 511u) & ~511u;
-    if (c->stage_bytes_override) in_cap = c->stage_bytes_override;
     CU(cudaEventRecord(c->ev_a, s));
     cudaError_t le;
     if (v2) {
         switch (handler) {
-        case B9_H_IDENTITY: le = launch_drain2<0>(a, in_cap, c->sm_count, s, &grid); break;
-        case B9_H_CRC32:    le = launch_drain2<1>(a, in_cap, c->sm_count, s, &grid); break;
-        case B9_H_VADD_F32: le = launch_drain2<2>(a, in_cap, c->sm_count, s, &grid); break;
-        default:            le = launch_drain2<3>(a, in_cap, c->sm_count, s, &grid); break;
+        case B9_H_IDENTITY: le = launch_drain3<0>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
+        case B9_H_CRC32:    le = launch_drain3<1>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
+        case B9_H_VADD_F32: le = launch_drain3<2>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
+        default:            le = launch_drain3<3>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
         }
     } else switch (handler) {
     case B9_H_IDENTITY: le = launch_drain<0>(a, grid, s); break;
@@ -412,7 +414,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     CU(cudaStreamSynchronize(s));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
     c->stats.last_drain_kernel_ms = ms;
-    c->stats.last_drain_tiles = a.n_tiles;
+    c->stats.last_drain_tiles = (n + 127) / 128;   // (reported in units of 128 tasks)
     c->stats.drains++;
     if (c->h_ctl->overflow)
         return fail(B9_ENOSPC, "b9_drain_launch: results exceed max_result_bytes (%llu); drain fewer tasks or enlarge the staging",

@@ -1,22 +1,22 @@
-// drain kernel v2 — the production drain.
+// drain kernel v2 — the production drain (kernel `drain3_kernel` at the bottom of this file).
 //
-// Persistent CTAs, ticket work stealing and ballot compaction as in v1 (drain_kernel.cuh), with the
-// data path rebuilt around the B200 memory system and the inter-CTA ordering chain removed:
+// Persistent workers, ticket work stealing and ballot compaction as in v1 (drain_kernel.cuh), with
+// the data path rebuilt around the B200 memory system and every inter-worker dependency removed:
 //
+//   * the worker is a WARP: own ticket pipeline, own slice of shared memory, own mbarrier, own
+//     cursor add; no block barrier in the loop;
+//   * a warp-tile's payload bytes are ONE contiguous range of the ring in the common case; lane 0
+//     pulls it into the warp's stage buffer with a single bulk async copy (cp.async.bulk / TMA 1-D,
+//     completion on the warp's mbarrier);
+//   * G lanes share a task (G = 2 for identity): 16-byte shared loads, SWAR classification of the
+//     string body, 16-byte global stores;
 //   * result RECORDS (id, status, has, offset, length) are FIFO-dense: record j belongs to the j-th
 //     ready task. When no pending task is cancelled (the host knows) j is plain arithmetic on the
-//     ticket; otherwise the per-tile ready counts — known from the slot words alone, long before
-//     the tile is processed — go through a decoupled look-back;
-//   * result BYTES are placed by ONE atomicAdd per tile on a byte cursor: dense, but in completion
-//     order. (v1 chained the byte prefix through an in-order look-back; ncu showed the whole grid
-//     falling into lockstep behind it, 32 tiles resolved per L2 round trip — profiles/r1_v2a_*.)
-//
-//   * a tile's payload bytes are ONE contiguous range of the ring in the common case; warp 0 pulls
-//     it into shared memory with a single bulk async copy (cp.async.bulk / TMA 1-D, completion on
-//     an mbarrier), double buffered so the next tile streams in while this one is processed;
-//   * phase A and B are thread-per-task over the staged bytes (16-byte shared loads, SWAR
-//     classification of the string body, 16-byte global stores): small uniform tasks keep all 32
-//     lanes busy, which a warp-per-task layout cannot (a 284-byte task fills 18 of 32 lanes);
+//     ticket; otherwise the per-tile ready counts — known from the slot words alone — go through a
+//     decoupled look-back;
+//   * result BYTES are placed by ONE atomicAdd per warp-tile on a byte cursor: dense, but in
+//     completion order (v1 chained the byte prefix through an in-order look-back; ncu showed the
+//     whole grid in lockstep behind it, 32 tiles resolved per L2 round trip — profiles/r1_v2a_*);
 //   * strings with escapes / non-ASCII (the 1 % "adversarial" share, and most of configs[2]) are
 //     NOT walked by one lane: the warp splits the body into 32 chunks, every lane finds its first
 //     code-unit boundary by a bounded look-behind and transcodes its chunk (esc_* below);
@@ -29,15 +29,6 @@
 #include "drain_kernel.cuh"
 
 namespace b9 {
-
-constexpr int D2_TASKS   = 64;               // tasks per tile
-constexpr int D2_THREADS = D2_TASKS;         // (host code sizes tiles with this name)
-constexpr int D2_STAGES  = 1;
-// G threads share one task. Shared memory caps the TASKS resident on an SM (~900 for 284-byte
-// payloads, one stage); thread-per-task would stop at ~16-25 warps/SM, too few to cover the
-// shared-memory, atomic and barrier latencies (profiles/r1_v2c_*). G = 2 doubles the warps for the
-// same bytes; G = 4 with two stages was slower (8-warp CTAs idling at block barriers, r1_v2d_*).
-template <int HANDLER> struct D2Cfg { static constexpr int G = (HANDLER == 0) ? 2 : 1; static constexpr int THREADS = D2_TASKS * G; };
 
 // ------------------------------------------------------------------ PTX: mbarrier + bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,19 +50,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-
-// ------------------------------------------------------------------ per-stage tile metadata
-struct D2Meta {
-    uint64_t goff[D2_TASKS];     // physical ring offset of each task's payload
-    uint32_t soff[D2_TASKS];     // offset inside the stage buffer (when staged)
-    uint32_t len[D2_TASKS];
-    uint8_t  ready[D2_TASKS];
-    unsigned long long tile;
-    uint32_t nt;
-    uint32_t staged;               // 1: payload bytes are (arriving) in shared memory; 0: read from global
-    uint32_t base_cnt;             // records of all earlier tiles (index of this tile's first record)
-    uint32_t ready_cnt;            // ready tasks in this tile
-};
 
 // ------------------------------------------------------------------ SWAR classification
 // any byte of the four words outside printable ASCII, or equal to '"' or '\\'?
@@ -331,7 +309,7 @@ __device__ __forceinline__ bool plain_byte(uint32_t c) { return c >= 0x20u && c 
 // as  (run of plain bytes)* (one escape / UTF-8 unit)  so that the branchy unit decoder runs once
 // per round for the whole warp. `lane_info` (optional, shared memory, 32 words) keeps each lane's
 // first-unit offset and output length for esc_emit.
-__device__ __forceinline__ bool esc_measure(const uint8_t* __restrict__ body, uint32_t n, int lane, uint32_t* out_len, uint32_t* lane_info) {
+__device__ __noinline__ bool esc_measure(const uint8_t* __restrict__ body, uint32_t n, int lane, uint32_t* out_len, uint32_t* lane_info) {
     const uint32_t S = (n + 31u) / 32u;
     const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
     bool ok = true;
@@ -353,7 +331,7 @@ __device__ __forceinline__ bool esc_measure(const uint8_t* __restrict__ body, ui
 }
 
 // Warp-cooperative: write json.dumps(body) to dst (global). Only called after esc_measure said ok.
-__device__ __forceinline__ void esc_emit(const uint8_t* __restrict__ body, uint32_t n, int lane, uint8_t* __restrict__ dst, const uint32_t* lane_info) {
+__device__ __noinline__ void esc_emit(const uint8_t* __restrict__ body, uint32_t n, int lane, uint8_t* __restrict__ dst, const uint32_t* lane_info) {
     const uint32_t S = (n + 31u) / 32u;
     const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
     bool ok = true;
@@ -383,127 +361,85 @@ __device__ __forceinline__ void esc_emit(const uint8_t* __restrict__ body, uint3
 }
 
 // ------------------------------------------------------------------ the kernel
-constexpr int D2_ESC_SLOTS = 8;          // escaped strings per tile whose per-lane sizes are kept for phase B
-template <int HANDLER>
-struct D2Shared {
-    D2Meta meta[D2_STAGES];
-    TaskRec rec[D2_TASKS];
-    uint32_t excl_bytes[D2_TASKS];       // exclusive prefix of out_len inside the tile
-    uint32_t excl_cnt[D2_TASKS];         // exclusive prefix of ready inside the tile
-    uint32_t slow_list[D2_TASKS]; uint32_t n_slow;
-    uint32_t esc_info[D2_ESC_SLOTS][32];
-    unsigned long long base;
-    uint32_t crc_table[HANDLER == 1 ? 256 : 1];
-    alignas(8) uint64_t mbar[D2_STAGES];
+// ================================================================== the kernel: warp-autonomous
+// Every WARP is an independent worker with its own ticket pipeline, its own slice of shared memory
+// (slot metadata + one stage buffer + one mbarrier) and its own cursor add. There is no block
+// barrier anywhere in the loop: while one warp waits for its bulk copy or its atomic, the other
+// ~27 warps of the SM are in their compute phases. (The CTA-per-tile versions spent most of their
+// time at __syncthreads behind warp 0's staging, the cursor atomic and the escaped-string pass:
+// profiles/r1_v2c/v2d/v2e.)
+constexpr int D3_WARPS = 4;                  // warps per CTA (a container only)
+template <int HANDLER> struct D3Cfg {
+    static constexpr int G = (HANDLER == 0) ? 2 : 1;      // threads per task
+    static constexpr int T = 32 / G;                      // tasks per warp-tile
+};
+constexpr int D2_THREADS = 16;               // host: tasks per look-back slot (smallest warp-tile)
+
+template <int T>
+struct D3Warp {
+    uint64_t goff[T];              // physical ring offset of each task's payload
+    uint32_t soff[T];              // offset inside the stage buffer (when staged)
+    uint32_t len[T];
+    uint32_t esc_info[2][32];      // per-lane chunk sizes of up to two escaped strings (phase A -> phase B)
+    alignas(8) uint64_t mbar;
 };
 
-// warp 0, step 1: start the loads of a tile's slot words (two tasks per lane); nothing is consumed
-// here, so the latency overlaps whatever the warp does until d2_stage_tile.
-struct D2MetaRegs { uint64_t off[2], hdr[2]; };
-__device__ __forceinline__ void d2_load_meta(const DrainArgs& a, unsigned long long tile, int lane, D2MetaRegs& r) {
-    const uint32_t t0 = (uint32_t)tile * D2_TASKS;
-    const uint32_t nt = min((uint32_t)D2_TASKS, a.n_tasks - t0);
-    #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const uint32_t k = lane + 32 * q;
-        r.off[q] = 0; r.hdr[q] = 0;
-        if (k < nt) {
-            const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
-            r.hdr[q] = __ldg(a.hdr + slot);
-            r.off[q] = __ldg(a.off + slot);
-        }
+struct D3MetaRegs { uint64_t off, hdr; };
+template <int T>
+__device__ __forceinline__ void d3_load_meta(const DrainArgs& a, unsigned long long tile, int lane, D3MetaRegs& r) {
+    const uint32_t t0 = (uint32_t)tile * T;
+    r.off = 0; r.hdr = 0;
+    if (lane < T && t0 + lane < a.n_tasks) {
+        const uint32_t slot = (uint32_t)((a.first_task + t0 + lane) & a.slot_mask);
+        r.hdr = __ldg(a.hdr + slot);
+        r.off = __ldg(a.off + slot);
     }
 }
 
-// warp 0, step 2: decide how to stage the tile and fire the bulk copies
-__device__ inline void d2_stage_tile(const DrainArgs& a, unsigned long long tile, const D2MetaRegs& r, D2Meta& m, uint8_t* buf,
-                                     uint32_t in_cap, uint64_t* bar, int lane) {
-    const uint32_t t0 = (uint32_t)tile * D2_TASKS;
-    const uint32_t nt = min((uint32_t)D2_TASKS, a.n_tasks - t0);
-    uint64_t off[2], end[2]; uint32_t len[2]; bool valid[2];
-    #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const uint32_t k = lane + 32 * q;
-        valid[q] = k < nt;
-        off[q] = r.off[q]; len[q] = valid[q] ? hdr_len(r.hdr[q]) : 0u;
-        if (valid[q]) { m.goff[k] = off[q]; m.len[k] = len[q]; m.ready[k] = !(hdr_flags(r.hdr[q]) & 1u); }
-        end[q] = off[q] + len[q];
-    }
-    // contiguous?  task k starts where task k-1 ended
-    uint64_t prev0 = __shfl_up_sync(0xffffffffu, end[0], 1);
-    uint64_t prev1 = __shfl_up_sync(0xffffffffu, end[1], 1);
-    const uint64_t end0_last = __shfl_sync(0xffffffffu, end[0], 31);
-    if (lane == 0) { prev0 = off[0]; prev1 = end0_last; }
-    bool contig = (!valid[0] || off[0] == prev0) && (!valid[1] || off[1] == prev1);
-    contig = __all_sync(0xffffffffu, contig);
-    const uint64_t gs = __shfl_sync(0xffffffffu, off[0], 0);
-    const uint32_t last = nt - 1;
-    const uint64_t ge0 = __shfl_sync(0xffffffffu, end[0], last & 31), ge1 = __shfl_sync(0xffffffffu, end[1], last & 31);
-    const uint64_t ge = (last < 32) ? ge0 : ge1;
-    uint32_t staged = 0;
-    if (contig) {
-        const uint64_t as = gs & ~15ull;
-        const uint64_t bytes = ((ge + 15ull) & ~15ull) - as;
-        if (bytes <= in_cap) {
-            staged = 1;
-            #pragma unroll
-            for (int q = 0; q < 2; ++q) if (valid[q]) m.soff[lane + 32 * q] = (uint32_t)(off[q] - as);
-            if (lane == 0) {
-                mbar_expect_tx(bar, (uint32_t)bytes);
-                if (bytes) bulk_g2s(buf, a.payload + as, (uint32_t)bytes, bar);
-            }
-        }
-    } else {
-        // scattered tile (it spans pushes): one copy per task, each widened to 16-byte boundaries
-        uint32_t asz[2];
+// the rare count chain (some pending task is cancelled): decoupled look-back over warp-tiles
+__device__ __noinline__ uint32_t d3_count_lookback(const DrainArgs& a, unsigned long long tile, uint32_t rc, int lane) {
+    uint64_t excl = 0;
+    if (tile == 0) { if (lane == 0) st_volatile_u64(a.tile_state + 0, LB_INC | rc); return 0; }
+    if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_AGG | rc);
+    long long look = (long long)tile - 1;
+    for (;;) {
+        const long long idx = look - lane;
+        uint64_t w = (idx >= 0) ? ld_volatile_u64(a.tile_state + idx) : LB_INC;
+        while (__any_sync(0xffffffffu, (w & LB_STATUS) == 0)) { if ((w & LB_STATUS) == 0) w = ld_volatile_u64(a.tile_state + idx); }
+        const uint32_t inc_mask = __ballot_sync(0xffffffffu, (w & LB_STATUS) == LB_INC);
+        uint64_t v = lb_value(w);
+        if (inc_mask) { const int first = __ffs(inc_mask) - 1; if (lane > first) v = 0; }
         #pragma unroll
-        for (int q = 0; q < 2; ++q) asz[q] = (valid[q] && len[q]) ? (uint32_t)(((end[q] + 15ull) & ~15ull) - (off[q] & ~15ull)) : 0u;
-        const uint32_t ex0 = warp_excl_scan(asz[0], lane);
-        const uint32_t tot0 = __shfl_sync(0xffffffffu, ex0 + asz[0], 31);
-        const uint32_t ex1 = tot0 + warp_excl_scan(asz[1], lane);
-        const uint32_t total = __shfl_sync(0xffffffffu, ex1 + asz[1], 31);
-        if (total <= in_cap) {
-            staged = 1;
-            if (lane == 0) mbar_expect_tx(bar, total);
-            __syncwarp();
-            if (valid[0]) { m.soff[lane] = ex0 + (uint32_t)(off[0] & 15ull); if (asz[0]) bulk_g2s(buf + ex0, a.payload + (off[0] & ~15ull), asz[0], bar); }
-            if (valid[1]) { m.soff[lane + 32] = ex1 + (uint32_t)(off[1] & 15ull); if (asz[1]) bulk_g2s(buf + ex1, a.payload + (off[1] & ~15ull), asz[1], bar); }
-        }
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (inc_mask) break;
+        look -= 32;
     }
-    // ---- record indices: ready counts are known from the slot words alone
-    const uint32_t rc = __popc(__ballot_sync(0xffffffffu, valid[0] && !(hdr_flags(r.hdr[0]) & 1u)))
-                      + __popc(__ballot_sync(0xffffffffu, valid[1] && !(hdr_flags(r.hdr[1]) & 1u)));
-    uint32_t base_cnt = t0;                                   // nothing cancelled anywhere: pure arithmetic
-    if (a.count_mode) {                                       // some pending task is cancelled: chain the counts
-        uint64_t excl = 0;
-        if (tile == 0) { if (lane == 0) st_volatile_u64(a.tile_state + 0, LB_INC | rc); }
-        else {
-            if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_AGG | rc);
-            long long look = (long long)tile - 1;
-            for (;;) {
-                const long long idx = look - lane;
-                uint64_t w = (idx >= 0) ? ld_volatile_u64(a.tile_state + idx) : LB_INC;
-                while (__any_sync(0xffffffffu, (w & LB_STATUS) == 0)) { if ((w & LB_STATUS) == 0) w = ld_volatile_u64(a.tile_state + idx); }
-                const uint32_t inc_mask = __ballot_sync(0xffffffffu, (w & LB_STATUS) == LB_INC);
-                uint64_t v = lb_value(w);
-                if (inc_mask) { const int first = __ffs(inc_mask) - 1; if (lane > first) v = 0; }
-                #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                excl += v;
-                if (inc_mask) break;
-                look -= 32;
-            }
-            if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_INC | (excl + rc));
-        }
-        base_cnt = (uint32_t)excl;
-    }
-    if (lane == 0) {
-        m.tile = tile; m.nt = nt; m.staged = staged; m.base_cnt = base_cnt; m.ready_cnt = rc;
-        if (tile == a.n_tiles - 1) a.ctl->total_cnt = base_cnt + rc;
-    }
+    if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_INC | (excl + rc));
+    return (uint32_t)excl;
 }
 
-// ---- per-task bodies, inlined once for shared-memory payloads (LDS) and once for global ones ----
+// scattered tile (it spans pushes): one bulk copy per task, each widened to 16-byte boundaries
+template <int T>
+__device__ __noinline__ uint32_t d3_stage_scattered(const DrainArgs& a, uint64_t off, uint32_t len, bool valid, D3Warp<T>& W, uint8_t* buf,
+                                                    uint32_t in_cap, int lane) {
+    const uint64_t end = off + len;
+    const uint32_t asz = (valid && len) ? (uint32_t)(((end + 15ull) & ~15ull) - (off & ~15ull)) : 0u;
+    const uint32_t ex = warp_excl_scan(asz, lane);
+    const uint32_t total = __shfl_sync(0xffffffffu, ex + asz, 31);
+    if (total > in_cap) return 0;
+    if (lane == 0) mbar_expect_tx(&W.mbar, total);
+    __syncwarp();
+    if (valid) { W.soff[lane] = ex + (uint32_t)(off & 15ull); if (asz) bulk_g2s(buf + ex, a.payload + (off & ~15ull), asz, &W.mbar); }
+    return 1;
+}
+
+// out-of-line generic-pointer versions for tiles that could not be staged (and other cold paths)
+template <int G>
+__device__ __noinline__ uint32_t quick_clean_framed_generic(const uint8_t* p, uint32_t len, int sub, bool active) { return quick_clean_framed<G>(p, len, sub, active); }
+template <int G>
+__device__ __noinline__ void group_copy_generic(uint8_t* dst, const uint8_t* src, uint32_t n, int sub) { group_copy<G>(dst, src, n, sub); }
+
 template <int HANDLER>
 __device__ __forceinline__ void d2_phase_b_task(const uint8_t* __restrict__ p, const TaskRec& rec, uint8_t* __restrict__ o) {
     if (rec.mode == OM_VADD) vadd_write(p, rec.src_off, rec.src_len, o);
@@ -528,158 +464,157 @@ __device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, T
 }
 
 template <int HANDLER>
-__global__ void __launch_bounds__(D2Cfg<HANDLER>::THREADS, 8) drain2_kernel(DrainArgs a, uint32_t in_cap) {
-    constexpr int G = D2Cfg<HANDLER>::G, THREADS = D2Cfg<HANDLER>::THREADS, WARPS = THREADS / 32;
-    extern __shared__ __align__(128) uint8_t d2_smem[];
-    using Sh = D2Shared<HANDLER>;
-    Sh& S = *reinterpret_cast<Sh*>(d2_smem);
-    uint8_t* const bufs = d2_smem + ((sizeof(Sh) + 127u) & ~127u);
-    const uint32_t buf_stride = (in_cap + 64u + 127u) & ~127u;             // 64 bytes of readable slack behind each stage
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = tid / G, sub = tid % G;                                  // my task inside the tile, my share of it
+__global__ void __launch_bounds__(D3_WARPS * 32, 8) drain3_kernel(DrainArgs a, uint32_t in_cap, uint32_t warp_stride) {
+    constexpr int G = D3Cfg<HANDLER>::G, T = D3Cfg<HANDLER>::T;
+    extern __shared__ __align__(128) uint8_t d3_smem[];
+    __shared__ uint32_t s_crc_table[HANDLER == 1 ? 256 : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* const wbase = d3_smem + (size_t)warp * warp_stride;
+    D3Warp<T>& W = *reinterpret_cast<D3Warp<T>*>(wbase);
+    uint8_t* const sbuf = wbase + ((sizeof(D3Warp<T>) + 127u) & ~127u);   // stage buffer (+64 bytes of readable slack)
+    const int k = lane / G, sub = lane % G;                                // my task inside the warp-tile, my share of it
 
-    if (tid == 0) { mbar_init(&S.mbar[0], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.n_slow = 0; }
-    if (HANDLER == 1) for (int i = tid; i < 256; i += THREADS) S.crc_table[i] = crc_table_entry(i);
+    if (HANDLER == 1) { for (int i = threadIdx.x; i < 256; i += D3_WARPS * 32) s_crc_table[i] = crc_table_entry(i); __syncthreads(); }
+    if (lane == 0) { mbar_init(&W.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
 
-    // warp 0 keeps two tickets ahead of the tile being processed: the slot words of the next tile are
-    // already in registers when its turn comes (no global latency between the end of one tile and the
-    // bulk copy of the next), and the ticket after that is in flight. Holding tickets is harmless: no
-    // CTA waits on another CTA's unprocessed tile (the byte cursor is an atomic, not a chain).
-    unsigned long long t_cur = ~0ull;      // tile to process next; its slot words are in `mregs`
-    unsigned long long t_raw = ~0ull;      // lane 0: ticket claimed for the tile after t_cur
-    D2MetaRegs mregs; mregs.off[0] = mregs.off[1] = mregs.hdr[0] = mregs.hdr[1] = 0;
-    if (warp == 0) {
-        if (lane == 0) { t_cur = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
-        t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
-        if (t_cur < a.n_tiles) d2_load_meta(a, t_cur, lane, mregs);
-    }
-    __syncthreads();
+    // two tickets ahead: the slot words of the next tile are in registers when its turn comes, and
+    // the ticket after that is in flight; nothing global sits between the end of a tile and the bulk
+    // copy of the next one. (Holding tickets is harmless: nobody waits on another worker's tile.)
+    unsigned long long t_cur = 0, t_raw = 0;
+    if (lane == 0) { t_cur = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
+    t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
+    D3MetaRegs mregs; mregs.off = 0; mregs.hdr = 0;
+    if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
     uint32_t parity = 0;
-    const uint32_t stage = 0;
-    D2Meta& M = S.meta[0];
 
-    for (;;) {
-        if (warp == 0) {
-            if (t_cur < a.n_tiles) d2_stage_tile(a, t_cur, mregs, M, bufs, in_cap, &S.mbar[0], lane);
-            else if (lane == 0) M.tile = t_cur;
-            t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
-            if (t_cur < a.n_tiles) d2_load_meta(a, t_cur, lane, mregs);
-            if (lane == 0) t_raw = atomicAdd(&a.ctl->ticket, 1ull);
-        }
-        __syncthreads();                                                   // [0] tile metadata visible
-        const unsigned long long tile = M.tile;
-        if (tile >= a.n_tiles) break;
-        const uint32_t nt = M.nt;
-        const uint32_t t0 = (uint32_t)tile * D2_TASKS;
-        const bool staged = M.staged != 0;
-        const uint8_t* const sbuf = bufs + (size_t)stage * buf_stride;
-        if (staged) { mbar_wait(&S.mbar[0], parity); parity ^= 1u; }
+    while (t_cur < a.n_tiles) {
+        // ---------------- stage: decide how the tile's bytes get to shared memory, fire the copy --------
+        const unsigned long long tile = t_cur;
+        const uint32_t t0 = (uint32_t)tile * T;
+        const uint32_t nt = min((uint32_t)T, a.n_tasks - t0);
+        const bool valid = lane < (int)nt;
+        const uint64_t m_off = mregs.off;
+        const uint32_t m_len = valid ? hdr_len(mregs.hdr) : 0u;
+        const bool m_ready = valid && !(hdr_flags(mregs.hdr) & 1u);
+        const uint64_t m_end = m_off + m_len;
+        uint64_t prev = __shfl_up_sync(0xffffffffu, m_end, 1);
+        if (lane == 0) prev = m_off;
+        const bool contig = __all_sync(0xffffffffu, !valid || m_off == prev);
+        const uint64_t gs = __shfl_sync(0xffffffffu, m_off, 0);
+        const uint64_t ge = __shfl_sync(0xffffffffu, m_end, (int)nt - 1);
+        uint32_t staged = 0;
+        if (valid) { W.goff[lane] = m_off; W.len[lane] = m_len; }
+        if (contig) {
+            const uint64_t as = gs & ~15ull;
+            const uint64_t bytes = ((ge + 15ull) & ~15ull) - as;
+            if (bytes <= in_cap) {
+                staged = 1;
+                if (valid) W.soff[lane] = (uint32_t)(m_off - as);
+                if (lane == 0) { mbar_expect_tx(&W.mbar, (uint32_t)bytes); if (bytes) bulk_g2s(sbuf, a.payload + as, (uint32_t)bytes, &W.mbar); }
+            }
+        } else staged = d3_stage_scattered<T>(a, m_off, m_len, valid, W, sbuf, in_cap, lane);
+        // record indices: ready counts are known from the slot words alone
+        const uint32_t ready_mask_t = __ballot_sync(0xffffffffu, m_ready);       // bit = task index
+        const uint32_t rc = __popc(ready_mask_t);
+        const uint32_t base_cnt = a.count_mode ? d3_count_lookback(a, tile, rc, lane) : t0;
+        if (lane == 0 && tile == a.n_tiles - 1) a.ctl->total_cnt = base_cnt + rc;
+        // advance the ticket pipeline (loads/atomics issued here are consumed one iteration later)
+        t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
+        if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
+        if (lane == 0) t_raw = atomicAdd(&a.ctl->ticket, 1ull);
+        __syncwarp();                                                      // W.* visible to all lanes
+        if (staged) { mbar_wait(&W.mbar, parity); parity ^= 1u; }
 
-        // ---------------- phase A: G threads per task ------------------------------------------------
-        const bool mine = k < (int)nt && M.ready[k];
-        const uint32_t my_len = mine ? M.len[k] : 0u;
+        // ---------------- phase A: G lanes per task ----------------------------------------------------
+        const bool mine = k < (int)nt && ((ready_mask_t >> k) & 1u);
+        const uint32_t my_len = mine ? W.len[k] : 0u;
+        const uint32_t my_soff = (mine && staged) ? W.soff[k] : 0u;
+        const uint64_t my_goff = mine ? W.goff[k] : 0ull;
         TaskRec rec; rec.ready = mine; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
+        uint32_t slow_mask = 0;                                            // bit = lane of a task the quick look could not settle
         if (HANDLER == 0) {
             uint32_t q;
-            if (staged) q = quick_clean_framed<G>(sbuf + (mine ? M.soff[k] : 0u), my_len, sub, mine);
-            else        q = quick_clean_framed<G>(a.payload + (mine ? M.goff[k] : 0ull), my_len, sub, mine);
+            if (staged) q = quick_clean_framed<G>(sbuf + my_soff, my_len, sub, mine);
+            else        q = quick_clean_framed_generic<G>(a.payload + my_goff, my_len, sub, mine);
+            bool slow = false;
             if (mine) {
                 if (q == 3u) {
                     const uint32_t tok = my_len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
                     if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
-                } else {
-                    rec.mode = (q & 1u) ? OM_STR_PAR : OM_NONE;          // settled in the cooperative pass
-                    if (sub == 0) S.slow_list[atomicAdd(&S.n_slow, 1u)] = (uint32_t)k;
+                } else { rec.mode = (q & 1u) ? OM_STR_PAR : OM_NONE; slow = sub == 0; }
+            }
+            slow_mask = __ballot_sync(0xffffffffu, slow);
+            // cooperative pass: the whole warp sizes each such task
+            uint32_t slot = 0;
+            for (uint32_t rem = slow_mask; rem; rem &= rem - 1u, ++slot) {
+                const int owner = __ffs(rem) - 1;                          // lane with sub == 0 of that task
+                const int ks = owner / G;
+                const uint32_t len = W.len[ks];
+                const uint8_t* p = staged ? (const uint8_t*)(sbuf + W.soff[ks]) : a.payload + W.goff[ks];
+                const uint32_t omode = __shfl_sync(0xffffffffu, (uint32_t)rec.mode, owner);
+                bool done = false; uint32_t ol = 0;
+                const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
+                if (omode == OM_STR_PAR) done = esc_measure(p + FRAME_PRE_LEN, n, lane, &ol, slot < 2 ? W.esc_info[slot] : nullptr);
+                if (k == ks) {                                             // all G lanes of the task keep the same record
+                    if (done) { rec.has = 1; rec.mode = OM_STR_PAR; rec.src_off = FRAME_PRE_LEN; rec.src_len = n; rec.out_len = ol; }
+                    else { rec.mode = OM_NONE; rec.has = 0; rec.out_len = 0; }
+                }
+                if (!done && lane == owner) d2_parse_and_size<0>(p, len, rec, nullptr);
+                if (!done) {                                               // share the owner's sequentially computed record with its partner lanes
+                    const uint32_t w0 = __shfl_sync(0xffffffffu, rec.src_off, owner), w1 = __shfl_sync(0xffffffffu, rec.src_len, owner), w2 = __shfl_sync(0xffffffffu, rec.out_len, owner);
+                    const uint32_t w3 = __shfl_sync(0xffffffffu, (uint32_t)rec.status | ((uint32_t)rec.has << 8) | ((uint32_t)rec.mode << 16), owner);
+                    if (k == ks) { rec.src_off = w0; rec.src_len = w1; rec.out_len = w2; rec.status = (uint8_t)w3; rec.has = (uint8_t)(w3 >> 8); rec.mode = (uint8_t)(w3 >> 16); }
                 }
             }
         } else if (mine) {
-            const uint8_t* p = staged ? (const uint8_t*)(sbuf + M.soff[k]) : a.payload + M.goff[k];
-            d2_parse_and_size<HANDLER>(p, my_len, rec, S.crc_table);
-        }
-        if (sub == 0 && k < D2_TASKS) S.rec[k] = rec;
-        __syncthreads();                                                   // [1] records + slow list complete
-        // ---------------- phase A, cooperative pass over the tasks the quick look could not settle --
-        const uint32_t ns = (HANDLER == 0) ? S.n_slow : 0u;
-        if (ns) {
-            for (uint32_t s = warp; s < ns; s += WARPS) {
-                const uint32_t ks = S.slow_list[s];
-                const uint32_t len = M.len[ks];
-                TaskRec r2 = S.rec[ks];
-                bool done = false;
-                if (r2.mode == OM_STR_PAR) {                               // canonical frame, body needs transcoding
-                    uint32_t ol;
-                    const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
-                    uint32_t* info = s < D2_ESC_SLOTS ? S.esc_info[s] : nullptr;
-                    const bool ok = staged ? esc_measure(sbuf + M.soff[ks] + FRAME_PRE_LEN, n, lane, &ol, info)
-                                           : esc_measure(a.payload + M.goff[ks] + FRAME_PRE_LEN, n, lane, &ol, info);
-                    if (ok) { r2.has = 1; r2.src_off = FRAME_PRE_LEN; r2.src_len = n; r2.out_len = ol; done = true; }
-                }
-                if (!done && lane == 0) {
-                    const uint8_t* p = staged ? (const uint8_t*)(sbuf + M.soff[ks]) : a.payload + M.goff[ks];
-                    r2.mode = OM_NONE; r2.has = 0; r2.out_len = 0;
-                    d2_parse_and_size<0>(p, len, r2, nullptr);
-                    r2.ready = 1;
-                }
-                if (lane == 0) S.rec[ks] = r2;
-            }
-            __syncthreads();                                               // [2] slow tasks sized
+            const uint8_t* p = staged ? (const uint8_t*)(sbuf + my_soff) : a.payload + my_goff;
+            d2_parse_and_size<HANDLER>(p, my_len, rec, s_crc_table);
         }
 
-        // ---------------- compaction (ballot) + sizes (scan) + ONE cursor add, all in warp 0 ---------
-        if (warp == 0) {
-            const uint32_t l0 = S.rec[lane].out_len, l1 = S.rec[lane + 32].out_len;
-            const uint32_t m0 = __ballot_sync(0xffffffffu, S.rec[lane].ready), m1 = __ballot_sync(0xffffffffu, S.rec[lane + 32].ready);
-            const uint32_t e0 = warp_excl_scan(l0, lane);
-            const uint32_t tot0 = __shfl_sync(0xffffffffu, e0 + l0, 31);
-            const uint32_t e1 = tot0 + warp_excl_scan(l1, lane);
-            const uint32_t tb = __shfl_sync(0xffffffffu, e1 + l1, 31);
-            S.excl_bytes[lane] = e0; S.excl_bytes[lane + 32] = e1;
-            const uint32_t below = (1u << lane) - 1u;
-            S.excl_cnt[lane] = __popc(m0 & below); S.excl_cnt[lane + 32] = __popc(m0) + __popc(m1 & below);
-            if (lane == 0) {
-                const unsigned long long base = tb ? atomicAdd(&a.ctl->bytes, (unsigned long long)tb) : 0ull;
-                S.base = base;
-                if (base + tb > a.out_cap) { a.ctl->overflow = 1u; S.base = ~0ull; }
-                S.n_slow = 0;                                              // for the next tile (touched again only after [4])
-            }
-        }
-        __syncthreads();                                                   // [3] offsets known
-        const unsigned long long base_bytes = S.base;
-        const bool fits = base_bytes != ~0ull;
-        const uint32_t base_cnt = M.base_cnt;
+        // ---------------- compaction (ballot) + sizes (scan) + ONE cursor add per warp-tile -------------
+        const uint32_t my_bytes = (sub == 0) ? rec.out_len : 0u;
+        const uint32_t ex_bytes0 = warp_excl_scan(my_bytes, lane);
+        const uint32_t tb = __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
+        const uint32_t ex_bytes = __shfl_sync(0xffffffffu, ex_bytes0, k * G);      // every lane of a task sees the task's offset
+        const uint32_t ex_cnt = __popc(ready_mask_t & ((1u << k) - 1u));
+        unsigned long long base = 0;
+        if (lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const bool fits = base + tb <= a.out_cap;
+        if (!fits && lane == 0) a.ctl->overflow = 1u;
 
-        // ---------------- phase B: G threads per task ------------------------------------------------
+        // ---------------- phase B: G lanes per task ----------------------------------------------------
         if (mine) {
-            if (ns) rec = S.rec[k];                                        // the cooperative pass may have rewritten it
-            const uint64_t ob = base_bytes + S.excl_bytes[k];
+            const uint64_t ob = base + ex_bytes;
             if (sub == 0) {
                 const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
-                const uint32_t j = base_cnt + S.excl_cnt[k];
+                const uint32_t j = base_cnt + ex_cnt;
                 a.out_off[j] = fits ? ob : 0; a.out_len[j] = rec.out_len; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
             }
             if (rec.has && fits) {
                 if (rec.mode == OM_COPY) {
-                    if (staged) group_copy<G>(a.out_payload + ob, sbuf + M.soff[k] + rec.src_off, rec.src_len, sub);
-                    else        group_copy<G>(a.out_payload + ob, a.payload + M.goff[k] + rec.src_off, rec.src_len, sub);
+                    if (staged) group_copy<G>(a.out_payload + ob, sbuf + my_soff + rec.src_off, rec.src_len, sub);
+                    else        group_copy_generic<G>(a.out_payload + ob, a.payload + my_goff + rec.src_off, rec.src_len, sub);
                 } else if (sub == 0 && rec.mode != OM_STR_PAR) {
-                    const uint8_t* p = staged ? (const uint8_t*)(sbuf + M.soff[k]) : a.payload + M.goff[k];
+                    const uint8_t* p = staged ? (const uint8_t*)(sbuf + my_soff) : a.payload + my_goff;
                     d2_phase_b_task<HANDLER>(p, rec, a.out_payload + ob);
                 }
             }
         }
-        // ---------------- phase B, cooperative: transcode the escaped strings -----------------------
-        if (ns && fits) {
-            for (uint32_t s = warp; s < ns; s += WARPS) {
-                const uint32_t ks = S.slow_list[s];
-                const TaskRec r2 = S.rec[ks];
-                if (r2.mode != OM_STR_PAR || !r2.has) continue;
-                const uint32_t* info = s < D2_ESC_SLOTS ? S.esc_info[s] : nullptr;
-                uint8_t* o = a.out_payload + base_bytes + S.excl_bytes[ks];
-                if (staged) esc_emit(sbuf + M.soff[ks] + r2.src_off, r2.src_len, lane, o, info);
-                else        esc_emit(a.payload + M.goff[ks] + r2.src_off, r2.src_len, lane, o, info);
+        if (HANDLER == 0 && fits) {                                        // cooperative: transcode the escaped strings
+            uint32_t slot = 0;
+            for (uint32_t rem = slow_mask; rem; rem &= rem - 1u, ++slot) {
+                const int owner = __ffs(rem) - 1;
+                const int ks = owner / G;
+                const uint32_t omode = __shfl_sync(0xffffffffu, (uint32_t)rec.mode | ((uint32_t)rec.has << 8), owner);
+                const uint32_t o_off = __shfl_sync(0xffffffffu, ex_bytes, owner), o_n = __shfl_sync(0xffffffffu, rec.src_len, owner);
+                if (omode != ((uint32_t)OM_STR_PAR | (1u << 8))) continue;
+                const uint8_t* p = staged ? (const uint8_t*)(sbuf + W.soff[ks]) : a.payload + W.goff[ks];
+                esc_emit(p + FRAME_PRE_LEN, o_n, lane, a.out_payload + base + o_off, slot < 2 ? W.esc_info[slot] : nullptr);
             }
         }
-        __syncthreads();                                                   // [4] stage buffer, records, metadata free again
+        __syncwarp();                                                      // stage buffer and W.* free again
     }
 }
 

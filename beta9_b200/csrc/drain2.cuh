@@ -368,9 +368,14 @@ __device__ __noinline__ void esc_emit(const uint8_t* __restrict__ body, uint32_t
 // ~27 warps of the SM are in their compute phases. (The CTA-per-tile versions spent most of their
 // time at __syncthreads behind warp 0's staging, the cursor atomic and the escaped-string pass:
 // profiles/r1_v2c/v2d/v2e.)
-constexpr int D3_WARPS = 4;                  // warps per CTA (a container only)
+constexpr int D3_WARPS = 2;                  // warps per CTA (a container only)
 template <int HANDLER> struct D3Cfg {
-    static constexpr int G = (HANDLER == 0) ? 2 : 1;      // threads per task
+    // threads per task. G = 2 doubles the warps per staged byte but also doubles the per-task setup
+    // instructions (both lanes execute them); with no barriers to hide, G = 1 wins (r1_v3a vs r1_v3b).
+#ifndef B9_IDENTITY_G
+#define B9_IDENTITY_G 1
+#endif
+    static constexpr int G = (HANDLER == 0) ? B9_IDENTITY_G : 1;
     static constexpr int T = 32 / G;                      // tasks per warp-tile
 };
 constexpr int D2_THREADS = 16;               // host: tasks per look-back slot (smallest warp-tile)
@@ -464,7 +469,7 @@ __device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, T
 }
 
 template <int HANDLER>
-__global__ void __launch_bounds__(D3_WARPS * 32, 8) drain3_kernel(DrainArgs a, uint32_t in_cap, uint32_t warp_stride) {
+__global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, uint32_t in_cap, uint32_t warp_stride) {
     constexpr int G = D3Cfg<HANDLER>::G, T = D3Cfg<HANDLER>::T;
     extern __shared__ __align__(128) uint8_t d3_smem[];
     __shared__ uint32_t s_crc_table[HANDLER == 1 ? 256 : 1];

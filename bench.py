@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--handler", default="identity")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--adversarial", type=float, default=0.01, help="share of tasks whose string needs escaping (SURVEY.md §8d: 1 %%)")
     return ap.parse_args()
 
 
@@ -105,7 +106,7 @@ def dist_env():
 def workload(args, rank):
     from beta9_b200 import synth
     if args.handler == "identity":
-        return synth.strings_batch(args.tasks, args.chars, seed=synth.SEED + 1000 * rank)
+        return synth.strings_batch(args.tasks, args.chars, adversarial_frac=args.adversarial, seed=synth.SEED + 1000 * rank)
     raise SystemExit(f"bench: handler {args.handler} has no bench workload yet")
 
 
@@ -269,7 +270,7 @@ def main():
             "metric": "tasks_per_sec", "value": value, "unit": "tasks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"configs[1]: {n} x {args.chars}-char identity tasks per GPU (1% adversarial escapes), "
+            "config": {"workload": f"configs[1]: {n} x {args.chars}-char identity tasks per GPU ({100 * args.adversarial:g}% adversarial escapes), "
                                    f"resident in HBM", "handler": args.handler, "tasks_per_gpu": n,
                        "parallelism": f"shard{world}" if world > 1 else "single",
                        "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; no flush needed"},

@@ -81,6 +81,7 @@ struct b9_ctx {
     uint32_t max_drain_tasks = 0; uint64_t max_result_bytes = 0;
     uint8_t* d_out_payload = nullptr; uint64_t* d_out_off = nullptr; uint4* d_out_ids = nullptr;
     uint8_t* d_out_status = nullptr; uint8_t* d_out_has = nullptr; uint32_t* d_out_len = nullptr;
+    SlowItem* d_slow = nullptr;                 // identity: work list of the second kernel
     uint64_t cancelled_pending = 0;            // pending tasks carrying B9_TF_CANCELLED (pushed so, or expired)
     DrainCtl* d_ctl = nullptr; uint64_t* d_tile_state = nullptr;
     DrainCtl* h_ctl = nullptr;                 // pinned
@@ -223,6 +224,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     CUC(cudaMalloc(&c->d_out_status, md));
     CUC(cudaMalloc(&c->d_out_has, md));
     CUC(cudaMalloc(&c->d_out_len, (size_t)md * sizeof(uint32_t)));
+    CUC(cudaMalloc(&c->d_slow, (size_t)md * sizeof(SlowItem)));
     CUC(cudaMalloc(&c->d_ctl, sizeof(DrainCtl)));
     CUC(cudaMalloc(&c->d_tile_state, ((size_t)md / D2_THREADS + 2) * sizeof(uint64_t)));
     CUC(cudaMalloc(&c->d_count, sizeof(unsigned long long)));
@@ -246,7 +248,7 @@ void b9_ctx_destroy(b9_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_payload); cudaFree(c->d_off); cudaFree(c->d_hdr); cudaFree(c->d_ids); cudaFree(c->d_ts); cudaFree(c->d_exp);
     cudaFree(c->d_in_off); cudaFree(c->d_in_ts); cudaFree(c->d_in_exp); cudaFree(c->d_in_retries); cudaFree(c->d_in_flags);
-    cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len);
+    cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len); cudaFree(c->d_slow);
     cudaFree(c->d_ctl); cudaFree(c->d_tile_state); cudaFree(c->d_count);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_count) cudaFreeHost(c->h_count);
@@ -386,6 +388,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_ids = c->d_out_ids;
     a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.handler = handler;
     a.count_mode = c->cancelled_pending ? 1u : 0u;
+    a.slow = c->d_slow;
     cudaStream_t s = c->stream;
     const bool v2 = c->drain_version == 2;
     if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;     // upper bound over the handlers' warp-tile sizes (state array memset)
@@ -408,8 +411,15 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     default:            le = launch_drain<3>(a, grid, s); break;
     }
     if (le != cudaSuccess) return fail(B9_EIO, "drain kernel launch failed: %s", cudaGetErrorString(le));
-    CU(cudaEventRecord(c->ev_b, s));
     c->stats.kernel_launches++;
+    if (v2 && handler == B9_H_IDENTITY) {
+        // second kernel: the tasks the main identity kernel deferred (escaped strings, foreign framing, ...)
+        drain_slow_kernel<<<c->sm_count * 4, DS_WARPS * 32, 0, s>>>(a);
+        le = cudaGetLastError();
+        if (le != cudaSuccess) return fail(B9_EIO, "drain_slow_kernel launch failed: %s", cudaGetErrorString(le));
+        c->stats.kernel_launches++;
+    }
+    CU(cudaEventRecord(c->ev_b, s));
     CU(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(DrainCtl), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);

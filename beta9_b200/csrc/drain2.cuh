@@ -537,40 +537,18 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         const uint32_t my_soff = (mine && staged) ? W.soff[k] : 0u;
         const uint64_t my_goff = mine ? W.goff[k] : 0ull;
         TaskRec rec; rec.ready = mine; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
-        uint32_t slow_mask = 0;                                            // bit = lane of a task the quick look could not settle
         if (HANDLER == 0) {
+            // identity: settle the common case here (canonical frame, clean body -> the token is its own
+            // json.dumps); everything else is handed to drain_slow_kernel through the work list, so that
+            // this loop stays small enough for the instruction cache and no worker stalls on a 1 % case
             uint32_t q;
             if (staged) q = quick_clean_framed<G>(sbuf + my_soff, my_len, sub, mine);
             else        q = quick_clean_framed_generic<G>(a.payload + my_goff, my_len, sub, mine);
-            bool slow = false;
             if (mine) {
                 if (q == 3u) {
                     const uint32_t tok = my_len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
                     if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
-                } else { rec.mode = (q & 1u) ? OM_STR_PAR : OM_NONE; slow = sub == 0; }
-            }
-            slow_mask = __ballot_sync(0xffffffffu, slow);
-            // cooperative pass: the whole warp sizes each such task
-            uint32_t slot = 0;
-            for (uint32_t rem = slow_mask; rem; rem &= rem - 1u, ++slot) {
-                const int owner = __ffs(rem) - 1;                          // lane with sub == 0 of that task
-                const int ks = owner / G;
-                const uint32_t len = W.len[ks];
-                const uint8_t* p = staged ? (const uint8_t*)(sbuf + W.soff[ks]) : a.payload + W.goff[ks];
-                const uint32_t omode = __shfl_sync(0xffffffffu, (uint32_t)rec.mode, owner);
-                bool done = false; uint32_t ol = 0;
-                const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
-                if (omode == OM_STR_PAR) done = esc_measure(p + FRAME_PRE_LEN, n, lane, &ol, slot < 2 ? W.esc_info[slot] : nullptr);
-                if (k == ks) {                                             // all G lanes of the task keep the same record
-                    if (done) { rec.has = 1; rec.mode = OM_STR_PAR; rec.src_off = FRAME_PRE_LEN; rec.src_len = n; rec.out_len = ol; }
-                    else { rec.mode = OM_NONE; rec.has = 0; rec.out_len = 0; }
-                }
-                if (!done && lane == owner) d2_parse_and_size<0>(p, len, rec, nullptr);
-                if (!done) {                                               // share the owner's sequentially computed record with its partner lanes
-                    const uint32_t w0 = __shfl_sync(0xffffffffu, rec.src_off, owner), w1 = __shfl_sync(0xffffffffu, rec.src_len, owner), w2 = __shfl_sync(0xffffffffu, rec.out_len, owner);
-                    const uint32_t w3 = __shfl_sync(0xffffffffu, (uint32_t)rec.status | ((uint32_t)rec.has << 8) | ((uint32_t)rec.mode << 16), owner);
-                    if (k == ks) { rec.src_off = w0; rec.src_len = w1; rec.out_len = w2; rec.status = (uint8_t)w3; rec.has = (uint8_t)(w3 >> 8); rec.mode = (uint8_t)(w3 >> 16); }
-                }
+                } else { rec.mode = OM_DEFER; rec.value = (long long)(q & 1u); }
             }
         } else if (mine) {
             const uint8_t* p = staged ? (const uint8_t*)(sbuf + my_soff) : a.payload + my_goff;
@@ -595,7 +573,11 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             if (sub == 0) {
                 const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
                 const uint32_t j = base_cnt + ex_cnt;
-                a.out_off[j] = fits ? ob : 0; a.out_len[j] = rec.out_len; a.out_ids[j] = __ldg(a.ids + slot); a.out_status[j] = rec.status; a.out_has[j] = rec.has;
+                a.out_ids[j] = __ldg(a.ids + slot);
+                if (HANDLER == 0 && rec.mode == OM_DEFER) {                // the second kernel writes the rest of the record
+                    SlowItem it; it.goff = my_goff; it.len = my_len | (rec.value ? 0x80000000u : 0u); it.j = j;
+                    a.slow[atomicAdd(&a.ctl->n_slow, 1u)] = it;
+                } else { a.out_off[j] = fits ? ob : 0; a.out_len[j] = rec.out_len; a.out_status[j] = rec.status; a.out_has[j] = rec.has; }
             }
             if (rec.has && fits) {
                 if (rec.mode == OM_COPY) {
@@ -607,19 +589,54 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                 }
             }
         }
-        if (HANDLER == 0 && fits) {                                        // cooperative: transcode the escaped strings
-            uint32_t slot = 0;
-            for (uint32_t rem = slow_mask; rem; rem &= rem - 1u, ++slot) {
-                const int owner = __ffs(rem) - 1;
-                const int ks = owner / G;
-                const uint32_t omode = __shfl_sync(0xffffffffu, (uint32_t)rec.mode | ((uint32_t)rec.has << 8), owner);
-                const uint32_t o_off = __shfl_sync(0xffffffffu, ex_bytes, owner), o_n = __shfl_sync(0xffffffffu, rec.src_len, owner);
-                if (omode != ((uint32_t)OM_STR_PAR | (1u << 8))) continue;
-                const uint8_t* p = staged ? (const uint8_t*)(sbuf + W.soff[ks]) : a.payload + W.goff[ks];
-                esc_emit(p + FRAME_PRE_LEN, o_n, lane, a.out_payload + base + o_off, slot < 2 ? W.esc_info[slot] : nullptr);
-            }
-        }
         __syncwarp();                                                      // stage buffer and W.* free again
+    }
+}
+
+// ---------------------------------------------------------------- identity, second kernel
+// One warp per deferred task (escaped / non-ASCII strings, foreign framing, non-string arguments),
+// straight from the ring in global memory. Thousands of independent warps: latency is irrelevant here.
+constexpr int DS_WARPS = 8;
+__global__ void __launch_bounds__(DS_WARPS * 32) drain_slow_kernel(DrainArgs a) {
+    __shared__ uint32_t s_info[DS_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_slow = a.ctl->n_slow;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(&a.ctl->slow_head, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n_slow) break;
+        const SlowItem it = a.slow[i];
+        const uint32_t len = it.len & 0x7FFFFFFFu;
+        const uint8_t* p = a.payload + it.goff;
+        TaskRec rec; rec.ready = 1; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
+        bool par = false;
+        if (it.len & 0x80000000u) {                                        // canonical frame: the body needs transcoding
+            uint32_t ol;
+            const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
+            par = esc_measure(p + FRAME_PRE_LEN, n, lane, &ol, s_info[warp]);
+            if (par) { rec.has = 1; rec.mode = OM_STR_PAR; rec.src_off = FRAME_PRE_LEN; rec.src_len = n; rec.out_len = ol; }
+        }
+        if (!par) {                                                        // the sequential validating parser decides
+            if (lane == 0) d2_parse_and_size<0>(p, len, rec, nullptr);
+            rec.src_off = __shfl_sync(0xffffffffu, rec.src_off, 0); rec.src_len = __shfl_sync(0xffffffffu, rec.src_len, 0);
+            rec.out_len = __shfl_sync(0xffffffffu, rec.out_len, 0);
+            const uint32_t w = __shfl_sync(0xffffffffu, (uint32_t)rec.status | ((uint32_t)rec.has << 8) | ((uint32_t)rec.mode << 16), 0);
+            rec.status = (uint8_t)w; rec.has = (uint8_t)(w >> 8); rec.mode = (uint8_t)(w >> 16);
+        }
+        unsigned long long base = 0;
+        if (lane == 0 && rec.out_len) base = atomicAdd(&a.ctl->bytes, (unsigned long long)rec.out_len);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const bool fits = base + rec.out_len <= a.out_cap;
+        if (!fits && lane == 0) a.ctl->overflow = 1u;
+        if (rec.has && fits) {
+            uint8_t* o = a.out_payload + base;
+            if (rec.mode == OM_STR_PAR) esc_emit(p + rec.src_off, rec.src_len, lane, o, s_info[warp]);
+            else if (rec.mode == OM_COPY) warp_copy(o, p + rec.src_off, rec.src_len, lane);
+            else if (lane == 0) d2_phase_b_task<0>(p, rec, o);
+        }
+        if (lane == 0) { a.out_off[it.j] = fits ? base : 0; a.out_len[it.j] = rec.out_len; a.out_status[it.j] = rec.status; a.out_has[it.j] = rec.has; }
+        __syncwarp();
     }
 }
 

@@ -41,6 +41,15 @@ struct DrainCtl {
     unsigned long long bytes;       // v2: result-byte cursor (one atomicAdd per tile); final value = total bytes
     unsigned int overflow;          // result staging too small
     unsigned int total_cnt;         // v2: result records of the whole window
+    unsigned int n_slow;            // v2 identity: tasks deferred to the second kernel (escapes, foreign framing)
+    unsigned int slow_head;         // v2 identity: next deferred task to take
+};
+
+// a task the main identity kernel could not settle with its quick look
+struct SlowItem {
+    uint64_t goff;                  // physical ring offset of the payload
+    uint32_t len;                   // payload length; bit 31 = the SDK's canonical frame is present
+    uint32_t j;                     // index of the task's result record
 };
 
 struct DrainArgs {
@@ -65,11 +74,13 @@ struct DrainArgs {
     uint64_t* tile_state;           // [n_tiles], zeroed before launch
     int handler;
     uint32_t count_mode;            // v2: 0 = no pending task is cancelled (record index = task index), 1 = chain the ready counts
+    SlowItem* slow;                 // v2 identity: [n_tasks] work list for the second kernel
 };
 
 // what phase A leaves for phase B, per task of the tile
 enum OutMode : uint8_t { OM_NONE = 0, OM_COPY, OM_STR_ESC /* one thread walks the token */, OM_U32_DEC, OM_I64_DEC, OM_VADD,
-                         OM_STR_PAR /* warp transcodes the framed body in 32 chunks (drain2) */ };
+                         OM_STR_PAR /* warp transcodes the framed body in 32 chunks (drain2) */,
+                         OM_DEFER /* identity main kernel: left to drain_slow_kernel */ };
 struct TaskRec {
     uint32_t src_off;    // OM_COPY / OM_STR_ESC / OM_VADD: byte offset inside the payload
     uint32_t src_len;

@@ -303,55 +303,92 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
 }
 
 __device__ __forceinline__ bool plain_byte(uint32_t c) { return c >= 0x20u && c < 0x7Fu && c != '"' && c != '\\'; }
+// bit 7 of every byte of w that is NOT a plain byte (same exactness argument as swar_special16)
+__device__ __forceinline__ uint32_t special_mask32(uint32_t w) {
+    const uint32_t K1 = 0x01010101u, K60 = 0x60606060u, K7F = 0x7F7F7F7Fu, H = 0x80808080u;
+    return ((w + K1) | w | ~(w + K60) | ~((w ^ 0x22222222u) + K7F) | ~((w ^ 0x5C5C5C5Cu) + K7F)) & H;
+}
+// any 'A'..'F' among the four hex digits of a \uXXXX (digits have bit 6 clear, a..f have bit 5 set)
+__device__ __forceinline__ bool hex_has_upper(uint32_t w) { return ((w & 0x40404040u) & ~((w & 0x20202020u) << 1)) != 0; }
 
-// Warp-cooperative: json.dumps length of the framed string body, or false if the body is not a
-// well-formed JSON string ending exactly at the frame's closing quote. Every lane walks its chunk
-// as  (run of plain bytes)* (one escape / UTF-8 unit)  so that the branchy unit decoder runs once
-// per round for the whole warp. `lane_info` (optional, shared memory, 32 words) keeps each lane's
-// first-unit offset and output length for esc_emit.
-__device__ __noinline__ bool esc_measure(const uint8_t* __restrict__ body, uint32_t n, int lane, uint32_t* out_len, uint32_t* lane_info) {
+// What one lane learned about its chunk of an escaped string body.
+struct EscLane {
+    uint32_t start;        // first unit boundary at or after the chunk start
+    uint32_t out_len;      // json.dumps bytes produced by the chunk's units
+    uint32_t npatch;       // same-length units whose text must be rewritten (lone surrogate -> �, upper-case hex)
+    uint32_t patch_pos[2]; // body offsets of those units
+    uint32_t patch_cp[2];
+    bool ok;               // chunk is well-formed JSON string text
+    bool len_change;       // some unit's json.dumps form has another length than its input text
+};
+
+// Warp-cooperative scan of a framed string body: plain bytes are skipped four at a time, only
+// escapes / non-ASCII bytes go through the unit decoder. Returns false if the body is not a
+// well-formed JSON string ending at the frame's closing quote. *out_len = 2 + sum of units.
+// *fast = every unit keeps its length (true for everything json.dumps itself produced): then
+// json.dumps(body) is the input text with at most a few same-length patches.
+__device__ __noinline__ bool esc_scan(const uint8_t* __restrict__ body, uint32_t n, int lane, EscLane& L, uint32_t* out_len, bool* fast) {
     const uint32_t S = (n + 31u) / 32u;
     const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
-    bool ok = true;
-    uint32_t mine = 0, start = lo;
+    L.start = lo; L.out_len = 0; L.npatch = 0; L.ok = true; L.len_change = false;
+    L.patch_pos[0] = L.patch_pos[1] = 0; L.patch_cp[0] = L.patch_cp[1] = 0;
     if (lo < hi) {
-        start = first_unit_start(body, n, lo);
-        uint32_t i = start;
+        uint32_t i = first_unit_start(body, n, lo);
+        L.start = i;
+        uint32_t mine = 0;
         while (i < hi) {
-            while (i < hi && plain_byte(body[i])) { ++i; ++mine; }
+            // run of plain bytes: four at a time (reading up to 3 bytes past hi is inside the payload: the frame suffix follows)
+            bool stop = false;
+            while (i < hi) {
+                const uint32_t m = special_mask32(ld_u32_unaligned(body + i));
+                const uint32_t adv = m ? (uint32_t)(__ffs(m) - 1) >> 3 : 4u;
+                const uint32_t take = min(adv, hi - i);
+                i += take; mine += take;
+                if (adv < 4u || i >= hi) { stop = true; break; }
+            }
+            (void)stop;
             if (i >= hi) break;
-            mine += py_escaped_len(next_unit(body, i, n, &ok));
-            if (!ok) break;
+            const uint32_t i0 = i;
+            const uint32_t cp = next_unit(body, i, n, &L.ok);
+            if (!L.ok) break;
+            const uint32_t ol = py_escaped_len(cp), il = i - i0;
+            mine += ol;
+            if (ol != il) L.len_change = true;
+            else if (il >= 6u) {                                      // \uXXXX or a surrogate pair, same length: is the text already canonical?
+                bool differs = cp == 0xFFFDu || hex_has_upper(ld_u32_unaligned(body + i0 + 2));
+                if (il == 12u) differs |= hex_has_upper(ld_u32_unaligned(body + i0 + 8));
+                if (differs) {
+                    if (L.npatch < 2u) { L.patch_pos[L.npatch] = i0; L.patch_cp[L.npatch] = cp; }
+                    ++L.npatch;
+                }
+            }
         }
+        L.out_len = mine;
     }
-    ok = __all_sync(0xffffffffu, ok);
-    *out_len = 2u + warp_sum(mine);
-    if (lane_info) lane_info[lane] = mine | ((start - lo) << 24);     // chunk output < 2^24 bytes for any accepted payload
+    const bool ok = __all_sync(0xffffffffu, L.ok);
+    *out_len = 2u + warp_sum(L.out_len);
+    *fast = __all_sync(0xffffffffu, !L.len_change && L.npatch <= 2u);
     return ok;
 }
 
-// Warp-cooperative: write json.dumps(body) to dst (global). Only called after esc_measure said ok.
-__device__ __noinline__ void esc_emit(const uint8_t* __restrict__ body, uint32_t n, int lane, uint8_t* __restrict__ dst, const uint32_t* lane_info) {
+// fast emit: the token itself, then the same-length patches
+__device__ __forceinline__ void esc_emit_fast(const uint8_t* __restrict__ token, uint32_t tok_len, int lane, uint8_t* __restrict__ dst, const EscLane& L) {
+    warp_copy(dst, token, tok_len, lane);
+    __syncwarp();
+    for (uint32_t q = 0; q < L.npatch && q < 2u; ++q) py_emit(L.patch_cp[q], dst + 1 + L.patch_pos[q]);
+}
+
+// general emit (units change length): every lane re-walks its chunk and writes at its scanned offset
+__device__ __noinline__ void esc_emit_general(const uint8_t* __restrict__ body, uint32_t n, int lane, uint8_t* __restrict__ dst, const EscLane& L) {
     const uint32_t S = (n + 31u) / 32u;
     const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
     bool ok = true;
-    uint32_t mine = 0, start = lo;
-    if (lane_info) { const uint32_t w = lane_info[lane]; mine = w & 0xFFFFFFu; start = lo + (w >> 24); }
-    else if (lo < hi) {
-        start = first_unit_start(body, n, lo);
-        uint32_t i = start;
-        while (i < hi) {
-            while (i < hi && plain_byte(body[i])) { ++i; ++mine; }
-            if (i >= hi) break;
-            mine += py_escaped_len(next_unit(body, i, n, &ok));
-        }
-    }
-    const uint32_t at = 1u + warp_excl_scan(mine, lane);
+    const uint32_t at = 1u + warp_excl_scan(L.out_len, lane);
     if (lane == 0) dst[0] = '"';
-    if (lane == 31) dst[at + mine] = '"';
+    if (lane == 31) dst[at + L.out_len] = '"';
     if (lo < hi) {
         uint8_t* o = dst + at;
-        uint32_t i = start;
+        uint32_t i = L.start;
         while (i < hi) {
             while (i < hi) { const uint32_t c = body[i]; if (!plain_byte(c)) break; *o++ = (uint8_t)c; ++i; }
             if (i >= hi) break;
@@ -360,7 +397,6 @@ __device__ __noinline__ void esc_emit(const uint8_t* __restrict__ body, uint32_t
     }
 }
 
-// ------------------------------------------------------------------ the kernel
 // ================================================================== the kernel: warp-autonomous
 // Every WARP is an independent worker with its own ticket pipeline, its own slice of shared memory
 // (slot metadata + one stage buffer + one mbarrier) and its own cursor add. There is no block
@@ -598,7 +634,6 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
 // straight from the ring in global memory. Thousands of independent warps: latency is irrelevant here.
 constexpr int DS_WARPS = 8;
 __global__ void __launch_bounds__(DS_WARPS * 32) drain_slow_kernel(DrainArgs a) {
-    __shared__ uint32_t s_info[DS_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_slow = a.ctl->n_slow;
     for (;;) {
@@ -610,12 +645,14 @@ __global__ void __launch_bounds__(DS_WARPS * 32) drain_slow_kernel(DrainArgs a) 
         const uint32_t len = it.len & 0x7FFFFFFFu;
         const uint8_t* p = a.payload + it.goff;
         TaskRec rec; rec.ready = 1; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
-        bool par = false;
+        bool par = false, fast = false;
+        EscLane L; L.start = 0; L.out_len = 0; L.npatch = 0; L.ok = true; L.len_change = false;
+        L.patch_pos[0] = L.patch_pos[1] = 0; L.patch_cp[0] = L.patch_cp[1] = 0;
+        const uint32_t nbody = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
         if (it.len & 0x80000000u) {                                        // canonical frame: the body needs transcoding
             uint32_t ol;
-            const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
-            par = esc_measure(p + FRAME_PRE_LEN, n, lane, &ol, s_info[warp]);
-            if (par) { rec.has = 1; rec.mode = OM_STR_PAR; rec.src_off = FRAME_PRE_LEN; rec.src_len = n; rec.out_len = ol; }
+            par = esc_scan(p + FRAME_PRE_LEN, nbody, lane, L, &ol, &fast);
+            if (par) { rec.has = 1; rec.mode = OM_STR_PAR; rec.src_off = FRAME_PRE_LEN; rec.src_len = nbody; rec.out_len = ol; }
         }
         if (!par) {                                                        // the sequential validating parser decides
             if (lane == 0) d2_parse_and_size<0>(p, len, rec, nullptr);
@@ -631,7 +668,10 @@ __global__ void __launch_bounds__(DS_WARPS * 32) drain_slow_kernel(DrainArgs a) 
         if (!fits && lane == 0) a.ctl->overflow = 1u;
         if (rec.has && fits) {
             uint8_t* o = a.out_payload + base;
-            if (rec.mode == OM_STR_PAR) esc_emit(p + rec.src_off, rec.src_len, lane, o, s_info[warp]);
+            if (rec.mode == OM_STR_PAR) {
+                if (fast) esc_emit_fast(p + FRAME_PRE_LEN - 1, nbody + 2, lane, o, L);
+                else      esc_emit_general(p + FRAME_PRE_LEN, nbody, lane, o, L);
+            }
             else if (rec.mode == OM_COPY) warp_copy(o, p + rec.src_off, rec.src_len, lane);
             else if (lane == 0) d2_phase_b_task<0>(p, rec, o);
         }

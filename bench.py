@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--tasks", type=int, default=1_000_000, help="tasks per GPU per step")
     ap.add_argument("--chars", type=int, default=256)
     ap.add_argument("--handler", default="identity")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--adversarial", type=float, default=0.01, help="share of tasks whose string needs escaping (SURVEY.md §8d: 1 %%)")
     return ap.parse_args()
@@ -207,30 +207,45 @@ def main():
     assert res.n == n and dq.depth() == 0
 
     # ------------------------------------------------------------------ end to end through the C ABI, host buffers
-    pin_ids = dq.pinned(n * 16); pin_pl = dq.pinned(in_bytes); pin_off = dq.pinned((n + 1) * 8)
-    pin_ids.array[:] = batch.task_ids.reshape(-1); pin_pl.array[:] = batch.payload
-    pin_off.view(np.uint64, n + 1)[:] = batch.offsets
+    # Every step copies that step's inputs host->device from pinned memory and reads that step's result
+    # records back device->host. Steps are software-pipelined the way a gateway would run them: the push of
+    # batch k+1 is enqueued (b9_batch_push_async) before batch k is drained, so H2D(k+1) overlaps the kernel
+    # and D2H(k) on the full-duplex link. Two input buffer sets alternate; results land in one pinned set.
+    pins = []
+    for _ in range(2):
+        pi = dq.pinned(n * 16); pp = dq.pinned(in_bytes); po = dq.pinned((n + 1) * 8)
+        pi.array[:] = batch.task_ids.reshape(-1); pp.array[:] = batch.payload
+        po.view(np.uint64, n + 1)[:] = batch.offsets
+        pins.append((pi, pp, po))
     cap_bytes = out_bytes + 4096
     o_ids = dq.pinned(n * 16); o_st = dq.pinned(n); o_has = dq.pinned(n); o_off = dq.pinned(n * 8); o_len = dq.pinned(n * 4); o_pl = dq.pinned(cap_bytes)
     resbuf = L.Results(o_ids.ptr, o_st.ptr, o_has.ptr, o_off.ptr, o_len.ptr, o_pl.ptr, n, cap_bytes, 0, 0, 0, 0)
     lib = L.load()
     hid = {"identity": 0, "crc32": 1, "vadd_f32": 2, "json_sum": 3}[args.handler]
 
-    def e2e_step():
-        rc = lib.b9_batch_push(dq._ctx, pin_ids.ptr, pin_pl.ptr, pin_off.ptr, n, None)
+    def e2e_push(k):
+        pi, pp, po = pins[k & 1]
+        rc = lib.b9_batch_push_async(dq._ctx, pi.ptr, pp.ptr, po.ptr, n, None)
         if rc != 0:
             raise SystemExit("push failed: " + L.last_error())
+
+    def e2e_drain():
         r = lib.b9_drain(dq._ctx, hid, n, C.byref(resbuf))
         if r != n:
             raise SystemExit(f"drain returned {r}: " + L.last_error())
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_run(steps):
+        e2e_push(0)
+        for k in range(steps):
+            if k + 1 < steps:
+                e2e_push(k + 1)
+            e2e_drain()
+
+    e2e_run(3)
     s0 = dq.stats()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
+    e2e_run(args.e2e_steps)
     barrier()
     t1 = time.perf_counter()
     s1 = dq.stats()
@@ -280,12 +295,12 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "tasks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / args.e2e_steps,
-                    "api": "b9_batch_push + b9_drain with pinned host buffers"},
+                    "api": "b9_batch_push_async + b9_drain, pinned host buffers, push of step k+1 overlapped with drain of step k"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    for p in (pin_ids, pin_pl, pin_off, o_ids, o_st, o_has, o_off, o_len, o_pl):
+    for p in [x for t in pins for x in t] + [o_ids, o_st, o_has, o_off, o_len, o_pl]:
         p.free()
     dq.close()
     if dist is not None:

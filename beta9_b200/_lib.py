@@ -52,6 +52,7 @@ SYMBOLS = {
     "b9_host_alloc": (C.c_void_p, [C.c_void_p, C.c_uint64]),
     "b9_host_free": (None, [C.c_void_p, C.c_void_p]),
     "b9_batch_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PushMeta)]),
+    "b9_batch_push_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PushMeta)]),
     "b9_depth": (C.c_uint64, [C.c_void_p]),
     "b9_depth_bytes": (C.c_uint64, [C.c_void_p]),
     "b9_expire": (C.c_int64, [C.c_void_p, C.c_int64]),

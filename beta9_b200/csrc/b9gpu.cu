@@ -46,6 +46,7 @@ struct Segment {             // one push = one contiguous byte range of the payl
     uint32_t n;
     uint64_t phys_start, bytes;
     std::vector<uint64_t> rel;   // the batch's offsets (n+1), kept for exact byte accounting
+    cudaEvent_t ready;           // recorded on the ingest stream once the batch is fully on the device
 };
 
 constexpr uint64_t RING_SLACK = 256;   // readable bytes past the ring end (vector loads may over-read)
@@ -59,7 +60,9 @@ struct b9_ctx {
     int resident_ctas = 0;             // drain kernel (v1) CTAs that fit per SM x SMs
     int drain_version = 2;             // B9_DRAIN_KERNEL=1 selects the first-generation kernel (A/B checks)
     uint32_t stage_bytes_override = 0; // B9_STAGE_BYTES: force the v2 stage-buffer size
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;             // drain kernels + D2H
+    cudaStream_t stream_in = nullptr;          // H2D + ingest kernel (so that pushes overlap drains: PCIe is full duplex)
+    std::vector<cudaEvent_t> event_pool;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     std::mutex mu;
 
@@ -96,7 +99,10 @@ struct b9_ctx {
 namespace {
 
 void free_segments(b9_ctx* c) {
-    while (!c->segs.empty() && c->segs.front().first_task + c->segs.front().n <= c->head_task) c->segs.pop_front();
+    while (!c->segs.empty() && c->segs.front().first_task + c->segs.front().n <= c->head_task) {
+        c->event_pool.push_back(c->segs.front().ready);
+        c->segs.pop_front();
+    }
     if (c->segs.empty()) c->write_pos = 0;
 }
 
@@ -204,6 +210,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     CUC(cudaGetDeviceProperties(&prop, c->device));
     c->sm_count = prop.multiProcessorCount;
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b)); CUC(cudaEventCreate(&c->ev_c)); CUC(cudaEventCreate(&c->ev_d));
     const uint32_t rt = c->ring_tasks, md = c->max_drain_tasks;
     CUC(cudaMalloc(&c->d_payload, c->ring_bytes + RING_SLACK));
@@ -246,6 +253,9 @@ void b9_ctx_destroy(b9_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream_in) cudaStreamSynchronize(c->stream_in);
+    for (Segment& sg : c->segs) cudaEventDestroy(sg.ready);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->d_payload); cudaFree(c->d_off); cudaFree(c->d_hdr); cudaFree(c->d_ids); cudaFree(c->d_ts); cudaFree(c->d_exp);
     cudaFree(c->d_in_off); cudaFree(c->d_in_ts); cudaFree(c->d_in_exp); cudaFree(c->d_in_retries); cudaFree(c->d_in_flags);
     cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len); cudaFree(c->d_slow);
@@ -257,6 +267,7 @@ void b9_ctx_destroy(b9_ctx* c) {
     if (c->ev_c) cudaEventDestroy(c->ev_c);
     if (c->ev_d) cudaEventDestroy(c->ev_d);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream_in) cudaStreamDestroy(c->stream_in);
     delete c;
 }
 
@@ -275,7 +286,7 @@ void b9_host_free(b9_ctx* c, void* p) {
     cudaFreeHost(p);
 }
 
-int b9_batch_push(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, const uint64_t* offsets, uint32_t n, const b9_push_meta* meta) {
+static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, const uint64_t* offsets, uint32_t n, const b9_push_meta* meta, bool wait) {
     if (!c) return fail(B9_EINVAL, "b9_batch_push: ctx is NULL");
     if (n == 0) return B9_OK;
     if (!task_ids || !payload || !offsets) return fail(B9_EINVAL, "b9_batch_push: NULL buffer");
@@ -299,7 +310,10 @@ int b9_batch_push(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, co
     if (!place_segment(c, bytes, &start))
         return fail(B9_ENOSPC, "b9_batch_push: %llu payload bytes do not fit the ring (%llu pending of %llu)",
                     (unsigned long long)bytes, (unsigned long long)c->pending_bytes, (unsigned long long)c->ring_bytes);
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->stream_in;
+    cudaEvent_t ready;
+    if (!c->event_pool.empty()) { ready = c->event_pool.back(); c->event_pool.pop_back(); }
+    else CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     CU(cudaEventRecord(c->ev_a, s));
     if (bytes) CU(cudaMemcpyAsync(c->d_payload + start, payload + offsets[0], bytes, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(c->d_in_off, offsets, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
@@ -321,9 +335,12 @@ int b9_batch_push(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, co
                                                   c->d_off, c->d_hdr, c->d_ts, c->d_exp);
     CU(cudaGetLastError());
     c->stats.kernel_launches++;
-    CU(cudaStreamSynchronize(s));            // the caller may reuse its buffers as soon as we return
-    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->stats.last_push_h2d_ms = ms;
-    c->segs.push_back(Segment{c->tail_task, n, start, bytes, std::vector<uint64_t>(offsets, offsets + n + 1)});
+    CU(cudaEventRecord(ready, s));
+    if (wait) {
+        CU(cudaStreamSynchronize(s));        // the caller may reuse its buffers as soon as we return
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->stats.last_push_h2d_ms = ms;
+    }
+    c->segs.push_back(Segment{c->tail_task, n, start, bytes, std::vector<uint64_t>(offsets, offsets + n + 1), ready});
     c->write_pos = start + ((bytes + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
     c->tail_task += n;
     c->pending_bytes += bytes;
@@ -331,6 +348,14 @@ int b9_batch_push(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, co
     c->stats.tasks_pushed += n;
     c->stats.bytes_h2d += bytes + ((uint64_t)n + 1) * 8 + (uint64_t)n * 16 + meta_bytes;
     return B9_OK;
+}
+
+int b9_batch_push(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, const uint64_t* offsets, uint32_t n, const b9_push_meta* meta) {
+    return push_impl(c, task_ids, payload, offsets, n, meta, true);
+}
+
+int b9_batch_push_async(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, const uint64_t* offsets, uint32_t n, const b9_push_meta* meta) {
+    return push_impl(c, task_ids, payload, offsets, n, meta, false);
 }
 
 uint64_t b9_depth(b9_ctx* c) {
@@ -351,6 +376,7 @@ int64_t b9_expire(b9_ctx* c, int64_t now_unix_ns) {
     const uint64_t depth = c->tail_task - c->head_task;
     if (!depth) return 0;
     CU(cudaSetDevice(c->device));
+    for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));
     CU(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned long long), c->stream));
     expire_kernel<<<(uint32_t)((depth + 255) / 256), 256, 0, c->stream>>>(c->d_hdr, c->d_exp, c->slot_mask, c->head_task, (uint32_t)depth, now_unix_ns, c->d_count);
     CU(cudaGetLastError());
@@ -379,7 +405,10 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
         uint64_t lo = c->head_task, hi = c->head_task + n;
         for (const Segment& sg : c->segs) {
             uint64_t a = std::max<uint64_t>(lo, sg.first_task), b = std::min<uint64_t>(hi, sg.first_task + sg.n);
-            if (a < b) in_bytes += sg.rel[b - sg.first_task] - sg.rel[a - sg.first_task];
+            if (a < b) {
+                in_bytes += sg.rel[b - sg.first_task] - sg.rel[a - sg.first_task];
+                CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));     // this batch's H2D + ingest must have landed
+            }
         }
     }
     DrainArgs a{};
@@ -494,6 +523,7 @@ int b9_stats_get(b9_ctx* c, b9_stats* out) {
 int b9_sync(b9_ctx* c) {
     if (!c) return fail(B9_EINVAL, "b9_sync: ctx is NULL");
     CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream_in));
     CU(cudaStreamSynchronize(c->stream));
     return B9_OK;
 }

@@ -153,6 +153,13 @@ void        b9_host_free(b9_ctx *ctx, void *p);
 int      b9_batch_push(b9_ctx *ctx, const uint8_t *task_ids, const uint8_t *payload,
                        const uint64_t *offsets, uint32_t n, const b9_push_meta *meta);
 
+/* Same, but returns as soon as the copies are enqueued on the context's ingest stream: the caller's
+ * buffers MUST be page-locked (b9_host_alloc) and stay untouched until b9_sync() or until a drain has
+ * returned the batch's results. Lets the next batch stream in while the previous one is drained and
+ * read back (PCIe is full duplex). */
+int      b9_batch_push_async(b9_ctx *ctx, const uint8_t *task_ids, const uint8_t *payload,
+                             const uint64_t *offsets, uint32_t n, const b9_push_meta *meta);
+
 /* Pending tasks = what `TaskRepository.TasksInFlight` / `taskQueueClient.QueueLength` report for
  * this queue (pkg/repository/task_redis.go:112-119, taskqueue/client.go:99-106); feeds
  * `taskQueueAutoscalerSampleFunc` (taskqueue/autoscaler.go:18-51) unchanged. */

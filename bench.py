@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--handler", default="identity")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skew", type=float, default=0.0, help="N>1: rank 0 pushes (1+skew)x the tasks and every step starts with the NCCL rebalance")
     ap.add_argument("--adversarial", type=float, default=0.01, help="share of tasks whose string needs escaping (SURVEY.md §8d: 1 %%)")
     return ap.parse_args()
 
@@ -105,8 +106,11 @@ def dist_env():
 
 def workload(args, rank):
     from beta9_b200 import synth
+    n = args.tasks
+    if args.skew > 0 and rank == 0 and int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        n = int(n * (1 + args.skew))
     if args.handler == "identity":
-        return synth.strings_batch(args.tasks, args.chars, adversarial_frac=args.adversarial, seed=synth.SEED + 1000 * rank)
+        return synth.strings_batch(n, args.chars, adversarial_frac=args.adversarial, seed=synth.SEED + 1000 * rank)
     raise SystemExit(f"bench: handler {args.handler} has no bench workload yet")
 
 
@@ -167,6 +171,14 @@ def main():
     dq = DeviceQueue(device=local_rank, ring_bytes=max(1 << 30, 4 * in_bytes), ring_tasks=max(1 << 21, 4 * n),
                      max_drain_tasks=max(1 << 21, n), max_result_bytes=max(1 << 30, 2 * in_bytes))
 
+    rebalance = world > 1 and args.skew > 0
+    if rebalance:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(DeviceQueue.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        dq.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -179,8 +191,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def reduce_sum(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     # ------------------------------------------------------------------ device-resident steps
     dq.push_batch(batch.task_ids, batch.payload, batch.offsets)
+    rebalance_info = None
+    n_pushed = n
+    if rebalance:
+        # skewed ingest (rank 0 holds (1+skew)x): ONE NCCL all-to-all evens the pending bytes out before the drain
+        barrier()
+        r0 = time.perf_counter()
+        info = dq.rebalance()
+        barrier()
+        r_ms = reduce_max(1e3 * (time.perf_counter() - r0))
+        rebalance_info = {"ms": r_ms, "tasks_before_rank0": int(info.tasks_before) if rank == 0 else None,
+                          "bytes_moved_total": reduce_sum(float(info.bytes_sent)), "skew": args.skew}
+        n = dq.depth()                                   # my share after the exchange
+    n_total = int(round(reduce_sum(float(n))))
     kernel_ms = []
     for _ in range(args.warmup):
         dq.drain_launch(args.handler, n, peek=True)
@@ -199,12 +231,21 @@ def main():
     assert got == n, (got, n)
     out_bytes = int(dq.stats().last_drain_out_bytes)
     elapsed = reduce_max(t1 - t0)
-    value = world * n * args.steps / elapsed
+    value = n_total * args.steps / elapsed
     k_ms = reduce_max(statistics.mean(kernel_ms))
     # drop the resident batch
     dq.drain_launch(args.handler, n, peek=False)
     res = dq.fetch()
     assert res.n == n and dq.depth() == 0
+    if rebalance:
+        # the end-to-end leg below runs the un-skewed shard shape (the exchange is timed above)
+        res_n_after = n
+        n = min(n_pushed, args.tasks)
+        batch = batch.slice(0, n)
+        in_bytes = int(batch.payload.size)
+        dq.push_batch(batch.task_ids, batch.payload, batch.offsets)
+        res = dq.drain(args.handler, n)
+        out_bytes = int(res.payload.size)
 
     # ------------------------------------------------------------------ end to end through the C ABI, host buffers
     # Every step copies that step's inputs host->device from pinned memory and reads that step's result
@@ -250,7 +291,7 @@ def main():
     t1 = time.perf_counter()
     s1 = dq.stats()
     e2e_elapsed = reduce_max(t1 - t0)
-    e2e_value = world * n * args.e2e_steps / e2e_elapsed
+    e2e_value = int(round(reduce_sum(float(n)))) * args.e2e_steps / e2e_elapsed
     h2d = (s1.bytes_h2d - s0.bytes_h2d) // args.e2e_steps
     d2h = (s1.bytes_d2h - s0.bytes_d2h) // args.e2e_steps
     # the records that came back are the real ones
@@ -287,7 +328,7 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"configs[1]: {n} x {args.chars}-char identity tasks per GPU ({100 * args.adversarial:g}% adversarial escapes), "
                                    f"resident in HBM", "handler": args.handler, "tasks_per_gpu": n,
-                       "parallelism": f"shard{world}" if world > 1 else "single",
+                       "parallelism": (f"shard{world}" + ("+nccl_rebalance" if rebalance else "")) if world > 1 else "single",
                        "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "b9::drain_kernel<identity>", "kernel_ms": k_ms,
@@ -297,6 +338,7 @@ def main():
                     "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / args.e2e_steps,
                     "api": "b9_batch_push_async + b9_drain, pinned host buffers, push of step k+1 overlapped with drain of step k"},
             "gpu_launches": int(launches),
+            "rebalance": rebalance_info,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -40,6 +40,12 @@ class Stats(C.Structure):
                 ("last_drain_in_bytes", C.c_uint64), ("last_drain_out_bytes", C.c_uint64)]
 
 
+class RebalanceInfo(C.Structure):
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("tasks_before", C.c_uint64), ("bytes_before", C.c_uint64),
+                ("tasks_sent", C.c_uint64), ("bytes_sent", C.c_uint64), ("tasks_received", C.c_uint64),
+                ("bytes_received", C.c_uint64), ("tasks_after", C.c_uint64), ("bytes_after", C.c_uint64)]
+
+
 # every symbol include/b9gpu.h declares: (restype, argtypes)
 SYMBOLS = {
     "b9_abi_version": (C.c_uint32, []),
@@ -59,6 +65,10 @@ SYMBOLS = {
     "b9_drain": (C.c_int64, [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(Results)]),
     "b9_drain_launch": (C.c_int64, [C.c_void_p, C.c_int, C.c_uint32, C.c_int]),
     "b9_drain_fetch": (C.c_int64, [C.c_void_p, C.POINTER(Results)]),
+    "b9_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "b9_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "b9_rebalance": (C.c_int, [C.c_void_p, C.POINTER(RebalanceInfo)]),
+    "b9_rebalance_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "b9_stats_get": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "b9_sync": (C.c_int, [C.c_void_p]),
     "b9_task_queue_scale": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int)]),

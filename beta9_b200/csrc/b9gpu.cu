@@ -22,6 +22,9 @@
 #include "../../include/b9gpu.h"
 #include "drain_kernel.cuh"
 #include "drain2.cuh"
+#include "rebalance_plan.h"
+
+#include <dlfcn.h>
 
 using namespace b9;
 
@@ -40,6 +43,7 @@ int fail(int code, const char* fmt, ...) {
     return fail(B9_EIO, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 uint64_t pow2_ceil(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
+void nccl_comm_destroy(void* comm);   // defined with the NCCL loader below
 
 struct Segment {             // one push = one contiguous byte range of the payload ring
     uint64_t first_task;     // logical index of its first task
@@ -92,6 +96,9 @@ struct b9_ctx {
     // results waiting on the device for b9_drain_fetch
     bool have_results = false, res_peek = false;
     uint32_t res_n = 0, res_popped = 0; uint64_t res_bytes = 0, res_in_bytes = 0;
+
+    // ---- multi-GPU (NCCL, loaded with dlopen: the library has no link-time dependency on it)
+    void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
 
     b9_stats stats{};
 };
@@ -254,6 +261,7 @@ void b9_ctx_destroy(b9_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_in) cudaStreamSynchronize(c->stream_in);
+    if (c->nccl_comm) nccl_comm_destroy(c->nccl_comm);
     for (Segment& sg : c->segs) cudaEventDestroy(sg.ready);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->d_payload); cudaFree(c->d_off); cudaFree(c->d_hdr); cudaFree(c->d_ids); cudaFree(c->d_ts); cudaFree(c->d_exp);
@@ -290,16 +298,8 @@ static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload,
     if (!c) return fail(B9_EINVAL, "b9_batch_push: ctx is NULL");
     if (n == 0) return B9_OK;
     if (!task_ids || !payload || !offsets) return fail(B9_EINVAL, "b9_batch_push: NULL buffer");
-    // validate the index before anything is copied
-    for (uint32_t i = 0; i < n; ++i) {
-        if (offsets[i + 1] < offsets[i]) return fail(B9_EINVAL, "b9_batch_push: offsets not monotonic at task %u", i);
-        if (offsets[i + 1] - offsets[i] > c->max_task_bytes)
-            return fail(B9_E2BIG, "b9_batch_push: task %u is %llu bytes, max_task_bytes is %u", i,
-                        (unsigned long long)(offsets[i + 1] - offsets[i]), c->max_task_bytes);
-    }
+    if (offsets[n] < offsets[0]) return fail(B9_EINVAL, "b9_batch_push: offsets not monotonic");
     const uint64_t bytes = offsets[n] - offsets[0];
-    uint64_t n_cancelled = 0;
-    if (meta && meta->flags) for (uint32_t i = 0; i < n; ++i) n_cancelled += (meta->flags[i] & B9_TF_CANCELLED) ? 1 : 0;
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     free_segments(c);
@@ -315,7 +315,28 @@ static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload,
     if (!c->event_pool.empty()) { ready = c->event_pool.back(); c->event_pool.pop_back(); }
     else CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     CU(cudaEventRecord(c->ev_a, s));
+    // the payload DMA goes first (into ring space that is free until this push is committed), so that
+    // the O(n) host-side validation of the index below runs while the bytes are already on the wire
     if (bytes) CU(cudaMemcpyAsync(c->d_payload + start, payload + offsets[0], bytes, cudaMemcpyHostToDevice, s));
+    uint64_t n_cancelled = 0;
+    {
+        const uint32_t maxb = c->max_task_bytes;
+        uint64_t bad = ~0ull, big = ~0ull, prev = offsets[0];
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint64_t cur = offsets[i + 1];
+            if (cur < prev) { if (bad == ~0ull) bad = i; }
+            else if (cur - prev > maxb) { if (big == ~0ull) big = i; }
+            prev = cur;
+        }
+        if (bad != ~0ull || big != ~0ull) {
+            c->event_pool.push_back(ready);
+            cudaStreamSynchronize(s);            // the stray DMA must not outlive the caller's buffer
+            if (bad != ~0ull) return fail(B9_EINVAL, "b9_batch_push: offsets not monotonic at task %llu", (unsigned long long)bad);
+            return fail(B9_E2BIG, "b9_batch_push: task %llu is %llu bytes, max_task_bytes is %u", (unsigned long long)big,
+                        (unsigned long long)(offsets[big + 1] - offsets[big]), maxb);
+        }
+        if (meta && meta->flags) for (uint32_t i = 0; i < n; ++i) n_cancelled += (meta->flags[i] & B9_TF_CANCELLED) ? 1 : 0;
+    }
     CU(cudaMemcpyAsync(c->d_in_off, offsets, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     // ids go straight into their ring slots (two pieces when the slot ring wraps)
     const uint32_t slot0 = (uint32_t)(c->tail_task & c->slot_mask);
@@ -511,6 +532,290 @@ int64_t b9_drain(b9_ctx* c, int handler, uint32_t max_tasks, b9_results* out) {
     int64_t r = b9_drain_launch(c, handler, max_tasks, /*peek=*/0);
     if (r < 0) return r;
     return b9_drain_fetch(c, out);   // on B9_ENOSPC nothing is consumed and the records stay fetchable
+}
+
+// =========================================================================== multi-GPU: NCCL rebalance
+}  // extern "C" (reopened below)
+
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ struct B9NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct B9NcclId { char internal[128]; };
+constexpr int NCCL_U8 = 1, NCCL_U64 = 5;        // ncclUint8, ncclUint64 (nccl.h ncclDataType_t)
+
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int load_nccl() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.lib) return B9_OK;
+    const char* path = getenv("B9_NCCL_LIB");
+    void* h = dlopen(path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h && !path) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(B9_EIO, "cannot load NCCL (%s); set B9_NCCL_LIB", dlerror());
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return fail(B9_EIO, "NCCL symbol %s missing", name)
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllGather, "ncclAllGather"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = h;
+    return B9_OK;
+}
+void nccl_comm_destroy(void* comm) { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm); }
+#define NC(call) do { int r_ = (call); if (r_ != 0) return fail(B9_EIO, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
+
+// one warp per task: payload bytes into the send buffer, slot words into the meta sections
+__global__ void gather_tasks_kernel(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ off, const uint64_t* __restrict__ hdr,
+                                    const uint4* __restrict__ ids, const int64_t* __restrict__ ts, const int64_t* __restrict__ exp,
+                                    uint32_t slot_mask, uint64_t first_task, uint32_t n, const uint64_t* __restrict__ rel /* n+1, device */,
+                                    uint8_t* __restrict__ out_payload, int64_t* __restrict__ o_ts, int64_t* __restrict__ o_exp,
+                                    uint4* __restrict__ o_ids, uint8_t* __restrict__ o_flags, uint8_t* __restrict__ o_retries) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const uint32_t slot = (uint32_t)((first_task + w) & slot_mask);
+    const uint64_t h = hdr[slot];
+    const uint32_t len = hdr_len(h);
+    const uint8_t* src = payload + off[slot];
+    uint8_t* dst = out_payload + (rel[w] - rel[0]);
+    for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+    if (lane == 0) { o_ts[w] = ts[slot]; o_exp[w] = exp[slot]; o_ids[w] = ids[slot]; o_flags[w] = (uint8_t)hdr_flags(h); o_retries[w] = (uint8_t)(h >> 40); }
+}
+
+__global__ void count_cancelled_kernel(const uint64_t* __restrict__ hdr, uint32_t slot_mask, uint64_t first_task, uint32_t n, unsigned long long* __restrict__ count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (hdr_flags(hdr[(uint32_t)((first_task + i) & slot_mask)]) & 1u)) atomicAdd(count, 1ull);
+}
+
+// layout of one peer's meta message for n tasks (every section 16-byte aligned)
+struct MetaLayout { size_t rel, ts, exp, ids, flags, retries, total; };
+MetaLayout meta_layout(uint64_t n) {
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    MetaLayout m; size_t o = 0;
+    m.rel = o; o = al(o + (n + 1) * 8);
+    m.ts = o; o = al(o + n * 8);
+    m.exp = o; o = al(o + n * 8);
+    m.ids = o; o = al(o + n * 16);
+    m.flags = o; o = al(o + n);
+    m.retries = o; o = al(o + n);
+    m.total = o; return m;
+}
+
+// drop k tasks from the tail of the ring (they were handed to another rank)
+void drop_back(b9_ctx* c, uint64_t k) {
+    while (k && !c->segs.empty()) {
+        Segment& sg = c->segs.back();
+        if (sg.n <= k) {
+            k -= sg.n; c->tail_task -= sg.n; c->pending_bytes -= sg.bytes; c->write_pos = sg.phys_start;
+            c->event_pool.push_back(sg.ready); c->segs.pop_back();
+        } else {
+            const uint32_t keep = sg.n - (uint32_t)k;
+            const uint64_t nb = sg.rel[keep] - sg.rel[0];
+            c->pending_bytes -= sg.bytes - nb; c->tail_task -= k;
+            sg.n = keep; sg.bytes = nb; sg.rel.resize((size_t)keep + 1);
+            c->write_pos = sg.phys_start + ((nb + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
+            k = 0;
+        }
+    }
+    if (c->segs.empty()) c->write_pos = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b9_rebalance_plan(uint32_t world, uint32_t rank, const uint64_t* counts, const uint64_t* bytes, const uint64_t* prefix, uint64_t n,
+                      uint64_t* send_lo, uint64_t* send_hi) {
+    if (!counts || !bytes || !prefix || !send_lo || !send_hi) return fail(B9_EINVAL, "b9_rebalance_plan: NULL argument");
+    if (b9_plan_ranges(world, rank, counts, bytes, prefix, n, send_lo, send_hi)) return fail(B9_EINVAL, "b9_rebalance_plan: table inconsistent with prefix");
+    return B9_OK;
+}
+
+int b9_comm_unique_id(uint8_t* out128) {
+    if (!out128) return fail(B9_EINVAL, "b9_comm_unique_id: NULL");
+    int rc = load_nccl(); if (rc) return rc;
+    B9NcclId id; memset(&id, 0, sizeof id);
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(out128, id.internal, 128);
+    return B9_OK;
+}
+
+int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(B9_EINVAL, "b9_comm_init: bad argument");
+    int rc = load_nccl(); if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    B9NcclId id; memcpy(id.internal, id128, 128);
+    void* comm = nullptr;
+    NC(g_nccl.CommInitRank(&comm, world, id, rank));
+    c->nccl_comm = comm; c->comm_rank = rank; c->comm_world = world;
+    return B9_OK;
+}
+
+// Collective: every rank of the communicator must call it. Moves pending tasks between the ranks'
+// rings so that every rank holds ~1/W of the pending payload bytes: all-gather of
+// (count, bytes), the same byte-quantile plan on every rank, all-gather of the send matrix, then ONE
+// grouped ncclSend/ncclRecv exchange of slot words and payload bytes over NVLink.
+int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
+    if (!c) return fail(B9_EINVAL, "b9_rebalance: ctx is NULL");
+    if (!c->nccl_comm) return fail(B9_EINVAL, "b9_rebalance: b9_comm_init was not called");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const int W = c->comm_world, R = c->comm_rank;
+    cudaStream_t s = c->stream;
+    for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(s, sg.ready, 0));
+    c->have_results = false;
+    free_segments(c);
+    const uint64_t n = c->tail_task - c->head_task;
+    // byte prefix of my pending tasks (host bookkeeping holds every batch's offsets)
+    std::vector<uint64_t> prefix(n + 1, 0);
+    {
+        uint64_t k = 0, acc = 0;
+        for (const Segment& sg : c->segs) {
+            const uint64_t a = std::max<uint64_t>(c->head_task, sg.first_task) - sg.first_task;
+            for (uint64_t i = a; i < sg.n; ++i) { acc += sg.rel[i + 1] - sg.rel[i]; prefix[++k] = acc; }
+        }
+        if (k != n) return fail(B9_EIO, "b9_rebalance: ring bookkeeping inconsistent (%llu vs %llu)", (unsigned long long)k, (unsigned long long)n);
+    }
+    // ---- 1. all-gather (count, bytes)
+    uint64_t* d_tab = nullptr; uint64_t* h_tab = nullptr;
+    const size_t tab_words = (size_t)W * 2 + (size_t)W * W * 2;
+    CU(cudaMalloc(&d_tab, (2 + tab_words) * sizeof(uint64_t)));
+    CU(cudaHostAlloc(&h_tab, (2 + tab_words) * sizeof(uint64_t), cudaHostAllocDefault));
+    struct Cleanup { uint64_t* d; uint64_t* h; std::vector<void*> bufs; ~Cleanup() { cudaFree(d); cudaFreeHost(h); for (void* b : bufs) cudaFree(b); } } cl{d_tab, h_tab, {}};
+    h_tab[0] = n; h_tab[1] = prefix[n];
+    CU(cudaMemcpyAsync(d_tab, h_tab, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    NC(g_nccl.AllGather(d_tab, d_tab + 2, 2, NCCL_U64, c->nccl_comm, s));
+    CU(cudaMemcpyAsync(h_tab + 2, d_tab + 2, (size_t)W * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    std::vector<uint64_t> counts(W), bytes(W), lo(W), hi(W);
+    for (int r = 0; r < W; ++r) { counts[r] = h_tab[2 + 2 * r]; bytes[r] = h_tab[3 + 2 * r]; }
+    // ---- 2. plan
+    if (b9_plan_ranges((uint32_t)W, (uint32_t)R, counts.data(), bytes.data(), prefix.data(), n, lo.data(), hi.data()))
+        return fail(B9_EIO, "b9_rebalance: plan failed");
+    // ---- 3. all-gather of the send matrix rows (tasks, bytes per destination)
+    uint64_t* row = h_tab;   // reuse
+    for (int d = 0; d < W; ++d) { row[2 * d] = hi[d] - lo[d]; row[2 * d + 1] = prefix[hi[d]] - prefix[lo[d]]; }
+    uint64_t* d_row = d_tab; uint64_t* d_mat = d_tab + 2 + (size_t)W * 2;
+    CU(cudaMemcpyAsync(d_row, row, (size_t)W * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));   // d_tab has room: 2 + 2W >= 2W
+    NC(g_nccl.AllGather(d_row, d_mat, (size_t)W * 2, NCCL_U64, c->nccl_comm, s));
+    std::vector<uint64_t> mat((size_t)W * W * 2);
+    CU(cudaMemcpyAsync(mat.data(), d_mat, mat.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    auto M_tasks = [&](int src, int dst) { return mat[((size_t)src * W + dst) * 2]; };
+    auto M_bytes = [&](int src, int dst) { return mat[((size_t)src * W + dst) * 2 + 1]; };
+    // ---- 4. pack what leaves, allocate what arrives
+    std::vector<uint8_t*> s_meta(W, nullptr), s_pay(W, nullptr), r_meta(W, nullptr), r_pay(W, nullptr);
+    uint64_t sent_tasks = 0, sent_bytes = 0, recv_tasks = 0, recv_bytes = 0;
+    for (int d = 0; d < W; ++d) {
+        if (d == R) continue;
+        const uint64_t k = hi[d] - lo[d];
+        if (k) {
+            const MetaLayout ml = meta_layout(k);
+            const uint64_t pb = prefix[hi[d]] - prefix[lo[d]];
+            CU(cudaMalloc(&s_meta[d], ml.total)); cl.bufs.push_back(s_meta[d]);
+            CU(cudaMalloc(&s_pay[d], pb + 16)); cl.bufs.push_back(s_pay[d]);
+            CU(cudaMemcpyAsync(s_meta[d] + ml.rel, prefix.data() + lo[d], (k + 1) * 8, cudaMemcpyHostToDevice, s));
+            const uint32_t blocks = (uint32_t)((k * 32 + 255) / 256);
+            gather_tasks_kernel<<<blocks, 256, 0, s>>>(c->d_payload, c->d_off, c->d_hdr, c->d_ids, c->d_ts, c->d_exp, c->slot_mask,
+                                                       c->head_task + lo[d], (uint32_t)k, (const uint64_t*)(s_meta[d] + ml.rel), s_pay[d],
+                                                       (int64_t*)(s_meta[d] + ml.ts), (int64_t*)(s_meta[d] + ml.exp), (uint4*)(s_meta[d] + ml.ids),
+                                                       s_meta[d] + ml.flags, s_meta[d] + ml.retries);
+            CU(cudaGetLastError());
+            c->stats.kernel_launches++;
+            sent_tasks += k; sent_bytes += pb;
+        }
+        const uint64_t rk = M_tasks(d, R);
+        if (rk) {
+            CU(cudaMalloc(&r_meta[d], meta_layout(rk).total)); cl.bufs.push_back(r_meta[d]);
+            CU(cudaMalloc(&r_pay[d], M_bytes(d, R) + 16)); cl.bufs.push_back(r_pay[d]);
+            recv_tasks += rk; recv_bytes += M_bytes(d, R);
+        }
+    }
+    // capacity for what arrives (after what leaves is dropped)
+    if (n - sent_tasks + recv_tasks > c->ring_tasks)
+        return fail(B9_ENOSPC, "b9_rebalance: %llu incoming tasks do not fit the slot ring", (unsigned long long)recv_tasks);
+    // ---- 5. the exchange: one grouped send/recv
+    NC(g_nccl.GroupStart());
+    for (int d = 0; d < W; ++d) {
+        if (d == R) continue;
+        const uint64_t k = hi[d] - lo[d];
+        if (k) {
+            NC(g_nccl.Send(s_meta[d], meta_layout(k).total, NCCL_U8, d, c->nccl_comm, s));
+            const uint64_t pb = prefix[hi[d]] - prefix[lo[d]];
+            if (pb) NC(g_nccl.Send(s_pay[d], pb, NCCL_U8, d, c->nccl_comm, s));
+        }
+        const uint64_t rk = M_tasks(d, R);
+        if (rk) {
+            NC(g_nccl.Recv(r_meta[d], meta_layout(rk).total, NCCL_U8, d, c->nccl_comm, s));
+            if (M_bytes(d, R)) NC(g_nccl.Recv(r_pay[d], M_bytes(d, R), NCCL_U8, d, c->nccl_comm, s));
+        }
+    }
+    NC(g_nccl.GroupEnd());
+    CU(cudaStreamSynchronize(s));
+    // ---- 6. what left: a prefix of my FIFO went to lower ranks, a suffix to higher ranks
+    {
+        const uint64_t front = lo[R], back = n - hi[R];
+        if (front) { c->pending_bytes -= prefix[front]; c->head_task += front; free_segments(c); }
+        if (back) drop_back(c, back);
+    }
+    // ---- 7. what arrived is appended, source by source, as new segments of the ring
+    for (int src = 0; src < W; ++src) {
+        const uint64_t rk = (src == R) ? 0 : M_tasks(src, R);
+        if (!rk) continue;
+        const MetaLayout ml = meta_layout(rk);
+        const uint64_t pb = M_bytes(src, R);
+        std::vector<uint64_t> rel(rk + 1);
+        CU(cudaMemcpyAsync(rel.data(), r_meta[src] + ml.rel, (rk + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        uint64_t start = 0;
+        free_segments(c);
+        if (!place_segment(c, pb, &start)) return fail(B9_ENOSPC, "b9_rebalance: %llu incoming bytes do not fit the ring", (unsigned long long)pb);
+        if (pb) CU(cudaMemcpyAsync(c->d_payload + start, r_pay[src], pb, cudaMemcpyDeviceToDevice, s));
+        // slot words: ids may wrap in the slot ring
+        const uint32_t slot0 = (uint32_t)(c->tail_task & c->slot_mask);
+        const uint32_t first = (uint32_t)std::min<uint64_t>(rk, c->ring_tasks - slot0);
+        CU(cudaMemcpyAsync(c->d_ids + slot0, r_meta[src] + ml.ids, (size_t)first * 16, cudaMemcpyDeviceToDevice, s));
+        if (first < rk) CU(cudaMemcpyAsync(c->d_ids, r_meta[src] + ml.ids + (size_t)first * 16, (size_t)(rk - first) * 16, cudaMemcpyDeviceToDevice, s));
+        ingest_kernel<<<(uint32_t)((rk + 255) / 256), 256, 0, s>>>((const uint64_t*)(r_meta[src] + ml.rel), (uint32_t)rk, start, c->tail_task, c->slot_mask,
+                                                                  (const int64_t*)(r_meta[src] + ml.ts), (const int64_t*)(r_meta[src] + ml.exp),
+                                                                  r_meta[src] + ml.retries, r_meta[src] + ml.flags, c->d_off, c->d_hdr, c->d_ts, c->d_exp);
+        CU(cudaGetLastError());
+        c->stats.kernel_launches++;
+        cudaEvent_t ready;
+        if (!c->event_pool.empty()) { ready = c->event_pool.back(); c->event_pool.pop_back(); }
+        else CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(ready, s));
+        c->segs.push_back(Segment{c->tail_task, (uint32_t)rk, start, pb, std::move(rel), ready});
+        c->write_pos = start + ((pb + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
+        c->tail_task += rk; c->pending_bytes += pb;
+    }
+    // ---- 8. cancelled tasks may have moved either way: recount over the new window
+    {
+        const uint64_t depth = c->tail_task - c->head_task;
+        CU(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned long long), s));
+        if (depth) { count_cancelled_kernel<<<(uint32_t)((depth + 255) / 256), 256, 0, s>>>(c->d_hdr, c->slot_mask, c->head_task, (uint32_t)depth, c->d_count); CU(cudaGetLastError()); c->stats.kernel_launches++; }
+        CU(cudaMemcpyAsync(c->h_count, c->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        c->cancelled_pending = *c->h_count;
+    }
+    if (info) {
+        info->world = (uint32_t)W; info->rank = (uint32_t)R;
+        info->tasks_before = n; info->bytes_before = prefix[n];
+        info->tasks_sent = sent_tasks; info->bytes_sent = sent_bytes; info->tasks_received = recv_tasks; info->bytes_received = recv_bytes;
+        info->tasks_after = c->tail_task - c->head_task; info->bytes_after = c->pending_bytes;
+    }
+    return B9_OK;
 }
 
 int b9_stats_get(b9_ctx* c, b9_stats* out) {

@@ -172,6 +172,25 @@ class DeviceQueue:
         """b9_drain straight into caller-owned (ideally pinned) buffers described by `res`."""
         return self._check(self._lib.b9_drain(self._ctx, HANDLERS[handler], max_tasks, C.byref(res)))
 
+    # ---- multi-GPU (one DeviceQueue per rank / GPU)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = L.load().b9_comm_unique_id(buf)
+        if rc != 0:
+            raise L.B9Error(rc, L.last_error())
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.b9_comm_init(self._ctx, buf, rank, world))
+
+    def rebalance(self) -> "L.RebalanceInfo":
+        """Collective: byte-quantile rebalance of the pending ring over the communicator (NCCL all-to-all)."""
+        info = L.RebalanceInfo()
+        self._check(self._lib.b9_rebalance(self._ctx, C.byref(info)))
+        return info
+
     def stats(self) -> "L.Stats":
         s = L.Stats()
         self._check(self._lib.b9_stats_get(self._ctx, C.byref(s)))
@@ -182,6 +201,18 @@ class DeviceQueue:
 
     def pinned(self, nbytes: int) -> PinnedBuffer:
         return PinnedBuffer(self, nbytes)
+
+
+def rebalance_plan(world: int, rank: int, counts, nbytes, prefix) -> Tuple[np.ndarray, np.ndarray]:
+    """b9_rebalance_plan: local FIFO range [lo[d], hi[d]) destined for every rank d (pure host arithmetic)."""
+    counts = np.ascontiguousarray(counts, np.uint64); nbytes = np.ascontiguousarray(nbytes, np.uint64)
+    prefix = np.ascontiguousarray(prefix, np.uint64)
+    lo = np.zeros(world, np.uint64); hi = np.zeros(world, np.uint64)
+    rc = L.load().b9_rebalance_plan(world, rank, counts.ctypes.data, nbytes.ctypes.data, prefix.ctypes.data,
+                                    prefix.shape[0] - 1, lo.ctypes.data, hi.ctypes.data)
+    if rc != 0:
+        raise L.B9Error(rc, L.last_error())
+    return lo, hi
 
 
 def task_queue_scale(queue_length: int, tasks_per_container: int, max_containers: int, max_replicas: int) -> Tuple[int, bool]:

@@ -191,6 +191,29 @@ int64_t  b9_drain_fetch(b9_ctx *ctx, b9_results *out);
 /* Device-side encode of the queue wire records (the bytes `TaskMessage.Encode` produces,
  * pkg/types/task.go:79-90) is declared in the "wire" section once implemented. */
 
+/* ---- multi-GPU: one ctx (= one process, one GPU) per rank of a box -------------------------------
+ * The pending ring is sharded over the ranks; tasks are independent units, so the
+ * drain needs no collective. When ingest landed unevenly, b9_rebalance moves pending tasks so that
+ * every rank holds ~1/world of the pending payload BYTES: an all-gather of (count, bytes), the same
+ * byte-quantile plan on every rank (b9_rebalance_plan, also callable on its own), an all-gather of
+ * the send matrix, then one grouped ncclSend/ncclRecv all-to-all of slot words + payload over
+ * NVLink. NCCL is loaded with dlopen (B9_NCCL_LIB or libnccl.so.2). The unique id is created on one
+ * rank and handed to the others by the host (the gateway, or torch.distributed in bench.py). */
+typedef struct b9_rebalance_info {
+    uint32_t world, rank;
+    uint64_t tasks_before, bytes_before;
+    uint64_t tasks_sent, bytes_sent, tasks_received, bytes_received;
+    uint64_t tasks_after, bytes_after;
+} b9_rebalance_info;
+
+int      b9_comm_unique_id(uint8_t *out128);
+int      b9_comm_init(b9_ctx *ctx, const uint8_t *id128, int rank, int world);
+int      b9_rebalance(b9_ctx *ctx, b9_rebalance_info *info);   /* collective over the communicator */
+/* prefix[i] = payload bytes of the caller's pending tasks 0..i-1; fills the local FIFO range
+ * [send_lo[d], send_hi[d]) destined for every rank d. Pure host arithmetic. */
+int      b9_rebalance_plan(uint32_t world, uint32_t rank, const uint64_t *counts, const uint64_t *bytes,
+                           const uint64_t *prefix, uint64_t n, uint64_t *send_lo, uint64_t *send_hi);
+
 int      b9_stats_get(b9_ctx *ctx, b9_stats *out);
 int      b9_sync(b9_ctx *ctx);
 

@@ -223,7 +223,7 @@ def test_result_capacity_errors_do_not_consume():
         r = q.drain("identity", max_tasks=50)                            # 50 x 66 B fits
         assert r.n == 50 and q.depth() == 950
         with pytest.raises(L.B9Error) as e:
-            q.push_batch(b.task_ids[:1], np.zeros(1, np.uint8), np.array([0, 3 << 20], np.uint64))
+            q.push_batch(b.task_ids[:1], np.zeros(3 << 20, np.uint8), np.array([0, 3 << 20], np.uint64))
         assert e.value.code in (L.B9_E2BIG, L.B9_EINVAL)
     finally:
         q.close()

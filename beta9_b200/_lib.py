@@ -40,6 +40,11 @@ class Stats(C.Structure):
                 ("last_drain_in_bytes", C.c_uint64), ("last_drain_out_bytes", C.c_uint64)]
 
 
+class WireEnv(C.Structure):
+    _fields_ = [("workspace_name", C.c_char_p), ("stub_id", C.c_char_p), ("executor", C.c_char_p),
+                ("max_retries", C.c_uint32), ("timeout", C.c_int32), ("ttl", C.c_uint32)]
+
+
 class RebalanceInfo(C.Structure):
     _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("tasks_before", C.c_uint64), ("bytes_before", C.c_uint64),
                 ("tasks_sent", C.c_uint64), ("bytes_sent", C.c_uint64), ("tasks_received", C.c_uint64),
@@ -65,6 +70,7 @@ SYMBOLS = {
     "b9_drain": (C.c_int64, [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(Results)]),
     "b9_drain_launch": (C.c_int64, [C.c_void_p, C.c_int, C.c_uint32, C.c_int]),
     "b9_drain_fetch": (C.c_int64, [C.c_void_p, C.POINTER(Results)]),
+    "b9_wire_encode": (C.c_int64, [C.c_void_p, C.POINTER(WireEnv), C.c_uint32]),
     "b9_comm_unique_id": (C.c_int, [C.c_void_p]),
     "b9_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "b9_rebalance": (C.c_int, [C.c_void_p, C.POINTER(RebalanceInfo)]),

@@ -23,6 +23,7 @@
 #include "drain_kernel.cuh"
 #include "drain2.cuh"
 #include "rebalance_plan.h"
+#include "wire_encode.cuh"
 
 #include <dlfcn.h>
 
@@ -89,6 +90,7 @@ struct b9_ctx {
     uint8_t* d_out_payload = nullptr; uint64_t* d_out_off = nullptr; uint4* d_out_ids = nullptr;
     uint8_t* d_out_status = nullptr; uint8_t* d_out_has = nullptr; uint32_t* d_out_len = nullptr;
     SlowItem* d_slow = nullptr;                 // identity: work list of the second kernel
+    WireEnv* d_wire_env = nullptr;
     uint64_t cancelled_pending = 0;            // pending tasks carrying B9_TF_CANCELLED (pushed so, or expired)
     DrainCtl* d_ctl = nullptr; uint64_t* d_tile_state = nullptr;
     DrainCtl* h_ctl = nullptr;                 // pinned
@@ -239,6 +241,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     CUC(cudaMalloc(&c->d_out_has, md));
     CUC(cudaMalloc(&c->d_out_len, (size_t)md * sizeof(uint32_t)));
     CUC(cudaMalloc(&c->d_slow, (size_t)md * sizeof(SlowItem)));
+    CUC(cudaMalloc(&c->d_wire_env, sizeof(WireEnv)));
     CUC(cudaMalloc(&c->d_ctl, sizeof(DrainCtl)));
     CUC(cudaMalloc(&c->d_tile_state, ((size_t)md / D2_THREADS + 2) * sizeof(uint64_t)));
     CUC(cudaMalloc(&c->d_count, sizeof(unsigned long long)));
@@ -266,7 +269,7 @@ void b9_ctx_destroy(b9_ctx* c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->d_payload); cudaFree(c->d_off); cudaFree(c->d_hdr); cudaFree(c->d_ids); cudaFree(c->d_ts); cudaFree(c->d_exp);
     cudaFree(c->d_in_off); cudaFree(c->d_in_ts); cudaFree(c->d_in_exp); cudaFree(c->d_in_retries); cudaFree(c->d_in_flags);
-    cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len); cudaFree(c->d_slow);
+    cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len); cudaFree(c->d_slow); cudaFree(c->d_wire_env);
     cudaFree(c->d_ctl); cudaFree(c->d_tile_state); cudaFree(c->d_count);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_count) cudaFreeHost(c->h_count);
@@ -532,6 +535,77 @@ int64_t b9_drain(b9_ctx* c, int handler, uint32_t max_tasks, b9_results* out) {
     int64_t r = b9_drain_launch(c, handler, max_tasks, /*peek=*/0);
     if (r < 0) return r;
     return b9_drain_fetch(c, out);   // on B9_ENOSPC nothing is consumed and the records stay fetchable
+}
+
+// =========================================================================== wire records
+static size_t host_go_quote(const char* s, uint8_t* o, size_t cap) {
+    // encode.go appendString for an (assumed valid UTF-8) host string; HTML-safe
+    size_t n = 0;
+    auto put = [&](uint8_t c) { if (n < cap) o[n] = c; ++n; };
+    static const char HX[] = "0123456789abcdef";
+    put('"');
+    for (const unsigned char* p = (const unsigned char*)s; *p; ++p) {
+        unsigned char c = *p;
+        switch (c) {
+        case '"': put('\\'); put('"'); break;
+        case '\\': put('\\'); put('\\'); break;
+        case '\b': put('\\'); put('b'); break;
+        case '\f': put('\\'); put('f'); break;
+        case '\n': put('\\'); put('n'); break;
+        case '\r': put('\\'); put('r'); break;
+        case '\t': put('\\'); put('t'); break;
+        default:
+            if (c < 0x20 || c == '<' || c == '>' || c == '&') { put('\\'); put('u'); put('0'); put('0'); put(HX[c >> 4]); put(HX[c & 15]); }
+            else if (c == 0xE2 && p[1] == 0x80 && (p[2] == 0xA8 || p[2] == 0xA9)) { put('\\'); put('u'); put('2'); put('0'); put('2'); put(p[2] == 0xA8 ? '8' : '9'); p += 2; }
+            else put(c);
+        }
+    }
+    put('"');
+    return n;
+}
+
+int64_t b9_wire_encode(b9_ctx* c, const b9_wire_env* env, uint32_t max_tasks) {
+    if (!c || !env || !env->workspace_name || !env->stub_id) return fail(B9_EINVAL, "b9_wire_encode: NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->have_results = false;
+    const uint64_t depth = c->tail_task - c->head_task;
+    const uint32_t n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
+    c->res_n = 0; c->res_popped = 0; c->res_bytes = 0; c->res_in_bytes = 0; c->res_peek = true;
+    if (n == 0) { c->have_results = true; return 0; }
+    WireEnv we; memset(&we, 0, sizeof we);
+    {
+        uint8_t* o = we.mid; size_t k = 0; const size_t cap = sizeof we.mid;
+        auto lit = [&](const char* t) { for (; *t; ++t) { if (k < cap) o[k] = (uint8_t)*t; ++k; } };
+        lit("\",\"workspace_name\":"); k += host_go_quote(env->workspace_name, o + std::min(k, cap), cap - std::min(k, cap));
+        lit(",\"stub_id\":");          k += host_go_quote(env->stub_id, o + std::min(k, cap), cap - std::min(k, cap));
+        lit(",\"executor\":");         k += host_go_quote(env->executor ? env->executor : "taskqueue", o + std::min(k, cap), cap - std::min(k, cap));
+        lit(",\"args\":");
+        if (k > cap) return fail(B9_E2BIG, "b9_wire_encode: workspace/stub names too long");
+        we.mid_len = (uint32_t)k;
+    }
+    we.max_retries = env->max_retries; we.timeout = env->timeout; we.ttl = env->ttl;
+    cudaStream_t s = c->stream;
+    for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(s, sg.ready, 0));
+    CU(cudaMemcpyAsync(c->d_wire_env, &we, sizeof we, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
+    WireArgs a{};
+    a.payload = c->d_payload; a.off = c->d_off; a.hdr = c->d_hdr; a.ids = c->d_ids; a.ts = c->d_ts; a.exp = c->d_exp;
+    a.slot_mask = c->slot_mask; a.first_task = c->head_task; a.n_tasks = n;
+    a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_len = c->d_out_len;
+    a.out_ids = c->d_out_ids; a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.ctl = c->d_ctl;
+    CU(cudaEventRecord(c->ev_a, s));
+    wire_encode_kernel<<<(n + 127) / 128, 128, 0, s>>>(a, c->d_wire_env);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_b, s));
+    c->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(DrainCtl), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));     // (the stack copy of `we` is consumed by now as well)
+    if (c->h_ctl->overflow) return fail(B9_ENOSPC, "b9_wire_encode: records exceed max_result_bytes (%llu)", (unsigned long long)c->max_result_bytes);
+    c->res_bytes = c->h_ctl->bytes; c->res_n = n; c->res_popped = 0; c->have_results = true;
+    c->stats.last_drain_out_bytes = c->res_bytes;
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->stats.last_drain_kernel_ms = ms;
+    return (int64_t)n;
 }
 
 // =========================================================================== multi-GPU: NCCL rebalance

@@ -38,6 +38,9 @@ struct Parsed {
     uint8_t  a0_flags;        // SF_* of args[0] when it is a string
     uint32_t nargs;
     uint32_t a0_off, a0_len;  // byte span of args[0]'s token inside the payload
+    uint32_t args_off, args_len;   // span of the whole `args` value (last occurrence); len 0 = nil
+    uint32_t kw_off, kw_len;       // span of the `kwargs` value; len 0 = nil
+    uint8_t  kw_merged;            // kwargs appeared more than once with objects (Go merges the maps)
 };
 
 __device__ __forceinline__ bool is_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; }
@@ -307,6 +310,7 @@ __device__ inline bool only_ws(const uint8_t* __restrict__ p, uint32_t s, uint32
 // recognises the SDK's canonical frame without calling this; everything else lands here.
 __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n) {
     Parsed r; r.status = ST_OK; r.a0_kind = AK_NONE; r.kwargs_nonempty = 0; r.a0_flags = 0; r.nargs = 0; r.a0_off = 0; r.a0_len = 0;
+    r.args_off = r.args_len = r.kw_off = r.kw_len = 0; r.kw_merged = 0;
     uint32_t i = 0, sub_flags = 0;
 #define B9_REJECT() do { r.status = (sub_flags & SF_DEEP) ? ST_UNSUPPORTED : ST_REJECTED; return r; } while (0)
     while (i < n && is_ws(p[i])) ++i;
@@ -338,6 +342,7 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
         if (i >= n) B9_REJECT();
         if (which == 1) {                                   // Args []interface{}
             if (p[i] == '[') {
+                const uint32_t arr_start = i;
                 ++i;
                 uint32_t cnt = 0;
                 r.a0_kind = AK_NONE; r.a0_flags = 0;
@@ -374,9 +379,9 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
                     if (p[i] == ']') { ++i; break; }
                     B9_REJECT();
                 }
-                r.nargs = cnt;
+                r.nargs = cnt; r.args_off = arr_start; r.args_len = i - arr_start;
             } else if (p[i] == 'n' && scan_literal(p, i, n) >= 0) {
-                i += 4; r.nargs = 0; r.a0_kind = AK_NONE;
+                i += 4; r.nargs = 0; r.a0_kind = AK_NONE; r.args_len = 0;
             } else B9_REJECT();                             // UnmarshalTypeError or syntax error
         } else if (which == 2) {                            // Kwargs map[string]interface{}
             if (p[i] == '{') {
@@ -386,8 +391,10 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
                 if (ee < 0) B9_REJECT();
                 i = (uint32_t)ee;
                 if (!only_ws(p, vs + 1, i - 1)) r.kwargs_nonempty = 1;   // a non-nil map is merged into
+                if (r.kw_len) r.kw_merged = 1;
+                r.kw_off = vs; r.kw_len = i - vs;
             } else if (p[i] == 'n' && scan_literal(p, i, n) >= 0) {
-                i += 4; r.kwargs_nonempty = 0;
+                i += 4; r.kwargs_nonempty = 0; r.kw_len = 0; r.kw_merged = 0;
             } else B9_REJECT();
         } else {
             uint32_t ef = 0;

@@ -172,6 +172,13 @@ class DeviceQueue:
         """b9_drain straight into caller-owned (ideally pinned) buffers described by `res`."""
         return self._check(self._lib.b9_drain(self._ctx, HANDLERS[handler], max_tasks, C.byref(res)))
 
+    def wire_encode(self, workspace_name: str, stub_id: str, max_tasks: int = 1 << 22, executor: str = "taskqueue",
+                    max_retries: int = 3, timeout: int = 3600, ttl: int = 7200) -> DrainResult:
+        """TaskMessage.Encode (pkg/types/task.go:79-90) of the pending tasks, on the device; they stay pending."""
+        env = L.WireEnv(workspace_name.encode(), stub_id.encode(), executor.encode(), max_retries, timeout, ttl)
+        n = self._check(self._lib.b9_wire_encode(self._ctx, C.byref(env), max_tasks))
+        return self._fetch(n, None)
+
     # ---- multi-GPU (one DeviceQueue per rank / GPU)
     @staticmethod
     def comm_unique_id() -> bytes:

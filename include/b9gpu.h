@@ -188,8 +188,23 @@ int64_t  b9_drain(b9_ctx *ctx, int handler, uint32_t max_tasks, b9_results *out)
 int64_t  b9_drain_launch(b9_ctx *ctx, int handler, uint32_t max_tasks, int peek);
 int64_t  b9_drain_fetch(b9_ctx *ctx, b9_results *out);
 
-/* Device-side encode of the queue wire records (the bytes `TaskMessage.Encode` produces,
- * pkg/types/task.go:79-90) is declared in the "wire" section once implemented. */
+/* ---- queue wire records ------------------------------------------------------------------------
+ * b9_wire_encode materialises, for the first max_tasks pending tasks (they stay pending), the bytes
+ * `TaskMessage.Encode` produces (pkg/types/task.go:55-65,79-90) — what client.Push RPUSHes
+ * (taskqueue/client.go:29-41) and Dispatcher.Send stores as task state (pkg/task/dispatch.go:105-112):
+ * the durable record the Go host keeps in Redis. Fetch them with b9_drain_fetch (record i = pending
+ * task i; status 0 = bytes present, 3 = the payload is invalid JSON (no task would exist), 4 = outside
+ * the device encoder's domain: non-integer numbers, unsorted / duplicate map keys). Per-task
+ * timestamp / expires / retries come from b9_push_meta. */
+typedef struct b9_wire_env {
+    const char *workspace_name;   /* TaskMessage.WorkspaceName                                     */
+    const char *stub_id;          /* TaskMessage.StubId                                            */
+    const char *executor;         /* TaskMessage.Executor; NULL = "taskqueue" (types.ExecutorTaskQueue) */
+    uint32_t    max_retries;      /* TaskPolicy.MaxRetries (pkg/types/task.go:118-123)             */
+    int32_t     timeout;          /* TaskPolicy.Timeout                                            */
+    uint32_t    ttl;              /* TaskPolicy.TTL                                                */
+} b9_wire_env;
+int64_t  b9_wire_encode(b9_ctx *ctx, const b9_wire_env *env, uint32_t max_tasks);
 
 /* ---- multi-GPU: one ctx (= one process, one GPU) per rank of a box -------------------------------
  * The pending ring is sharded over the ranks; tasks are independent units, so the

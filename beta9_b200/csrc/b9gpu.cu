@@ -50,7 +50,6 @@ struct Segment {             // one push = one contiguous byte range of the payl
     uint64_t first_task;     // logical index of its first task
     uint32_t n;
     uint64_t phys_start, bytes;
-    std::vector<uint64_t> rel;   // the batch's offsets (n+1), kept for exact byte accounting
     cudaEvent_t ready;           // recorded on the ingest stream once the batch is fully on the device
 };
 
@@ -113,6 +112,19 @@ void free_segments(b9_ctx* c) {
         c->segs.pop_front();
     }
     if (c->segs.empty()) c->write_pos = 0;
+}
+
+// Physical payload offset of logical task `idx` of segment `sg` (idx == first_task + n gives the segment's
+// end). Only partial-segment operations need it (a drain that stops inside a batch, the rebalance), so
+// the host keeps no per-task index: the slot ring on the device is the index. Synchronous, 8 bytes.
+int task_phys_off(b9_ctx* c, const Segment& sg, uint64_t idx, uint64_t* out) {
+    if (idx == sg.first_task) { *out = sg.phys_start; return B9_OK; }
+    if (idx == sg.first_task + sg.n) { *out = sg.phys_start + sg.bytes; return B9_OK; }
+    CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));
+    CU(cudaMemcpyAsync(&c->h_ctl->total, c->d_off + (uint32_t)(idx & c->slot_mask), sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c->h_ctl->total;
+    return B9_OK;
 }
 
 // where can a segment of `bytes` go? returns false when the ring cannot take it now
@@ -364,7 +376,7 @@ static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload,
         CU(cudaStreamSynchronize(s));        // the caller may reuse its buffers as soon as we return
         float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->stats.last_push_h2d_ms = ms;
     }
-    c->segs.push_back(Segment{c->tail_task, n, start, bytes, std::vector<uint64_t>(offsets, offsets + n + 1), ready});
+    c->segs.push_back(Segment{c->tail_task, n, start, bytes, ready});
     c->write_pos = start + ((bytes + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
     c->tail_task += n;
     c->pending_bytes += bytes;
@@ -430,8 +442,11 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
         for (const Segment& sg : c->segs) {
             uint64_t a = std::max<uint64_t>(lo, sg.first_task), b = std::min<uint64_t>(hi, sg.first_task + sg.n);
             if (a < b) {
-                in_bytes += sg.rel[b - sg.first_task] - sg.rel[a - sg.first_task];
                 CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));     // this batch's H2D + ingest must have landed
+                uint64_t o0 = 0, o1 = 0;
+                int rc = task_phys_off(c, sg, a, &o0); if (rc) return rc;
+                rc = task_phys_off(c, sg, b, &o1); if (rc) return rc;
+                in_bytes += o1 - o0;
             }
         }
     }
@@ -686,7 +701,7 @@ MetaLayout meta_layout(uint64_t n) {
 }
 
 // drop k tasks from the tail of the ring (they were handed to another rank)
-void drop_back(b9_ctx* c, uint64_t k) {
+int drop_back(b9_ctx* c, uint64_t k) {
     while (k && !c->segs.empty()) {
         Segment& sg = c->segs.back();
         if (sg.n <= k) {
@@ -694,14 +709,17 @@ void drop_back(b9_ctx* c, uint64_t k) {
             c->event_pool.push_back(sg.ready); c->segs.pop_back();
         } else {
             const uint32_t keep = sg.n - (uint32_t)k;
-            const uint64_t nb = sg.rel[keep] - sg.rel[0];
+            uint64_t cut = 0;
+            int rc = task_phys_off(c, sg, sg.first_task + keep, &cut); if (rc) return rc;
+            const uint64_t nb = cut - sg.phys_start;
             c->pending_bytes -= sg.bytes - nb; c->tail_task -= k;
-            sg.n = keep; sg.bytes = nb; sg.rel.resize((size_t)keep + 1);
+            sg.n = keep; sg.bytes = nb;
             c->write_pos = sg.phys_start + ((nb + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
             k = 0;
         }
     }
     if (c->segs.empty()) c->write_pos = 0;
+    return B9_OK;
 }
 
 }  // namespace
@@ -753,13 +771,16 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     const uint64_t n = c->tail_task - c->head_task;
     // byte prefix of my pending tasks (host bookkeeping holds every batch's offsets)
     std::vector<uint64_t> prefix(n + 1, 0);
-    {
-        uint64_t k = 0, acc = 0;
-        for (const Segment& sg : c->segs) {
-            const uint64_t a = std::max<uint64_t>(c->head_task, sg.first_task) - sg.first_task;
-            for (uint64_t i = a; i < sg.n; ++i) { acc += sg.rel[i + 1] - sg.rel[i]; prefix[++k] = acc; }
-        }
-        if (k != n) return fail(B9_EIO, "b9_rebalance: ring bookkeeping inconsistent (%llu vs %llu)", (unsigned long long)k, (unsigned long long)n);
+    if (n) {   // lengths come back from the slot ring (the host keeps no per-task index)
+        std::vector<uint64_t> hdrs(n);
+        const uint32_t slot0 = (uint32_t)(c->head_task & c->slot_mask);
+        const uint64_t first = std::min<uint64_t>(n, c->ring_tasks - slot0);
+        CU(cudaMemcpyAsync(hdrs.data(), c->d_hdr + slot0, first * 8, cudaMemcpyDeviceToHost, s));
+        if (first < n) CU(cudaMemcpyAsync(hdrs.data() + first, c->d_hdr, (n - first) * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        for (uint64_t i = 0; i < n; ++i) prefix[i + 1] = prefix[i] + hdr_len(hdrs[i]);
+        if (prefix[n] != c->pending_bytes) return fail(B9_EIO, "b9_rebalance: ring bookkeeping inconsistent (%llu vs %llu bytes)",
+                                                       (unsigned long long)prefix[n], (unsigned long long)c->pending_bytes);
     }
     // ---- 1. all-gather (count, bytes)
     uint64_t* d_tab = nullptr; uint64_t* h_tab = nullptr;
@@ -841,7 +862,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     {
         const uint64_t front = lo[R], back = n - hi[R];
         if (front) { c->pending_bytes -= prefix[front]; c->head_task += front; free_segments(c); }
-        if (back) drop_back(c, back);
+        if (back) { int rc = drop_back(c, back); if (rc) return rc; }
     }
     // ---- 7. what arrived is appended, source by source, as new segments of the ring
     for (int src = 0; src < W; ++src) {
@@ -849,9 +870,6 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         if (!rk) continue;
         const MetaLayout ml = meta_layout(rk);
         const uint64_t pb = M_bytes(src, R);
-        std::vector<uint64_t> rel(rk + 1);
-        CU(cudaMemcpyAsync(rel.data(), r_meta[src] + ml.rel, (rk + 1) * 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
         uint64_t start = 0;
         free_segments(c);
         if (!place_segment(c, pb, &start)) return fail(B9_ENOSPC, "b9_rebalance: %llu incoming bytes do not fit the ring", (unsigned long long)pb);
@@ -870,7 +888,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         if (!c->event_pool.empty()) { ready = c->event_pool.back(); c->event_pool.pop_back(); }
         else CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
         CU(cudaEventRecord(ready, s));
-        c->segs.push_back(Segment{c->tail_task, (uint32_t)rk, start, pb, std::move(rel), ready});
+        c->segs.push_back(Segment{c->tail_task, (uint32_t)rk, start, pb, ready});
         c->write_pos = start + ((pb + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
         c->tail_task += rk; c->pending_bytes += pb;
     }

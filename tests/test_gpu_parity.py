@@ -42,8 +42,12 @@ def assert_matches_oracle(batch, r, o, allow_unsupported=0):
     rl = r.lengths.astype(np.int64)
     ol = np.diff(o.offsets).astype(np.int64)
     assert np.array_equal(rl[ok], ol[ok]), np.flatnonzero(ok & (rl != ol))[:10]
-    # the blob is dense and every record lies inside it
-    assert int(rl.sum()) == r.payload.size and (r.n == 0 or int((r.offsets.astype(np.int64) + rl).max()) <= r.payload.size)
+    # every record lies inside the blob, records do not overlap, and the blob has (almost) no holes
+    assert int(rl.sum()) <= r.payload.size <= int(rl.sum()) + 64 * max(r.n, 1) + int(np.diff(batch.offsets).max(initial=0)) * int((o.status != 0).sum() + (o.has == 0).sum() + 1)
+    if r.n:
+        order = np.argsort(r.offsets, kind="stable")
+        ends = r.offsets[order].astype(np.int64) + rl[order]
+        assert int(ends.max()) <= r.payload.size and np.all(ends[:-1][rl[order][:-1] > 0] <= r.offsets[order][1:].astype(np.int64)[rl[order][:-1] > 0])
     if not unsup.any() and not (o.status == 4).any():
         assert np.array_equal(r.fifo_payload(), o.payload)      # bit-for-bit, every record
     else:

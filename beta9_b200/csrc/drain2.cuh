@@ -51,6 +51,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// A plain atomicAdd executed by one lane makes the compiler wrap it in its warp-aggregation pattern
+// (elect + ATOMG + SHFL of the result), which consumes the result on the spot — the worker then stalls
+// for the whole L2 round trip exactly where the software pipeline wanted the latency hidden (ncu:
+// the two broadcast SHFLs carried 27 % of the main kernel's stall samples). Raw PTX keeps the result
+// in flight until its first real use.
+__device__ __forceinline__ unsigned long long atom_add_u64_deferred(unsigned long long* p, unsigned long long v) {
+    unsigned long long old;
+    asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+
 // ------------------------------------------------------------------ SWAR classification
 // any byte of the four words outside printable ASCII, or equal to '"' or '\\'?
 // Exactness: a false positive can only occur in a group that also holds a byte >= 0x80, which is
@@ -538,7 +549,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
     // the ticket after that is in flight; nothing global sits between the end of a tile and the bulk
     // copy of the next one. (Holding tickets is harmless: nobody waits on another worker's tile.)
     unsigned long long t_cur = 0, t_raw = 0;
-    if (lane == 0) { t_cur = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
+    if (lane == 0) { t_cur = atom_add_u64_deferred(&a.ctl->ticket, 1ull); t_raw = atom_add_u64_deferred(&a.ctl->ticket, 1ull); }
     t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
     D3MetaRegs mregs; mregs.off = 0; mregs.hdr = 0;
     if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
@@ -582,7 +593,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             spec = (m_ready && m_len >= FRAME_PRE_LEN + FRAME_SUF_LEN) ? m_len - (FRAME_PRE_LEN + FRAME_SUF_LEN - 2) : 0u;
             spec_ex = warp_excl_scan(spec, lane);
             spec_tot = __shfl_sync(0xffffffffu, spec_ex + spec, 31);
-            if (lane == 0 && spec_tot) spec_base = atomicAdd(&a.ctl->bytes, (unsigned long long)spec_tot);   // consumed in phase B
+            if (lane == 0 && spec_tot) spec_base = atom_add_u64_deferred(&a.ctl->bytes, (unsigned long long)spec_tot);   // consumed in phase B
         }
         const uint4 my_id = valid ? __ldg(a.ids + (uint32_t)((a.first_task + t0 + lane) & a.slot_mask)) : make_uint4(0, 0, 0, 0);
         // record indices: ready counts are known from the slot words alone
@@ -593,7 +604,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         // advance the ticket pipeline (loads/atomics issued here are consumed one iteration later)
         t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
         if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
-        if (lane == 0) t_raw = atomicAdd(&a.ctl->ticket, 1ull);
+        if (lane == 0) t_raw = atom_add_u64_deferred(&a.ctl->ticket, 1ull);
         __syncwarp();                                                      // W.* visible to all lanes
         if (staged) { mbar_wait(&W.mbar, parity); parity ^= 1u; }
 
@@ -630,7 +641,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             const uint32_t ex_bytes0 = warp_excl_scan(my_bytes, lane);
             tb = __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
             ex_bytes = __shfl_sync(0xffffffffu, ex_bytes0, k * G);                 // every lane of a task sees the task's offset
-            if (lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb);
+            if (lane == 0 && tb) base = atom_add_u64_deferred(&a.ctl->bytes, (unsigned long long)tb);
         }
         const uint32_t ex_cnt = __popc(ready_mask_t & ((1u << k) - 1u));
         base = __shfl_sync(0xffffffffu, base, 0);

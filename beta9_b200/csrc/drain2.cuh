@@ -449,6 +449,11 @@ struct D3Warp {
     uint32_t len[T];
     uint32_t esc_info[2][32];      // per-lane chunk sizes of up to two escaped strings (phase A -> phase B)
     alignas(8) uint64_t mbar;
+    // the two hot counters' addresses, re-read from shared memory at every use: an address the compiler
+    // cannot prove warp-uniform keeps ptxas from rewriting the single-lane atomic into its aggregation
+    // pattern (ATOMG + immediate SHFL of the result), which would consume the result on the spot
+    unsigned long long* volatile p_ticket;
+    unsigned long long* volatile p_bytes;
 };
 
 struct D3MetaRegs { uint64_t off, hdr; };
@@ -542,14 +547,14 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
     const int k = lane / G, sub = lane % G;                                // my task inside the warp-tile, my share of it
 
     if (HANDLER == 1) { for (int i = threadIdx.x; i < 256; i += D3_WARPS * 32) s_crc_table[i] = crc_table_entry(i); __syncthreads(); }
-    if (lane == 0) { mbar_init(&W.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (lane == 0) { mbar_init(&W.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); W.p_ticket = &a.ctl->ticket; W.p_bytes = &a.ctl->bytes; }
     __syncwarp();
 
     // two tickets ahead: the slot words of the next tile are in registers when its turn comes, and
     // the ticket after that is in flight; nothing global sits between the end of a tile and the bulk
     // copy of the next one. (Holding tickets is harmless: nobody waits on another worker's tile.)
     unsigned long long t_cur = 0, t_raw = 0;
-    if (lane == 0) { t_cur = atom_add_u64_deferred(&a.ctl->ticket, 1ull); t_raw = atom_add_u64_deferred(&a.ctl->ticket, 1ull); }
+    if (lane == 0) { t_cur = atom_add_u64_deferred(W.p_ticket, 1ull); t_raw = atom_add_u64_deferred(W.p_ticket, 1ull); }
     t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
     D3MetaRegs mregs; mregs.off = 0; mregs.hdr = 0;
     if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
@@ -593,7 +598,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             spec = (m_ready && m_len >= FRAME_PRE_LEN + FRAME_SUF_LEN) ? m_len - (FRAME_PRE_LEN + FRAME_SUF_LEN - 2) : 0u;
             spec_ex = warp_excl_scan(spec, lane);
             spec_tot = __shfl_sync(0xffffffffu, spec_ex + spec, 31);
-            if (lane == 0 && spec_tot) spec_base = atom_add_u64_deferred(&a.ctl->bytes, (unsigned long long)spec_tot);   // consumed in phase B
+            if (lane == 0 && spec_tot) spec_base = atom_add_u64_deferred(W.p_bytes, (unsigned long long)spec_tot);   // consumed in phase B
         }
         const uint4 my_id = valid ? __ldg(a.ids + (uint32_t)((a.first_task + t0 + lane) & a.slot_mask)) : make_uint4(0, 0, 0, 0);
         // record indices: ready counts are known from the slot words alone
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         // advance the ticket pipeline (loads/atomics issued here are consumed one iteration later)
         t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
         if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
-        if (lane == 0) t_raw = atom_add_u64_deferred(&a.ctl->ticket, 1ull);
+        if (lane == 0) t_raw = atom_add_u64_deferred(W.p_ticket, 1ull);
         __syncwarp();                                                      // W.* visible to all lanes
         if (staged) { mbar_wait(&W.mbar, parity); parity ^= 1u; }
 
@@ -641,7 +646,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             const uint32_t ex_bytes0 = warp_excl_scan(my_bytes, lane);
             tb = __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
             ex_bytes = __shfl_sync(0xffffffffu, ex_bytes0, k * G);                 // every lane of a task sees the task's offset
-            if (lane == 0 && tb) base = atom_add_u64_deferred(&a.ctl->bytes, (unsigned long long)tb);
+            if (lane == 0 && tb) base = atom_add_u64_deferred(W.p_bytes, (unsigned long long)tb);
         }
         const uint32_t ex_cnt = __popc(ready_mask_t & ((1u << k) - 1u));
         base = __shfl_sync(0xffffffffu, base, 0);

@@ -45,10 +45,12 @@ def assert_matches_oracle(batch, r, o, allow_unsupported=0):
     # every record lies inside the blob and records do not overlap (the blob may hold small gaps: slots
     # reserved for tasks that produced fewer bytes than the canonical frame predicts)
     assert int(rl.sum()) <= r.payload.size
-    if r.n:
-        order = np.argsort(r.offsets, kind="stable")
-        ends = r.offsets[order].astype(np.int64) + rl[order]
-        assert int(ends.max()) <= r.payload.size and np.all(ends[:-1][rl[order][:-1] > 0] <= r.offsets[order][1:].astype(np.int64)[rl[order][:-1] > 0])
+    nz = np.flatnonzero(rl > 0)
+    if nz.size:
+        starts = r.offsets[nz].astype(np.int64); lens = rl[nz]
+        order = np.argsort(starts, kind="stable")
+        ends = starts[order] + lens[order]
+        assert int(ends.max()) <= r.payload.size and np.all(ends[:-1] <= starts[order][1:])
     if not unsup.any() and not (o.status == 4).any():
         assert np.array_equal(r.fifo_payload(), o.payload)      # bit-for-bit, every record
     else:

@@ -51,17 +51,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// A plain atomicAdd executed by one lane makes the compiler wrap it in its warp-aggregation pattern
-// (elect + ATOMG + SHFL of the result), which consumes the result on the spot — the worker then stalls
-// for the whole L2 round trip exactly where the software pipeline wanted the latency hidden (ncu:
-// the two broadcast SHFLs carried 27 % of the main kernel's stall samples). Raw PTX keeps the result
-// in flight until its first real use.
-__device__ __forceinline__ unsigned long long atom_add_u64_deferred(unsigned long long* p, unsigned long long v) {
-    unsigned long long old;
-    asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
-    return old;
-}
-
 // ------------------------------------------------------------------ SWAR classification
 // any byte of the four words outside printable ASCII, or equal to '"' or '\\'?
 // Exactness: a false positive can only occur in a group that also holds a byte >= 0x80, which is
@@ -360,21 +349,6 @@ __device__ __noinline__ bool esc_scan(const uint8_t* __restrict__ body, uint32_t
             (void)stop;
             if (i >= hi) break;
             const uint32_t i0 = i;
-            // the two commonest non-plain units inline; everything else through the general decoder
-            if (body[i] == '\\' && i + 2 <= n) {
-                const uint8_t e1 = body[i + 1];
-                if (e1 == 'u' && i + 6 <= n) {
-                    const uint32_t hw = ld_u32_unaligned(body + i + 2);
-                    const int hv = hex4(body + i + 2);
-                    if (hv >= 0 && (hv < 0xD800 || hv > 0xDFFF)) {
-                        const uint32_t ol1 = py_escaped_len((uint32_t)hv);
-                        mine += ol1; i += 6;
-                        if (ol1 != 6u) L.len_change = true;
-                        else if (hex_has_upper(hw)) { if (L.npatch < 2u) { L.patch_pos[L.npatch] = i0; L.patch_cp[L.npatch] = (uint32_t)hv; } ++L.npatch; }
-                        continue;
-                    }
-                } else if (e1 == '"' || e1 == '\\' || e1 == 'n' || e1 == 't' || e1 == 'r' || e1 == 'b' || e1 == 'f') { mine += 2; i += 2; continue; }
-            }
             const uint32_t cp = next_unit(body, i, n, &L.ok);
             if (!L.ok) break;
             const uint32_t ol = py_escaped_len(cp), il = i - i0;
@@ -449,11 +423,6 @@ struct D3Warp {
     uint32_t len[T];
     uint32_t esc_info[2][32];      // per-lane chunk sizes of up to two escaped strings (phase A -> phase B)
     alignas(8) uint64_t mbar;
-    // the two hot counters' addresses, re-read from shared memory at every use: an address the compiler
-    // cannot prove warp-uniform keeps ptxas from rewriting the single-lane atomic into its aggregation
-    // pattern (ATOMG + immediate SHFL of the result), which would consume the result on the spot
-    unsigned long long* volatile p_ticket;
-    unsigned long long* volatile p_bytes;
 };
 
 struct D3MetaRegs { uint64_t off, hdr; };
@@ -547,14 +516,14 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
     const int k = lane / G, sub = lane % G;                                // my task inside the warp-tile, my share of it
 
     if (HANDLER == 1) { for (int i = threadIdx.x; i < 256; i += D3_WARPS * 32) s_crc_table[i] = crc_table_entry(i); __syncthreads(); }
-    if (lane == 0) { mbar_init(&W.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); W.p_ticket = &a.ctl->ticket; W.p_bytes = &a.ctl->bytes; }
+    if (lane == 0) { mbar_init(&W.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
 
     // two tickets ahead: the slot words of the next tile are in registers when its turn comes, and
     // the ticket after that is in flight; nothing global sits between the end of a tile and the bulk
     // copy of the next one. (Holding tickets is harmless: nobody waits on another worker's tile.)
     unsigned long long t_cur = 0, t_raw = 0;
-    if (lane == 0) { t_cur = atom_add_u64_deferred(W.p_ticket, 1ull); t_raw = atom_add_u64_deferred(W.p_ticket, 1ull); }
+    if (lane == 0) { t_cur = atomicAdd(&a.ctl->ticket, 1ull); t_raw = atomicAdd(&a.ctl->ticket, 1ull); }
     t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
     D3MetaRegs mregs; mregs.off = 0; mregs.hdr = 0;
     if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
@@ -586,21 +555,6 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                 if (lane == 0) { mbar_expect_tx(&W.mbar, (uint32_t)bytes); if (bytes) bulk_g2s(sbuf, a.payload + as, (uint32_t)bytes, &W.mbar); }
             }
         } else staged = d3_stage_scattered<T>(a, m_off, m_len, valid, W, sbuf, in_cap, lane);
-        // identity: reserve the result bytes NOW, from the slot words alone — a task that turns out to be
-        // the SDK's canonical frame around a clean string produces exactly len - 26 bytes (its token).
-        // The cursor atomic then completes under the bulk copy and phase A instead of stalling the worker
-        // between phase A and phase B. Tasks that turn out different keep their slot as scratch: the second
-        // kernel writes into it when the real output fits (always true for what json.dumps produced, whose
-        // escapes keep their length) and allocates afresh otherwise, so the blob stays (almost) hole-free.
-        static_assert(HANDLER != 0 || G == 1, "speculative placement assumes one lane per task");
-        uint32_t spec = 0, spec_ex = 0, spec_tot = 0; unsigned long long spec_base = 0;
-        if (HANDLER == 0) {
-            spec = (m_ready && m_len >= FRAME_PRE_LEN + FRAME_SUF_LEN) ? m_len - (FRAME_PRE_LEN + FRAME_SUF_LEN - 2) : 0u;
-            spec_ex = warp_excl_scan(spec, lane);
-            spec_tot = __shfl_sync(0xffffffffu, spec_ex + spec, 31);
-            if (lane == 0 && spec_tot) spec_base = atom_add_u64_deferred(W.p_bytes, (unsigned long long)spec_tot);   // consumed in phase B
-        }
-        const uint4 my_id = valid ? __ldg(a.ids + (uint32_t)((a.first_task + t0 + lane) & a.slot_mask)) : make_uint4(0, 0, 0, 0);
         // record indices: ready counts are known from the slot words alone
         const uint32_t ready_mask_t = __ballot_sync(0xffffffffu, m_ready);       // bit = task index
         const uint32_t rc = __popc(ready_mask_t);
@@ -609,7 +563,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         // advance the ticket pipeline (loads/atomics issued here are consumed one iteration later)
         t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
         if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
-        if (lane == 0) t_raw = atom_add_u64_deferred(W.p_ticket, 1ull);
+        if (lane == 0) t_raw = atomicAdd(&a.ctl->ticket, 1ull);
         __syncwarp();                                                      // W.* visible to all lanes
         if (staged) { mbar_wait(&W.mbar, parity); parity ^= 1u; }
 
@@ -638,17 +592,13 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         }
 
         // ---------------- compaction (ballot) + sizes (scan) + ONE cursor add per warp-tile -------------
-        uint32_t ex_bytes, tb;
-        unsigned long long base = 0;
-        if (HANDLER == 0) { ex_bytes = spec_ex; tb = spec_tot; base = spec_base; }            // reserved at staging time
-        else {
-            const uint32_t my_bytes = (sub == 0) ? rec.out_len : 0u;
-            const uint32_t ex_bytes0 = warp_excl_scan(my_bytes, lane);
-            tb = __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
-            ex_bytes = __shfl_sync(0xffffffffu, ex_bytes0, k * G);                 // every lane of a task sees the task's offset
-            if (lane == 0 && tb) base = atom_add_u64_deferred(W.p_bytes, (unsigned long long)tb);
-        }
+        const uint32_t my_bytes = (sub == 0) ? rec.out_len : 0u;
+        const uint32_t ex_bytes0 = warp_excl_scan(my_bytes, lane);
+        const uint32_t tb = __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
+        const uint32_t ex_bytes = __shfl_sync(0xffffffffu, ex_bytes0, k * G);      // every lane of a task sees the task's offset
         const uint32_t ex_cnt = __popc(ready_mask_t & ((1u << k) - 1u));
+        unsigned long long base = 0;
+        if (lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb);
         base = __shfl_sync(0xffffffffu, base, 0);
         const bool fits = base + tb <= a.out_cap;
         if (!fits && lane == 0) a.ctl->overflow = 1u;
@@ -657,11 +607,11 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         if (mine) {
             const uint64_t ob = base + ex_bytes;
             if (sub == 0) {
+                const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
                 const uint32_t j = base_cnt + ex_cnt;
-                a.out_ids[j] = (G == 1) ? my_id : __ldg(a.ids + (uint32_t)((a.first_task + t0 + k) & a.slot_mask));
+                a.out_ids[j] = __ldg(a.ids + slot);
                 if (HANDLER == 0 && rec.mode == OM_DEFER) {                // the second kernel writes the rest of the record
                     SlowItem it; it.goff = my_goff; it.len = my_len | (rec.value ? 0x80000000u : 0u); it.j = j;
-                    it.slot_off = ob; it.slot_cap = fits ? spec : 0u; it.pad = 0;
                     a.slow[atomicAdd(&a.ctl->n_slow, 1u)] = it;
                 } else { a.out_off[j] = fits ? ob : 0; a.out_len[j] = rec.out_len; a.out_status[j] = rec.status; a.out_has[j] = rec.has; }
             }
@@ -711,11 +661,9 @@ __global__ void __launch_bounds__(DS_WARPS * 32) drain_slow_kernel(DrainArgs a) 
             const uint32_t w = __shfl_sync(0xffffffffu, (uint32_t)rec.status | ((uint32_t)rec.has << 8) | ((uint32_t)rec.mode << 16), 0);
             rec.status = (uint8_t)w; rec.has = (uint8_t)(w >> 8); rec.mode = (uint8_t)(w >> 16);
         }
-        unsigned long long base = it.slot_off;                              // the slot the main kernel reserved ...
-        if (rec.out_len > it.slot_cap) {                                   // ... unless the real output is bigger
-            if (lane == 0) base = atomicAdd(&a.ctl->bytes, (unsigned long long)rec.out_len);
-            base = __shfl_sync(0xffffffffu, base, 0);
-        }
+        unsigned long long base = 0;
+        if (lane == 0 && rec.out_len) base = atomicAdd(&a.ctl->bytes, (unsigned long long)rec.out_len);
+        base = __shfl_sync(0xffffffffu, base, 0);
         const bool fits = base + rec.out_len <= a.out_cap;
         if (!fits && lane == 0) a.ctl->overflow = 1u;
         if (rec.has && fits) {

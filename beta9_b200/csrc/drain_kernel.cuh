@@ -50,9 +50,6 @@ struct SlowItem {
     uint64_t goff;                  // physical ring offset of the payload
     uint32_t len;                   // payload length; bit 31 = the SDK's canonical frame is present
     uint32_t j;                     // index of the task's result record
-    uint64_t slot_off;              // result bytes reserved for it by the main kernel (speculative size) ...
-    uint32_t slot_cap;              // ... and how many; the second kernel uses the slot when its output fits
-    uint32_t pad;
 };
 
 struct DrainArgs {

@@ -751,6 +751,22 @@ int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
     void* comm = nullptr;
     NC(g_nccl.CommInitRank(&comm, world, id, rank));
     c->nccl_comm = comm; c->comm_rank = rank; c->comm_world = world;
+    // NCCL sets its point-to-point channels up lazily, on the first send/recv of every pair (seconds on an
+    // 8-GPU box): do that here, once, with a 16-byte all-to-all, so that b9_rebalance is never the first user
+    if (world > 1) {
+        uint8_t* d = nullptr;
+        CU(cudaMalloc(&d, (size_t)world * 32));
+        CU(cudaMemsetAsync(d, 0, (size_t)world * 32, c->stream));
+        NC(g_nccl.GroupStart());
+        for (int p = 0; p < world; ++p) {
+            if (p == rank) continue;
+            NC(g_nccl.Send(d + (size_t)p * 32, 16, NCCL_U8, p, comm, c->stream));
+            NC(g_nccl.Recv(d + (size_t)p * 32 + 16, 16, NCCL_U8, p, comm, c->stream));
+        }
+        NC(g_nccl.GroupEnd());
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+    }
     return B9_OK;
 }
 

@@ -111,7 +111,13 @@ def workload(args, rank):
         n = int(n * (1 + args.skew))
     if args.handler == "identity":
         return synth.strings_batch(n, args.chars, adversarial_frac=args.adversarial, seed=synth.SEED + 1000 * rank)
-    raise SystemExit(f"bench: handler {args.handler} has no bench workload yet")
+    if args.handler == "crc32":          # configs[2]: zipf 32..4096-char strings
+        return synth.crc_batch(n, seed=synth.SEED + 1000 * rank)
+    if args.handler == "vadd_f32":       # configs[3] payload shape: 2 x 32 fp32 as base64
+        return synth.vadd_batch(n, seed=synth.SEED + 1000 * rank)
+    if args.handler == "json_sum":       # configs[4] payload shape: 1 KB JSON documents
+        return synth.json_batch(n, seed=synth.SEED + 1000 * rank)
+    raise SystemExit(f"bench: unknown handler {args.handler}")
 
 
 def run_reference(args):
@@ -320,19 +326,23 @@ def main():
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         if os.path.exists(peaks_path):
             peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
-        algo = ALGO_BYTES_PER_TASK.get(args.handler, 0.0) * n
+        if args.handler in ALGO_BYTES_PER_TASK:
+            algo = ALGO_BYTES_PER_TASK[args.handler] * n
+        else:   # argument bytes as carried + result bytes + 2 x 32 B of index/id/header per task
+            algo = float(in_bytes - 28 * n + out_bytes + 64 * n)
         achieved = algo / (k_ms * 1e-3) / 1e9
         line = {
             "metric": "tasks_per_sec", "value": value, "unit": "tasks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"configs[1]: {n} x {args.chars}-char identity tasks per GPU ({100 * args.adversarial:g}% adversarial escapes), "
-                                   f"resident in HBM", "handler": args.handler, "tasks_per_gpu": n,
+            "config": {"workload": (f"configs[1]: {n} x {args.chars}-char identity tasks per GPU ({100 * args.adversarial:g}% adversarial escapes), resident in HBM"
+                                    if args.handler == "identity" else f"{args.handler}: {n} tasks per GPU, {in_bytes / n:.0f} payload bytes per task on average, resident in HBM"),
+                       "handler": args.handler, "tasks_per_gpu": n,
                        "parallelism": (f"shard{world}" + ("+nccl_rebalance" if rebalance else "")) if world > 1 else "single",
                        "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "b9::drain_kernel<identity>", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_task": ALGO_BYTES_PER_TASK.get(args.handler), "peak_source": peak_src},
+                         "traffic": None, "kernel": f"b9::drain3_kernel<{args.handler}>" + (" + drain_slow_kernel" if args.handler == "identity" else ""),
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_task": algo / n, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "tasks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / args.e2e_steps,

@@ -482,7 +482,9 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     c->stats.kernel_launches++;
     if (v2 && handler == B9_H_IDENTITY) {
         // second kernel: the tasks the main identity kernel deferred (escaped strings, foreign framing, ...)
-        drain_slow_kernel<<<c->sm_count * 4, DS_WARPS * 32, 0, s>>>(a);
+        static int slow_per_sm = 0;
+        if (!slow_per_sm) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slow_per_sm, drain_slow_kernel, DS_WARPS * 32, 0) != cudaSuccess || slow_per_sm < 1) slow_per_sm = 4; }
+        drain_slow_kernel<<<c->sm_count * slow_per_sm, DS_WARPS * 32, 0, s>>>(a);
         le = cudaGetLastError();
         if (le != cudaSuccess) return fail(B9_EIO, "drain_slow_kernel launch failed: %s", cudaGetErrorString(le));
         c->stats.kernel_launches++;

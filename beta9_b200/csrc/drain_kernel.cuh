@@ -107,10 +107,10 @@ __device__ inline void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __res
         uint32_t bits = sh * 8;
         for (uint32_t v = lane; v < nvec; v += 32) {
             const uint32_t* s4 = sw + 4 * v;
-            uint32_t w0 = __ldg(s4), w1 = __ldg(s4 + 1), w2 = __ldg(s4 + 2), w3 = __ldg(s4 + 3);
+            uint32_t w0 = s4[0], w1 = s4[1], w2 = s4[2], w3 = s4[3];   // plain loads: the source may be shared memory
             uint4 o;
             if (sh) {
-                uint32_t w4 = __ldg(s4 + 4);   // may read up to 3 bytes past the payload: the ring has slack
+                uint32_t w4 = s4[4];           // may read up to 3 bytes past the payload: the ring / stage buffer has slack
                 o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
                 o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
             } else { o.x = w0; o.y = w1; o.z = w2; o.w = w3; }

@@ -90,6 +90,7 @@ struct b9_ctx {
     uint8_t* d_out_status = nullptr; uint8_t* d_out_has = nullptr; uint32_t* d_out_len = nullptr;
     SlowItem* d_slow = nullptr;                 // identity: work list of the second kernel
     WireEnv* d_wire_env = nullptr;
+    uint32_t* d_crc_shift = nullptr;            // crc32: zero-byte shift tables
     uint64_t cancelled_pending = 0;            // pending tasks carrying B9_TF_CANCELLED (pushed so, or expired)
     DrainCtl* d_ctl = nullptr; uint64_t* d_tile_state = nullptr;
     DrainCtl* h_ctl = nullptr;                 // pinned
@@ -254,6 +255,20 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     CUC(cudaMalloc(&c->d_out_len, (size_t)md * sizeof(uint32_t)));
     CUC(cudaMalloc(&c->d_slow, (size_t)md * sizeof(SlowItem)));
     CUC(cudaMalloc(&c->d_wire_env, sizeof(WireEnv)));
+    {
+        // Z_k = advance the reflected CRC-32 register over 2^k zero bytes, as 4 byte-indexed tables per k
+        std::vector<uint32_t> tabs((size_t)CRC_SHIFT_LEVELS * 1024);
+        uint32_t step[256];
+        for (uint32_t i = 0; i < 256; ++i) { uint32_t v = i; for (int b = 0; b < 8; ++b) v = (v & 1u) ? (0xEDB88320u ^ (v >> 1)) : (v >> 1); step[i] = v; }
+        auto apply = [&](const uint32_t* t, uint32_t v) { return t[v & 255] ^ t[256 + ((v >> 8) & 255)] ^ t[512 + ((v >> 16) & 255)] ^ t[768 + (v >> 24)]; };
+        for (uint32_t j = 0; j < 4; ++j) for (uint32_t b = 0; b < 256; ++b) { uint32_t v = b << (8 * j); tabs[j * 256 + b] = step[v & 255] ^ (v >> 8); }   // k = 0: one zero byte
+        for (int k = 1; k < CRC_SHIFT_LEVELS; ++k) {
+            const uint32_t* prev = tabs.data() + (size_t)(k - 1) * 1024; uint32_t* cur = tabs.data() + (size_t)k * 1024;
+            for (uint32_t j = 0; j < 4; ++j) for (uint32_t b = 0; b < 256; ++b) cur[j * 256 + b] = apply(prev, apply(prev, b << (8 * j)));
+        }
+        CUC(cudaMalloc(&c->d_crc_shift, tabs.size() * sizeof(uint32_t)));
+        CUC(cudaMemcpy(c->d_crc_shift, tabs.data(), tabs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     CUC(cudaMalloc(&c->d_ctl, sizeof(DrainCtl)));
     CUC(cudaMalloc(&c->d_tile_state, ((size_t)md / D2_THREADS + 2) * sizeof(uint64_t)));
     CUC(cudaMalloc(&c->d_count, sizeof(unsigned long long)));
@@ -281,7 +296,7 @@ void b9_ctx_destroy(b9_ctx* c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->d_payload); cudaFree(c->d_off); cudaFree(c->d_hdr); cudaFree(c->d_ids); cudaFree(c->d_ts); cudaFree(c->d_exp);
     cudaFree(c->d_in_off); cudaFree(c->d_in_ts); cudaFree(c->d_in_exp); cudaFree(c->d_in_retries); cudaFree(c->d_in_flags);
-    cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len); cudaFree(c->d_slow); cudaFree(c->d_wire_env);
+    cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len); cudaFree(c->d_slow); cudaFree(c->d_wire_env); cudaFree(c->d_crc_shift);
     cudaFree(c->d_ctl); cudaFree(c->d_tile_state); cudaFree(c->d_count);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_count) cudaFreeHost(c->h_count);
@@ -456,7 +471,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_ids = c->d_out_ids;
     a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.handler = handler;
     a.count_mode = c->cancelled_pending ? 1u : 0u;
-    a.slow = c->d_slow;
+    a.slow = c->d_slow; a.crc_shift_tabs = c->d_crc_shift;
     cudaStream_t s = c->stream;
     const bool v2 = c->drain_version == 2;
     if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;     // upper bound over the handlers' warp-tile sizes (state array memset)

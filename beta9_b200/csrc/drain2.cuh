@@ -397,6 +397,363 @@ __device__ __noinline__ void esc_emit_general(const uint8_t* __restrict__ body, 
     }
 }
 
+// ------------------------------------------------------------------ warp-cooperative CRC-32 of a framed string
+// zlib.crc32(s.encode()) over the DECODED bytes, 32 chunks in parallel. With R(c, b) the reflected
+// table step and r_l the register after lane l's decoded bytes starting from 0, linearity gives
+//   R*(0xFFFFFFFF, B_0 || ... || B_31) = Z(0xFFFFFFFF, N) ^ XOR_l Z(r_l, bytes after lane l)
+// where Z(c, n) advances the register over n zero bytes. Z for n = 2^k is a fixed linear map, kept as
+// 4 x 256-entry byte tables per k (`shift_tabs`, built on the host): a shift costs 4 loads per set bit.
+constexpr int CRC_SHIFT_LEVELS = 32;         // any 32-bit byte count (128 KiB of tables, L2-resident)
+__device__ __forceinline__ uint32_t crc_zero_shift(uint32_t c, uint32_t nbytes, const uint32_t* __restrict__ shift_tabs) {
+    for (uint32_t k = 0; nbytes; ++k, nbytes >>= 1) {
+        if (nbytes & 1u) {
+            const uint32_t* t = shift_tabs + (size_t)k * 1024;
+            c = __ldg(t + (c & 0xFFu)) ^ __ldg(t + 256 + ((c >> 8) & 0xFFu)) ^ __ldg(t + 512 + ((c >> 16) & 0xFFu)) ^ __ldg(t + 768 + (c >> 24));
+        }
+    }
+    return c;
+}
+
+// returns false when the body is not a well-formed JSON string body (caller falls back to the sequential parser).
+// Force-inlined so that loads keep their address space (LDS for a staged tile, LDG otherwise).
+__device__ __forceinline__ bool crc_scan_coop(const uint8_t* __restrict__ body, uint32_t n, int lane, const uint32_t* crc_table,
+                                              const uint32_t* __restrict__ shift_tabs, uint32_t* crc_out) {
+    const uint32_t S = (n + 31u) / 32u;
+    const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
+    bool ok = true;
+    uint32_t r = 0, dec = 0;
+    if (lo < hi) {
+        // a chunk that starts on a plain byte with no backslash among the five bytes before it (the reach of
+        // a \uXXXX escape) starts on a unit boundary; anything else takes the general look-behind
+        uint32_t i = lo;
+        if (lo) {
+            bool easy = plain_byte(body[lo]);
+            #pragma unroll
+            for (uint32_t k = 1; k <= 5; ++k) easy = easy && (lo < k || body[lo - k] != '\\');
+            if (!easy) i = first_unit_start(body, n, lo);
+        }
+        while (i < hi) {
+            const uint32_t c = body[i], e = body[i + 1];                   // i + 1 <= n: the frame suffix follows the body
+            const bool simple = c == '\\' && (e == '"' || e == '\\' || e == '/');
+            if (plain_byte(c) || simple) { r = crc_byte(r, simple ? e : c, crc_table); ++dec; i += simple ? 2u : 1u; continue; }
+            const uint32_t cp = next_unit(body, i, n, &ok);
+            if (!ok) break;
+            if (cp < 0x80) { r = crc_byte(r, cp, crc_table); dec += 1; }
+            else if (cp < 0x800) { r = crc_byte(r, 0xC0 | (cp >> 6), crc_table); r = crc_byte(r, 0x80 | (cp & 0x3F), crc_table); dec += 2; }
+            else if (cp < 0x10000) {
+                r = crc_byte(r, 0xE0 | (cp >> 12), crc_table); r = crc_byte(r, 0x80 | ((cp >> 6) & 0x3F), crc_table); r = crc_byte(r, 0x80 | (cp & 0x3F), crc_table); dec += 3;
+            } else {
+                r = crc_byte(r, 0xF0 | (cp >> 18), crc_table); r = crc_byte(r, 0x80 | ((cp >> 12) & 0x3F), crc_table);
+                r = crc_byte(r, 0x80 | ((cp >> 6) & 0x3F), crc_table); r = crc_byte(r, 0x80 | (cp & 0x3F), crc_table); dec += 4;
+            }
+        }
+    }
+    if (!__all_sync(0xffffffffu, ok)) return false;
+    const uint32_t before = warp_excl_scan(dec, lane);
+    const uint32_t total = __shfl_sync(0xffffffffu, before + dec, 31);
+    uint32_t v = crc_zero_shift(r, total - before - dec, shift_tabs);
+    if (lane == 0) v ^= crc_zero_shift(0xFFFFFFFFu, total, shift_tabs);
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, d);
+    *crc_out = ~v;
+    return true;
+}
+
+template <int HANDLER> __device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, TaskRec& rec, const uint32_t* crc_table);
+// one crc32 task with the whole warp; the owner lane keeps the record
+__device__ __forceinline__ void crc_task_coop(const uint8_t* __restrict__ p, uint32_t len, int lane, bool owner, const uint32_t* crc_table,
+                                              const uint32_t* __restrict__ shift_tabs, TaskRec& rec) {
+    bool framed = len >= FRAME_PRE_LEN + FRAME_SUF_LEN;
+    if (framed) {
+        bool okb = true;
+        if (lane < (int)FRAME_PRE_LEN) okb = p[lane] == FRAME_PRE[lane];
+        else if (lane < (int)(FRAME_PRE_LEN + FRAME_SUF_LEN)) okb = p[len - FRAME_SUF_LEN + (lane - FRAME_PRE_LEN)] == FRAME_SUF[lane - FRAME_PRE_LEN];
+        framed = __all_sync(0xffffffffu, okb);
+    }
+    uint32_t crc = 0; bool done = false;
+    if (framed) done = crc_scan_coop(p + FRAME_PRE_LEN, len - FRAME_PRE_LEN - FRAME_SUF_LEN, lane, crc_table, shift_tabs, &crc);
+    if (owner) {
+        if (done) { if (crc) { rec.value = (long long)crc; rec.out_len = dec_len_u64(crc); rec.mode = OM_U32_DEC; rec.has = 1; } }
+        else d2_parse_and_size<1>(p, len, rec, crc_table);
+    }
+}
+
+// ------------------------------------------------------------------ vadd_f32, thread per task, in place in the stage buffer
+// The common case (canonical frame, plain base64 body, two equal fp32 vectors) is computed without a
+// data-dependent branch: characters go through a 256-entry table in shared memory (0..63, 0xFF = not
+// in the alphabet), three floats (16 characters of a, 16..20 of b) per step, and the result text is
+// written over the bytes of `a` already consumed, 4-byte aligned, so that phase B is a plain copy.
+// tab[0..255] = decode, tab[256..319] = encode.
+__device__ __forceinline__ uint32_t b64_dec4(uint32_t x, const uint8_t* tab, uint32_t& bad) {
+    const uint32_t v0 = tab[x & 0xFFu], v1 = tab[(x >> 8) & 0xFFu], v2 = tab[(x >> 16) & 0xFFu], v3 = tab[x >> 24];
+    bad |= v0 | v1 | v2 | v3;
+    return (v0 << 18) | (v1 << 12) | (v2 << 6) | v3;                   // stream bytes: bits 23..16, 15..8, 7..0
+}
+__device__ __forceinline__ uint32_t b64_enc4(uint32_t w, const uint8_t* tab) {
+    return (uint32_t)tab[256 + ((w >> 18) & 63u)] | ((uint32_t)tab[256 + ((w >> 12) & 63u)] << 8) |
+           ((uint32_t)tab[256 + ((w >> 6) & 63u)] << 16) | ((uint32_t)tab[256 + (w & 63u)] << 24);
+}
+// group g of the body; the padding characters of the last group read as 'A'
+__device__ __forceinline__ uint32_t b64_group_padded(const uint8_t* body, uint32_t g, uint32_t last, uint32_t pad) {
+    uint32_t x = ld_u32_unaligned(body + 4u * g);
+    if (g == last && pad) x = pad == 1u ? ((x & 0x00FFFFFFu) | 0x41000000u) : ((x & 0x0000FFFFu) | 0x41410000u);
+    return x;
+}
+// little-endian u32 at stream byte s (s..s+3) of the decoded body; used for the <= 2 floats after the last full step
+__device__ __forceinline__ uint32_t b64_u32_at(const uint8_t* body, uint32_t s, uint32_t last, uint32_t pad, const uint8_t* tab, uint32_t& bad) {
+    const uint32_t g = s / 3u, q = s - 3u * g;
+    const uint32_t u0 = b64_dec4(b64_group_padded(body, g, last, pad), tab, bad);
+    const uint32_t u1 = b64_dec4(b64_group_padded(body, g + 1u, last, pad), tab, bad);
+    const uint32_t s0 = __byte_perm(u0, u1, 0x6012), s1 = __byte_perm(u1, 0u, 0x4401);      // stream bytes 0..3, 4..5
+    return __funnelshift_r(s0, s1, 8u * q);
+}
+// returns 0 = not the common case, nothing touched; 1 = done (rec filled); 2 = stage bytes overwritten and
+// a non-alphabet character found: the caller re-reads the task from the ring and takes the general path
+__device__ __forceinline__ int vadd_fast(uint8_t* p, uint32_t len, const uint8_t* tab, TaskRec& rec) {
+    if (len < FRAME_PRE_LEN + FRAME_SUF_LEN + 4u) return 0;
+    const uint8_t* q = p + len - FRAME_SUF_LEN;
+    bool bad_frame = ld_u32_unaligned(p) != 0x7261227Bu;
+    bad_frame |= ld_u32_unaligned(p + 4) != 0x3A227367u;
+    bad_frame |= (ld_u32_unaligned(p + 8) & 0x00FFFFFFu) != 0x00225B20u;
+    bad_frame |= ld_u32_unaligned(q) != 0x202C5D22u;
+    bad_frame |= ld_u32_unaligned(q + 4) != 0x61776B22u;
+    bad_frame |= ld_u32_unaligned(q + 8) != 0x22736772u;
+    bad_frame |= ld_u32_unaligned(q + 12) != 0x7D7B203Au;
+    bad_frame |= q[16] != '}';
+    const uint32_t L = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
+    if (bad_frame || (L & 3u)) return 0;
+    uint8_t* const body = p + FRAME_PRE_LEN;
+    const uint32_t pad = body[L - 1] == '=' ? (body[L - 2] == '=' ? 2u : 1u) : 0u;
+    const uint32_t G = L >> 2, nbytes = G * 3u - pad;
+    if (nbytes & 7u) return 0;
+    const uint32_t n = nbytes >> 3;                                     // floats per vector (>= 1 here)
+    const uint32_t nblk = n / 3u, rem = n - 3u * nblk, ph = rem;        // (4n) % 3 == n % 3
+    const uint32_t gb0 = (4u * n) / 3u;
+    uint8_t* const out = body - ((uintptr_t)body & 3u);                 // result characters start here (<= body)
+    uint32_t bad = 0;
+    uint32_t unext = nblk ? b64_dec4(ld_u32_unaligned(body + 4u * gb0), tab, bad) : 0u;
+    for (uint32_t j = 0; j < nblk; ++j) {
+        const uint8_t* ca = body + 16u * j;
+        const uint8_t* cb = body + 4u * (gb0 + 4u * j);
+        const uint32_t a0 = b64_dec4(ld_u32_unaligned(ca), tab, bad), a1 = b64_dec4(ld_u32_unaligned(ca + 4), tab, bad);
+        const uint32_t a2 = b64_dec4(ld_u32_unaligned(ca + 8), tab, bad), a3 = b64_dec4(ld_u32_unaligned(ca + 12), tab, bad);
+        const uint32_t u0 = unext;
+        const uint32_t u1 = b64_dec4(ld_u32_unaligned(cb + 4), tab, bad), u2 = b64_dec4(ld_u32_unaligned(cb + 8), tab, bad);
+        const uint32_t u3 = b64_dec4(ld_u32_unaligned(cb + 12), tab, bad);
+        if (ph || j + 1u < nblk) unext = b64_dec4(ld_u32_unaligned(cb + 16), tab, bad);
+        const uint32_t s0 = __byte_perm(u0, u1, 0x6012), s1 = __byte_perm(u1, u2, 0x5601), s2 = __byte_perm(u2, u3, 0x4560);
+        const uint32_t s3 = __byte_perm(unext, 0u, 0x4012);
+        const uint32_t z0 = vadd_bits(__byte_perm(a0, a1, 0x6012), __funnelshift_r(s0, s1, 8u * ph));
+        const uint32_t z1 = vadd_bits(__byte_perm(a1, a2, 0x5601), __funnelshift_r(s1, s2, 8u * ph));
+        const uint32_t z2 = vadd_bits(__byte_perm(a2, a3, 0x4560), __funnelshift_r(s2, s3, 8u * ph));
+        uint32_t* o = (uint32_t*)(out + 16u * j);
+        o[0] = b64_enc4(__byte_perm(z0, 0u, 0x4012), tab);              // bytes 0..2
+        o[1] = b64_enc4(__byte_perm(z0, z1, 0x4345), tab);              // bytes 3..5: z0.b3, z1.b0, z1.b1
+        o[2] = b64_enc4(__byte_perm(z1, z2, 0x4234), tab);              // bytes 6..8: z1.b2, z1.b3, z2.b0
+        o[3] = b64_enc4(__byte_perm(z2, 0u, 0x4123), tab);              // bytes 9..11: z2.b1, z2.b2, z2.b3
+    }
+    uint32_t nchars = 16u * nblk;
+    if (rem) {
+        const uint32_t last = G - 1u;
+        uint32_t z[2] = {0u, 0u};
+        #pragma unroll
+        for (uint32_t t = 0; t < 2; ++t) {
+            if (t < rem) {
+                const uint32_t i = 3u * nblk + t;
+                z[t] = vadd_bits(b64_u32_at(body, 4u * i, last, pad, tab, bad), b64_u32_at(body, 4u * (n + i), last, pad, tab, bad));
+            }
+        }
+        uint32_t* o = (uint32_t*)(out + nchars);
+        o[0] = b64_enc4(__byte_perm(z[0], 0u, 0x4012), tab);
+        if (rem == 1u) {
+            o[1] = (b64_enc4(__byte_perm(z[0], 0u, 0x4344), tab) & 0x0000FFFFu) | 0x3D3D0000u;          // z0.b3 + "=="
+            nchars += 8u;
+        } else {
+            o[1] = b64_enc4(__byte_perm(z[0], z[1], 0x4345), tab);
+            o[2] = (b64_enc4(__byte_perm(z[1], 0u, 0x4234), tab) & 0x00FFFFFFu) | 0x3D000000u;           // z1.b2, z1.b3 + "="
+            nchars += 12u;
+        }
+    }
+    if (bad & 0x80u) return 2;
+    out[-1] = '"'; out[nchars] = '"';
+    rec.src_off = (uint32_t)(out - 1 - p); rec.src_len = nchars + 2u; rec.out_len = nchars + 2u; rec.mode = OM_COPY; rec.has = 1;
+    return 1;
+}
+
+// ------------------------------------------------------------------ json_sum, one task per warp, bit-parallel
+// configs[4]: `{"args": [DOC], "kwargs": {}}` with DOC a flat JSON object as json.dumps writes it
+// (members `"key": value`, values = non-negative integers, strings without escapes, arrays of integers;
+// one optional space after ',' and ':'). Lane r owns bytes [32r, 32r+32) of DOC (DOC <= 1 KiB):
+//   1. every byte -> a 4-bit class through a table in shared memory, gathered into four 32-bit planes;
+//   2. strings, brackets and separators by prefix-XOR of the class masks (simdjson's stage 1, per warp);
+//   3. the grammar as look-behind rules on those masks (each byte against its predecessor token);
+//   4. the last "values" key, its array span, and a Horner walk of each lane's own digits.
+// Anything the rules do not accept (escapes, non-ASCII, floats, negatives, nesting, literals, > 15 digits,
+// other whitespace, no "values" array) is NOT decided here: the caller runs the sequential parser.
+enum JsonCls : uint8_t { JC_NONE = 0, JC_QUOTE = 1, JC_DIGIT = 2, JC_COMMA = 3, JC_COLON = 4, JC_SPACE = 5, JC_OB = 6, JC_CB = 7,
+                         JC_LB = 8, JC_RB = 9, JC_OTHER = 10, JC_ZERO = 11, JC_BAD = 15 };
+__device__ __forceinline__ uint8_t json_cls_of(uint32_t c) {
+    if (c < 0x20u || c >= 0x7Fu || c == '\\') return JC_BAD;
+    switch (c) {
+    case '"': return JC_QUOTE; case ',': return JC_COMMA; case ':': return JC_COLON; case ' ': return JC_SPACE;
+    case '[': return JC_OB; case ']': return JC_CB; case '{': return JC_LB; case '}': return JC_RB; case '0': return JC_ZERO;
+    default: return (c >= '1' && c <= '9') ? JC_DIGIT : JC_OTHER;
+    }
+}
+__device__ __forceinline__ uint32_t prefix_xor32(uint32_t x) { x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; return x; }
+__device__ __forceinline__ uint32_t lane_prev(uint32_t m, int lane) { const uint32_t v = __shfl_up_sync(0xffffffffu, m, 1); return lane ? v : 0u; }
+// parity of `bit` over the lanes below this one
+__device__ __forceinline__ uint32_t parity_below(bool bit, int lane) { return __popc(__ballot_sync(0xffffffffu, bit) & ((1u << lane) - 1u)) & 1u; }
+
+constexpr uint32_t JSON_COOP_MAX_DOC = 1024;
+constexpr uint32_t JSON_PRE_LEN = FRAME_PRE_LEN - 1, JSON_SUF_LEN = FRAME_SUF_LEN - 1;     // the frame without the string quotes
+
+// 1 = decided (*sum_out valid, task COMPLETE), 0 = not decided
+__device__ __forceinline__ int json_sum_coop(const uint8_t* __restrict__ p, uint32_t len, int lane, const uint8_t* cls_tab,
+                                             const unsigned long long* pow10, unsigned long long* sum_out) {
+    if (len < JSON_PRE_LEN + JSON_SUF_LEN + 2u || len - JSON_PRE_LEN - JSON_SUF_LEN > JSON_COOP_MAX_DOC) return 0;
+    bool okb = true;
+    if (lane < (int)JSON_PRE_LEN) okb = p[lane] == FRAME_PRE[lane];
+    else if (lane < (int)(JSON_PRE_LEN + JSON_SUF_LEN)) okb = p[len - JSON_SUF_LEN + (lane - JSON_PRE_LEN)] == FRAME_SUF[1 + lane - JSON_PRE_LEN];
+    if (!__all_sync(0xffffffffu, okb)) return 0;
+    const uint8_t* const D = p + JSON_PRE_LEN;
+    const uint32_t n = len - JSON_PRE_LEN - JSON_SUF_LEN;
+    const uint32_t base = 32u * (uint32_t)lane;
+    const uint32_t cnt = base < n ? min(32u, n - base) : 0u;
+    const uint32_t inr = cnt == 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+
+    // ---- 1. my 32 bytes -> class planes
+    uint32_t w[8];
+    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    if (cnt) {
+        const uint8_t* q = D + base;
+        const uint32_t mis = (uint32_t)((uintptr_t)q & 3u);
+        const uint32_t* qa = (const uint32_t*)(q - mis);
+        uint32_t t[9];
+        #pragma unroll
+        for (int i = 0; i < 9; ++i) t[i] = qa[i];                      // up to 3 + 4 bytes past my chunk: frame suffix / stage slack
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __funnelshift_r(t[i], t[i + 1], 8u * mis);
+        #pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t cls = cls_tab[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu];
+            b0 = __funnelshift_r(b0, cls, 1); b1 = __funnelshift_r(b1, cls >> 1, 1);
+            b2 = __funnelshift_r(b2, cls >> 2, 1); b3 = __funnelshift_r(b3, cls >> 3, 1);
+        }
+        b0 &= inr; b1 &= inr; b2 &= inr; b3 &= inr;
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = 0;
+    }
+    const uint32_t Q = ~b3 & ~b2 & ~b1 & b0, DG9 = ~b3 & ~b2 & b1 & ~b0, CM = ~b3 & ~b2 & b1 & b0, CL = ~b3 & b2 & ~b1 & ~b0;
+    const uint32_t SP = ~b3 & b2 & ~b1 & b0, OB = ~b3 & b2 & b1 & ~b0, CB = ~b3 & b2 & b1 & b0, LB = b3 & ~b2 & ~b1 & ~b0;
+    const uint32_t RB = b3 & ~b2 & ~b1 & b0, OTH = b3 & ~b2 & b1 & ~b0, ZR = b3 & ~b2 & b1 & b0, BAD = b3 & b2;
+    uint32_t v = BAD;                                                   // violations, any lane, any bit
+
+    // ---- 2. strings / arrays / object-level separators
+    const uint32_t qinc = prefix_xor32(Q) ^ (parity_below(__popc(Q) & 1u, lane) ? 0xFFFFFFFFu : 0u);   // quotes in [0, i], parity
+    const uint32_t OPENQ = Q & qinc, CLOSEQ = Q & ~qinc;
+    const uint32_t out = ~(qinc & ~Q) & inr;                            // not string content
+    v |= OTH & out;
+    const uint32_t dg = (DG9 | ZR) & out, zr = ZR & out, cm = CM & out, cl = CL & out, sp = SP & out;
+    const uint32_t ob = OB & out, cb = CB & out, lb = LB & out, rb = RB & out;
+    const uint32_t br = ob | cb;
+    const uint32_t binc = prefix_xor32(br) ^ (parity_below(__popc(br) & 1u, lane) ? 0xFFFFFFFFu : 0u);
+    v |= (ob & ~binc) | (cb & binc);                                    // '[' opens at depth 0 only, ']' closes
+    const uint32_t arr = binc & ~ob & inr;                              // strictly inside an array
+    v |= cl & arr;
+    const uint32_t sep = (cm | cl) & ~arr;
+    const uint32_t sinc = prefix_xor32(sep) ^ (parity_below(__popc(sep) & 1u, lane) ? 0xFFFFFFFFu : 0u);
+    v |= (cl & ~sinc) | (cm & ~arr & sinc);                             // object level: ':' ',' ':' ',' ... ':'
+    const uint32_t quotes_odd = __popc(__ballot_sync(0xffffffffu, __popc(Q) & 1u)) & 1u;
+    const uint32_t br_odd = __popc(__ballot_sync(0xffffffffu, __popc(br) & 1u)) & 1u;
+    const uint32_t sep_odd = __popc(__ballot_sync(0xffffffffu, __popc(sep) & 1u)) & 1u;
+
+    // ---- 3. the grammar, each byte against its predecessor (one optional space after ',' ':')
+    const uint32_t p_closeq = lane_prev(CLOSEQ, lane), p_openq = lane_prev(OPENQ, lane), p_dg = lane_prev(dg, lane), p_zr = lane_prev(zr, lane);
+    const uint32_t p_cm = lane_prev(cm, lane), p_cl = lane_prev(cl, lane), p_sp = lane_prev(sp, lane);
+    const uint32_t p_ob = lane_prev(ob, lane), p_cb = lane_prev(cb, lane);
+    #define B9_P1(M, PM) (((M) << 1) | ((PM) >> 31))
+    #define B9_P2(M, PM) (((M) << 2) | ((PM) >> 30))
+    const uint32_t a_closeq = B9_P1(CLOSEQ, p_closeq), a_dg = B9_P1(dg, p_dg), a_cm = B9_P1(cm, p_cm), a_cl = B9_P1(cl, p_cl);
+    const uint32_t a_sp = B9_P1(sp, p_sp), a_ob = B9_P1(ob, p_ob), a_cb = B9_P1(cb, p_cb), a_zr = B9_P1(zr, p_zr);
+    const uint32_t a_lb = (lb << 1);                                    // '{' is byte 0 (checked below): never a lane's last byte... unless n == 1
+    const uint32_t t_cm = a_cm | (a_sp & B9_P2(cm, p_cm)), t_cl = a_cl | (a_sp & B9_P2(cl, p_cl));   // previous token, through the space
+    const uint32_t ds = dg & ~a_dg;                                     // first digit of a number
+    v |= sp & ~(a_cm | a_cl);
+    v |= a_closeq & inr & ~(cl | cm | rb);
+    v |= a_dg & inr & ~dg & ~(cm | cb | rb);
+    v |= a_cb & inr & ~(cm | rb);
+    v |= dg & a_zr & ~B9_P2(dg, p_dg);                                  // a digit after a leading zero
+    v |= OPENQ & (arr | ~(a_lb | t_cm | t_cl));
+    v |= cl & ~a_closeq;
+    v |= cm & ~arr & ~(a_closeq | a_dg | a_cb);
+    v |= cm & arr & ~a_dg;
+    v |= ob & ~t_cl;
+    v |= cb & ~(a_ob | a_dg);
+    v |= ds & ((arr & ~(a_ob | t_cm)) | (~arr & ~t_cl));
+    v |= lb ^ (lane == 0 ? 1u : 0u);                                    // exactly one '{', at byte 0
+    const uint32_t last = n - 1u;
+    const uint32_t lastbit = (last >> 5) == (uint32_t)lane ? (1u << (last & 31u)) : 0u;
+    v |= rb ^ lastbit;                                                  // exactly one '}', at byte n-1
+    v |= rb & ~(a_lb | a_closeq | a_dg | a_cb);
+    if (rb && !(rb & a_lb) && !sep_odd) v |= 1u;                        // a non-empty object ends after "key": value
+    if (__any_sync(0xffffffffu, v != 0u) || quotes_odd || br_odd) return 0;
+
+    // ---- 4a. the last `"values":` key: ':' at J, '"' at J-1 and J-8
+    uint32_t cand = cl & a_closeq & ((OPENQ << 8) | (p_openq >> 24));
+    int bestJ = -1;
+    while (cand) {
+        const int j = 31 - __clz(cand);
+        const uint8_t* k = D + base + j - 7;
+        if (k[0] == 'v' && k[1] == 'a' && k[2] == 'l' && k[3] == 'u' && k[4] == 'e' && k[5] == 's') { bestJ = (int)base + j; break; }
+        cand &= ~(1u << j);
+    }
+    bestJ = __reduce_max_sync(0xffffffffu, bestJ);
+    if (bestJ < 0) return 0;                                            // KeyError is the sequential path's to report
+    uint32_t vs = (uint32_t)bestJ + 1u;
+    if (D[vs] == ' ') ++vs;
+    if (D[vs] != '[') return 0;                                         // sum() of a non-list
+    const uint32_t after = vs >= base + 32u ? 0u : (vs < base ? 0xFFFFFFFFu : (vs - base == 31u ? 0u : (0xFFFFFFFFu << (vs - base + 1u))));
+    const uint32_t cb_after = cb & after;
+    const uint32_t ve = __reduce_min_sync(0xffffffffu, cb_after ? base + (uint32_t)(__ffs(cb_after) - 1) : 0xFFFFFFFFu);
+
+    // ---- 4b. Horner over my own digits; a number that runs into the next lane is finished there
+    unsigned long long sum = 0, val = 0, head_val = 0;
+    uint32_t rl = 0, head_len = 0, toolong = 0;
+    bool head = (p_dg >> 31) != 0u && (dg & 1u) != 0u;                  // my first byte continues the previous lane's number
+    #pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFu;
+        if ((dg >> j) & 1u) { val = val * 10ull + c; ++rl; }
+        else if (rl) {
+            toolong |= rl > 15u;
+            const uint32_t pos = base + (uint32_t)j - 1u;               // the number's last digit
+            if (head) { head_val = val; head_len = rl; head = false; }
+            else if (pos > vs && pos < ve) sum += val;
+            val = 0; rl = 0;
+        }
+    }
+    // a number still open at the end of my chunk is finished by the next lane (DOC ends with '}': that lane exists)
+    const bool open_tail = rl != 0u;
+    if (open_tail && head) toolong = 1u;                                // 32 digits in a row
+    const unsigned long long tv = __shfl_up_sync(0xffffffffu, open_tail ? val : 0ull, 1);
+    const uint32_t tl = __shfl_up_sync(0xffffffffu, open_tail ? rl : 0u, 1);
+    if (lane && (p_dg >> 31)) {
+        // the previous lane's last byte is a digit: its number ends with my first head_len digits (possibly none)
+        toolong |= tl + head_len > 15u;
+        const unsigned long long full = tv * pow10[min(head_len, 15u)] + head_val;
+        if (base - 1u > vs && base - 1u < ve) sum += full;
+    }
+    if (__any_sync(0xffffffffu, toolong != 0u)) return 0;
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    *sum_out = sum;
+    return 1;
+    #undef B9_P1
+    #undef B9_P2
+}
+
 // ================================================================== the kernel: warp-autonomous
 // Every WARP is an independent worker with its own ticket pipeline, its own slice of shared memory
 // (slot metadata + one stage buffer + one mbarrier) and its own cursor add. There is no block
@@ -412,9 +769,11 @@ template <int HANDLER> struct D3Cfg {
 #define B9_IDENTITY_G 1
 #endif
     static constexpr int G = (HANDLER == 0) ? B9_IDENTITY_G : 1;
-    static constexpr int T = 32 / G;                      // tasks per warp-tile
+    // tasks per warp-tile. crc32 (configs[2]: zipf 32..4096-byte strings, ~1 KB on average) works on a task
+    // with the whole warp, so its tiles are small: 4 tasks keep the stage buffer at ~5 KB, which leaves L1 room for the shift tables.
+    static constexpr int T = (HANDLER == 1) ? 4 : (HANDLER == 3) ? 8 : 32 / G;
 };
-constexpr int D2_THREADS = 16;               // host: tasks per look-back slot (smallest warp-tile)
+constexpr int D2_THREADS = 4;                // host: tasks per look-back slot (smallest warp-tile)
 
 template <int T>
 struct D3Warp {
@@ -509,6 +868,9 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
     constexpr int G = D3Cfg<HANDLER>::G, T = D3Cfg<HANDLER>::T;
     extern __shared__ __align__(128) uint8_t d3_smem[];
     __shared__ uint32_t s_crc_table[HANDLER == 1 ? 256 : 1];
+    __shared__ __align__(128) uint8_t s_b64[HANDLER == 2 ? 320 : 4];
+    __shared__ __align__(128) uint8_t s_jcls[HANDLER == 3 ? 256 : 4];
+    __shared__ unsigned long long s_pow10[HANDLER == 3 ? 16 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* const wbase = d3_smem + (size_t)warp * warp_stride;
     D3Warp<T>& W = *reinterpret_cast<D3Warp<T>*>(wbase);
@@ -516,6 +878,15 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
     const int k = lane / G, sub = lane % G;                                // my task inside the warp-tile, my share of it
 
     if (HANDLER == 1) { for (int i = threadIdx.x; i < 256; i += D3_WARPS * 32) s_crc_table[i] = crc_table_entry(i); __syncthreads(); }
+    if (HANDLER == 3) {
+        for (int i = threadIdx.x; i < 256; i += D3_WARPS * 32) s_jcls[i] = json_cls_of((uint32_t)i);
+        if (threadIdx.x < 16) { unsigned long long pw = 1; for (int i = 0; i < (int)threadIdx.x; ++i) pw *= 10ull; s_pow10[threadIdx.x] = pw; }
+        __syncthreads();
+    }
+    if (HANDLER == 2) {
+        for (int i = threadIdx.x; i < 320; i += D3_WARPS * 32) s_b64[i] = i < 256 ? (uint8_t)b64_val((uint8_t)i) : b64_chr((uint32_t)i - 256u);
+        __syncthreads();
+    }
     if (lane == 0) { mbar_init(&W.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
 
@@ -573,6 +944,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         const uint32_t my_soff = (mine && staged) ? W.soff[k] : 0u;
         const uint64_t my_goff = mine ? W.goff[k] : 0ull;
         TaskRec rec; rec.ready = mine; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
+        bool clobbered = false;
         if (HANDLER == 0) {
             // identity: settle the common case here (canonical frame, clean body -> the token is its own
             // json.dumps); everything else is handed to drain_slow_kernel through the work list, so that
@@ -586,9 +958,32 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                     if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
                 } else { rec.mode = OM_DEFER; rec.value = (long long)(q & 1u); }
             }
+        } else if (HANDLER == 1) {
+            // crc32: the whole warp works on one task at a time (tasks are long and of very different lengths)
+            for (uint32_t kt = 0; kt < nt; ++kt) {
+                if (!((ready_mask_t >> kt) & 1u)) continue;
+                if (staged) crc_task_coop(sbuf + W.soff[kt], W.len[kt], lane, lane == (int)kt, s_crc_table, a.crc_shift_tabs, rec);
+                else        crc_task_coop(a.payload + W.goff[kt], W.len[kt], lane, lane == (int)kt, s_crc_table, a.crc_shift_tabs, rec);
+            }
+        } else if (HANDLER == 3) {
+            // json_sum: the whole warp parses one document at a time
+            for (uint32_t kt = 0; kt < nt; ++kt) {
+                if (!((ready_mask_t >> kt) & 1u)) continue;
+                int done = 0; unsigned long long sum = 0;
+                if (staged) done = json_sum_coop(sbuf + W.soff[kt], W.len[kt], lane, s_jcls, s_pow10, &sum);
+                if (lane == (int)kt) {
+                    if (done) { if (sum) { rec.value = (long long)sum; rec.out_len = dec_len_u64(sum); rec.mode = OM_I64_DEC; rec.has = 1; } }
+                    else d2_parse_and_size<3>(staged ? (const uint8_t*)(sbuf + W.soff[kt]) : a.payload + W.goff[kt], W.len[kt], rec, nullptr);
+                }
+            }
         } else if (mine) {
-            const uint8_t* p = staged ? (const uint8_t*)(sbuf + my_soff) : a.payload + my_goff;
-            d2_parse_and_size<HANDLER>(p, my_len, rec, s_crc_table);
+            int fr = 0;
+            if (HANDLER == 2 && staged) fr = vadd_fast(sbuf + my_soff, my_len, s_b64, rec);
+            if (fr != 1) {
+                clobbered = fr == 2;                                       // stage bytes overwritten: read the ring instead
+                const uint8_t* p = (staged && !clobbered) ? (const uint8_t*)(sbuf + my_soff) : a.payload + my_goff;
+                d2_parse_and_size<HANDLER>(p, my_len, rec, s_crc_table);
+            }
         }
 
         // ---------------- compaction (ballot) + sizes (scan) + ONE cursor add per warp-tile -------------
@@ -620,7 +1015,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                     if (staged) group_copy<G>(a.out_payload + ob, sbuf + my_soff + rec.src_off, rec.src_len, sub);
                     else        group_copy_generic<G>(a.out_payload + ob, a.payload + my_goff + rec.src_off, rec.src_len, sub);
                 } else if (sub == 0 && rec.mode != OM_STR_PAR) {
-                    const uint8_t* p = staged ? (const uint8_t*)(sbuf + my_soff) : a.payload + my_goff;
+                    const uint8_t* p = (staged && !clobbered) ? (const uint8_t*)(sbuf + my_soff) : a.payload + my_goff;
                     d2_phase_b_task<HANDLER>(p, rec, a.out_payload + ob);
                 }
             }

@@ -160,14 +160,22 @@ __device__ __forceinline__ float b64_f32(const uint8_t* __restrict__ p, uint32_t
 }
 __device__ __forceinline__ uint32_t b64_encoded_len(uint32_t nbytes) { return ((nbytes + 2) / 3) * 4; }
 
+// IEEE-754 binary32 a+b, round-to-nearest-even, as the reference's runner computes it (numpy on x86-64,
+// SSE addss): a NaN operand is propagated quieted (the first operand wins), inf + -inf is the x86
+// "real indefinite" 0xFFC00000. The GPU's own NaN (0x7FFFFFFF) never reaches the result.
+__device__ __forceinline__ uint32_t vadd_bits(uint32_t xb, uint32_t yb) {
+    const uint32_t z = __float_as_uint(__fadd_rn(__uint_as_float(xb), __uint_as_float(yb)));
+    const bool xn = (xb & 0x7FFFFFFFu) > 0x7F800000u, yn = (yb & 0x7FFFFFFFu) > 0x7F800000u, zn = (z & 0x7FFFFFFFu) > 0x7F800000u;
+    return xn ? (xb | 0x00400000u) : yn ? (yb | 0x00400000u) : zn ? 0xFFC00000u : z;
+}
+
 // writes '"' + base64(a+b) + '"' for n floats per vector; body = p[s..)
 __device__ inline void vadd_write(const uint8_t* __restrict__ p, uint32_t s, uint32_t n, uint8_t* __restrict__ o) {
     *o++ = '"';
     uint32_t acc = 0, have = 0;
     const uint32_t total = 4 * n;
     for (uint32_t i = 0; i < n; ++i) {
-        float x = b64_f32(p, s, 4 * i), y = b64_f32(p, s, 4 * (n + i));
-        uint32_t z = __float_as_uint(__fadd_rn(x, y));
+        uint32_t z = vadd_bits(__float_as_uint(b64_f32(p, s, 4 * i)), __float_as_uint(b64_f32(p, s, 4 * (n + i))));
         #pragma unroll
         for (int k = 0; k < 4; ++k) {
             acc = (acc << 8) | ((z >> (8 * k)) & 0xFF); ++have;

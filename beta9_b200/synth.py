@@ -181,6 +181,25 @@ def vadd_batch(n: int, floats_per_vec: int = 32, seed: int = SEED, name: str = "
     return Batch(task_ids(n, seed), rows.reshape(-1), offsets, name)
 
 
+def vadd_special_batch(n: int, floats_per_vec: int = 32, seed: int = SEED, name: str = "vadd_f32_special") -> Batch:
+    """vadd_f32 payloads over raw random bit patterns (NaNs with payloads, infinities, denormals,
+    signed zeros, overflow to inf): the cases where an fp32 add is more than rounding."""
+    rng = np.random.default_rng(seed + 33)
+    bits = rng.integers(0, 1 << 32, size=(n, 2 * floats_per_vec), dtype=np.uint64).astype(np.uint32)
+    special = np.array([0x7F800000, 0xFF800000, 0x7FC00000, 0xFFC00000, 0x7FA00001, 0xFFA12345, 0x00000001, 0x80000001,
+                        0x007FFFFF, 0x00000000, 0x80000000, 0x7F7FFFFF, 0xFF7FFFFF, 0x3F800000, 0xBF800000, 0x7FFFFFFF], np.uint32)
+    pick = rng.random(bits.shape) < 0.5
+    bits[pick] = special[rng.integers(0, special.size, size=int(pick.sum()))]
+    raw = bits.view(np.uint8).reshape(n, -1)
+    b64 = _b64_rows(raw)
+    rows = np.empty((n, b64.shape[1] + len(PREFIX) + len(SUFFIX)), dtype=np.uint8)
+    rows[:, :len(PREFIX)] = np.frombuffer(PREFIX, np.uint8)
+    rows[:, len(PREFIX):len(PREFIX) + b64.shape[1]] = b64
+    rows[:, len(PREFIX) + b64.shape[1]:] = np.frombuffer(SUFFIX, np.uint8)
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(rows.shape[1])
+    return Batch(task_ids(n, seed), rows.reshape(-1), offsets, name)
+
+
 _B64 = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/", np.uint8)
 
 

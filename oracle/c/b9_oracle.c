@@ -626,8 +626,15 @@ static int run_handler(int h, val_t *args, val_t *kwargs, buf_t *out, int *has, 
         if (!n) return B9O_COMPLETE;                                   /* "" is falsy          */
         uint8_t *res = (uint8_t *)arena_alloc(ar, n * 4 + 4);
         for (size_t i = 0; i < n; i++) {
-            float x, y; memcpy(&x, raw + 4 * i, 4); memcpy(&y, raw + 4 * (n + i), 4);
-            volatile float z = x + y; float zz = z; memcpy(res + 4 * i, &zz, 4);
+            /* numpy `a + b` on x86-64 (SSE/AVX addps, a = first source): a NaN operand comes back
+             * quieted, the first one winning; inf + -inf is the "real indefinite" 0xFFC00000. Written
+             * out so that the answer does not depend on the operand order this compiler picks. */
+            float x, y; uint32_t xb, yb, zb;
+            memcpy(&x, raw + 4 * i, 4); memcpy(&y, raw + 4 * (n + i), 4); memcpy(&xb, &x, 4); memcpy(&yb, &y, 4);
+            if ((xb & 0x7FFFFFFFu) > 0x7F800000u) zb = xb | 0x00400000u;
+            else if ((yb & 0x7FFFFFFFu) > 0x7F800000u) zb = yb | 0x00400000u;
+            else { volatile float z = x + y; float zz = z; memcpy(&zb, &zz, 4); if ((zb & 0x7FFFFFFFu) > 0x7F800000u) zb = 0xFFC00000u; }
+            memcpy(res + 4 * i, &zb, 4);
         }
         size_t rl = n * 4;
         buf_putc(out, '"');

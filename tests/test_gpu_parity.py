@@ -133,16 +133,67 @@ def test_vadd_f32(dq):
         got = np.frombuffer(base64.b64decode(r.result(i)[1:-1]), "<f4")
         want = np.frombuffer(base64.b64decode(o.result(i)[1:-1]), "<f4")
         assert np.allclose(got, want, rtol=1e-6, atol=0)
-    for fpv in (1, 3, 5, 7):                      # every base64 padding phase
-        b = synth.vadd_batch(500, floats_per_vec=fpv, seed=fpv)
+    for fpv in list(range(1, 14)) + [31, 33, 64, 100]:      # every base64 phase of a, of b and of the padding
+        b = synth.vadd_batch(300, floats_per_vec=fpv, seed=fpv)
         r = run_gpu(dq, b, "vadd_f32")
         assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "vadd_f32"))
+        b = synth.vadd_special_batch(300, floats_per_vec=fpv, seed=fpv)     # NaN payloads, inf - inf, denormals
+        r = run_gpu(dq, b, "vadd_f32")
+        assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "vadd_f32"))
+
+
+def test_vadd_f32_corrupted_text(dq):
+    """One wrong character anywhere in an otherwise canonical task (outside the alphabet, '=' in the
+    middle, a missing character, an odd float count) must come out exactly as the oracle says."""
+    rng = np.random.default_rng(77)
+    payloads = []
+    for fpv in (1, 2, 3, 4, 32):
+        base = synth.vadd_batch(40, floats_per_vec=fpv, seed=100 + fpv)
+        for i in range(base.n):
+            p = bytearray(base.payload[int(base.offsets[i]):int(base.offsets[i + 1])].tobytes())
+            lo, hi = 11, len(p) - 17
+            kind = i % 5
+            pos = int(rng.integers(lo, hi))
+            if kind == 0: p[pos] = rng.choice(list(b"!#$%&'()*,-.:;<>?@[]^_`{|}~ \x7f\"\\\n"))
+            elif kind == 1: p[pos] = ord("=")
+            elif kind == 2: del p[pos]
+            elif kind == 3: p[pos:pos] = b"AAAA"           # four more characters: three more bytes, not two vectors any more
+            else: p[pos] = 0xC3                            # not ASCII (and not valid UTF-8)
+            payloads.append(bytes(p))
+    b = synth.from_payloads(payloads)
+    r = run_gpu(dq, b, "vadd_f32")
+    assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "vadd_f32"))
 
 
 def test_json_sum(dq):
     b = synth.json_batch(20_000)                  # BASELINE configs[4] payload shape
     r = run_gpu(dq, b, "json_sum")
     assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "json_sum", nthreads=16))
+
+
+def test_json_sum_fast_path_boundaries_and_mutants(dq):
+    """The warp-cooperative parser: numbers straddling every 32-byte lane boundary, documents around
+    the 1 KiB limit, both separator styles, and single-character mutants of canonical documents."""
+    import json
+    from tests.test_json_coop_model import _payloads
+    rng = np.random.default_rng(0xB9 + 7)
+    payloads = _payloads(rng, 800)
+    for shift in range(0, 70):                     # slide a run of 15-digit and short numbers across the lane boundaries
+        d = {"p": "x" * shift, "values": [999999999999999, 7, 123456789012345, 0, 10, 100000000000000] * 3, "q": 5}
+        payloads.append(json.dumps({"args": [d], "kwargs": {}}).encode())
+    for size in (900, 1000, 1023, 1024, 1025, 1100, 2048, 5000):      # around JSON_COOP_MAX_DOC
+        vals = rng.integers(0, 10**6, size=60).tolist()
+        d = {"id": size, "values": vals, "pad": ""}
+        d["pad"] = "y" * max(0, size - len(json.dumps(d)))
+        payloads.append(json.dumps({"args": [d], "kwargs": {}}).encode())
+    b = synth.from_payloads(payloads)
+    r = run_gpu(dq, b, "json_sum")
+    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "json_sum", nthreads=16)
+    assert_matches_oracle(b, r, o, allow_unsupported=b.n)
+    for i in np.flatnonzero(r.status == 4):        # declined only where the oracle's domain ends too, or on exotic numbers
+        assert o.status[i] in (0, 3, 4), payloads[i]
+    # the canonical documents must not be declined
+    assert int((r.status[-78:] == 4).sum()) == 0
 
 
 def test_wrong_handler_for_payload(dq):

@@ -43,6 +43,10 @@ def test_crc_zipf():
 def test_vadd():
     compare(synth.vadd_batch(2000), "vadd_f32")
     compare(synth.vadd_batch(300, floats_per_vec=5, seed=1), "vadd_f32")
+    # NaN payloads, infinities, denormals: the C restatement spells out the x86 rules, numpy (the
+    # reference's arithmetic, on this x86-64 host) is the judge
+    for fpv in (1, 2, 3, 32):
+        compare(synth.vadd_special_batch(400, floats_per_vec=fpv, seed=fpv), "vadd_f32")
 
 
 def test_json_sum():

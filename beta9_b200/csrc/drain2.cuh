@@ -399,60 +399,81 @@ __device__ __noinline__ void esc_emit_general(const uint8_t* __restrict__ body, 
 
 // ------------------------------------------------------------------ warp-cooperative CRC-32 of a framed string
 // zlib.crc32(s.encode()) over the DECODED bytes, 32 chunks in parallel. With R(c, b) the reflected
-// table step and r_l the register after lane l's decoded bytes starting from 0, linearity gives
-//   R*(0xFFFFFFFF, B_0 || ... || B_31) = Z(0xFFFFFFFF, N) ^ XOR_l Z(r_l, bytes after lane l)
+// table step and r_l the register after lane l's decoded bytes (lane 0 starts from 0xFFFFFFFF, the
+// others from 0), linearity gives
+//   R*(0xFFFFFFFF, B_0 || ... || B_31) = XOR_l Z(r_l, bytes after lane l)
 // where Z(c, n) advances the register over n zero bytes. Z for n = 2^k is a fixed linear map, kept as
 // 4 x 256-entry byte tables per k (`shift_tabs`, built on the host): a shift costs 4 loads per set bit.
 constexpr int CRC_SHIFT_LEVELS = 32;         // any 32-bit byte count (128 KiB of tables, L2-resident)
 __device__ __forceinline__ uint32_t crc_zero_shift(uint32_t c, uint32_t nbytes, const uint32_t* __restrict__ shift_tabs) {
-    for (uint32_t k = 0; nbytes; ++k, nbytes >>= 1) {
-        if (nbytes & 1u) {
-            const uint32_t* t = shift_tabs + (size_t)k * 1024;
-            c = __ldg(t + (c & 0xFFu)) ^ __ldg(t + 256 + ((c >> 8) & 0xFFu)) ^ __ldg(t + 512 + ((c >> 16) & 0xFFu)) ^ __ldg(t + 768 + (c >> 24));
-        }
+    // every lane walks the same levels (up to the warp's highest set bit) and applies its own: no divergence
+    const uint32_t levels = 32u - __clz(__reduce_or_sync(0xffffffffu, nbytes));
+    for (uint32_t k = 0; k < levels; ++k) {
+        const uint32_t* t = shift_tabs + (size_t)k * 1024;
+        const uint32_t s = __ldg(t + (c & 0xFFu)) ^ __ldg(t + 256 + ((c >> 8) & 0xFFu)) ^ __ldg(t + 512 + ((c >> 16) & 0xFFu)) ^ __ldg(t + 768 + (c >> 24));
+        c = ((nbytes >> k) & 1u) ? s : c;
     }
     return c;
 }
 
+// Explicit shared-window loads for the byte loop: 32-bit addresses, no generic-pointer arithmetic per byte.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+struct LdShared  { uint32_t base;   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return lds_u8(base + i); } };
+struct LdGeneric { const uint8_t* p; __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i]; } };
+__device__ __forceinline__ uint32_t crc_step(uint32_t r, uint32_t b, uint32_t tab_s) { return lds_u32(tab_s + (((r ^ b) & 0xFFu) << 2)) ^ (r >> 8); }
+
 // returns false when the body is not a well-formed JSON string body (caller falls back to the sequential parser).
-// Force-inlined so that loads keep their address space (LDS for a staged tile, LDG otherwise).
-__device__ __forceinline__ bool crc_scan_coop(const uint8_t* __restrict__ body, uint32_t n, int lane, const uint32_t* crc_table,
+// `ld(i)` reads body byte i (shared window or generic); `body` is the same memory as a generic pointer for the
+// rare out-of-line helpers; `tab_s` is the shared-window address of the 256-entry CRC table.
+template <class LD>
+__device__ __forceinline__ bool crc_scan_coop(LD ld, const uint8_t* __restrict__ body, uint32_t n, int lane, uint32_t tab_s,
                                               const uint32_t* __restrict__ shift_tabs, uint32_t* crc_out) {
     const uint32_t S = (n + 31u) / 32u;
     const uint32_t lo = min(n, (uint32_t)lane * S), hi = min(n, lo + S);
     bool ok = true;
-    uint32_t r = 0, dec = 0;
+    uint32_t r = lane == 0 ? 0xFFFFFFFFu : 0u, dec = 0;                   // lane 0 carries the register's start value
     if (lo < hi) {
         // a chunk that starts on a plain byte with no backslash among the five bytes before it (the reach of
         // a \uXXXX escape) starts on a unit boundary; anything else takes the general look-behind
         uint32_t i = lo;
         if (lo) {
-            bool easy = plain_byte(body[lo]);
+            bool easy = plain_byte(ld(lo));
             #pragma unroll
-            for (uint32_t k = 1; k <= 5; ++k) easy = easy && (lo < k || body[lo - k] != '\\');
+            for (uint32_t k = 1; k <= 5; ++k) easy = easy && (lo < k || ld(lo - k) != '\\');
             if (!easy) i = first_unit_start(body, n, lo);
         }
+        uint32_t c = i < hi ? ld(i) : 0u;
         while (i < hi) {
-            const uint32_t c = body[i], e = body[i + 1];                   // i + 1 <= n: the frame suffix follows the body
-            const bool simple = c == '\\' && (e == '"' || e == '\\' || e == '/');
-            if (plain_byte(c) || simple) { r = crc_byte(r, simple ? e : c, crc_table); ++dec; i += simple ? 2u : 1u; continue; }
-            const uint32_t cp = next_unit(body, i, n, &ok);
-            if (!ok) break;
-            if (cp < 0x80) { r = crc_byte(r, cp, crc_table); dec += 1; }
-            else if (cp < 0x800) { r = crc_byte(r, 0xC0 | (cp >> 6), crc_table); r = crc_byte(r, 0x80 | (cp & 0x3F), crc_table); dec += 2; }
-            else if (cp < 0x10000) {
-                r = crc_byte(r, 0xE0 | (cp >> 12), crc_table); r = crc_byte(r, 0x80 | ((cp >> 6) & 0x3F), crc_table); r = crc_byte(r, 0x80 | (cp & 0x3F), crc_table); dec += 3;
-            } else {
-                r = crc_byte(r, 0xF0 | (cp >> 18), crc_table); r = crc_byte(r, 0x80 | ((cp >> 12) & 0x3F), crc_table);
-                r = crc_byte(r, 0x80 | ((cp >> 6) & 0x3F), crc_table); r = crc_byte(r, 0x80 | (cp & 0x3F), crc_table); dec += 4;
+            // plain byte, or one of the two-byte escapes json.dumps writes for '"' and '\\' (and "\/"): no branch
+            const uint32_t e = ld(i + 1u);                                 // i + 1 <= n: the frame suffix follows the body
+            const uint32_t bs = c == '\\';
+            const uint32_t simple = bs & ((e == '"') | (e == '\\') | (e == '/'));
+            const uint32_t plain = (c - 0x20u < 0x5Fu) & (c != '"') & (bs ^ 1u);
+            if (plain | simple) {
+                r = crc_step(r, simple ? e : c, tab_s); ++dec;
+                if (simple) { i += 2u; c = ld(i); } else { i += 1u; c = e; }   // the look-ahead byte is the next byte
+                continue;
             }
+            uint32_t ii = i;                                               // (by reference: keep the loop counter in a register)
+            const uint32_t cp = next_unit(body, ii, n, &ok);
+            i = ii;
+            if (!ok) break;
+            if (cp < 0x80) { r = crc_step(r, cp, tab_s); dec += 1; }
+            else if (cp < 0x800) { r = crc_step(r, 0xC0 | (cp >> 6), tab_s); r = crc_step(r, 0x80 | (cp & 0x3F), tab_s); dec += 2; }
+            else if (cp < 0x10000) {
+                r = crc_step(r, 0xE0 | (cp >> 12), tab_s); r = crc_step(r, 0x80 | ((cp >> 6) & 0x3F), tab_s); r = crc_step(r, 0x80 | (cp & 0x3F), tab_s); dec += 3;
+            } else {
+                r = crc_step(r, 0xF0 | (cp >> 18), tab_s); r = crc_step(r, 0x80 | ((cp >> 12) & 0x3F), tab_s);
+                r = crc_step(r, 0x80 | ((cp >> 6) & 0x3F), tab_s); r = crc_step(r, 0x80 | (cp & 0x3F), tab_s); dec += 4;
+            }
+            c = ld(i);                                                     // i <= n: at worst the closing quote
         }
     }
     if (!__all_sync(0xffffffffu, ok)) return false;
     const uint32_t before = warp_excl_scan(dec, lane);
     const uint32_t total = __shfl_sync(0xffffffffu, before + dec, 31);
     uint32_t v = crc_zero_shift(r, total - before - dec, shift_tabs);
-    if (lane == 0) v ^= crc_zero_shift(0xFFFFFFFFu, total, shift_tabs);
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, d);
     *crc_out = ~v;
@@ -460,8 +481,8 @@ __device__ __forceinline__ bool crc_scan_coop(const uint8_t* __restrict__ body, 
 }
 
 template <int HANDLER> __device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, TaskRec& rec, const uint32_t* crc_table);
-// one crc32 task with the whole warp; the owner lane keeps the record
-__device__ __forceinline__ void crc_task_coop(const uint8_t* __restrict__ p, uint32_t len, int lane, bool owner, const uint32_t* crc_table,
+// one crc32 task with the whole warp; the owner lane keeps the record. `in_smem`: p points into this warp's stage buffer.
+__device__ __forceinline__ void crc_task_coop(const uint8_t* __restrict__ p, bool in_smem, uint32_t len, int lane, bool owner, const uint32_t* crc_table,
                                               const uint32_t* __restrict__ shift_tabs, TaskRec& rec) {
     bool framed = len >= FRAME_PRE_LEN + FRAME_SUF_LEN;
     if (framed) {
@@ -471,11 +492,31 @@ __device__ __forceinline__ void crc_task_coop(const uint8_t* __restrict__ p, uin
         framed = __all_sync(0xffffffffu, okb);
     }
     uint32_t crc = 0; bool done = false;
-    if (framed) done = crc_scan_coop(p + FRAME_PRE_LEN, len - FRAME_PRE_LEN - FRAME_SUF_LEN, lane, crc_table, shift_tabs, &crc);
+    if (framed) {
+        const uint8_t* body = p + FRAME_PRE_LEN;
+        const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN, tab_s = smem_u32(crc_table);
+        if (in_smem) { LdShared ld; ld.base = smem_u32(body); done = crc_scan_coop(ld, body, n, lane, tab_s, shift_tabs, &crc); }
+        else         { LdGeneric ld; ld.p = body;             done = crc_scan_coop(ld, body, n, lane, tab_s, shift_tabs, &crc); }
+    }
     if (owner) {
         if (done) { if (crc) { rec.value = (long long)crc; rec.out_len = dec_len_u64(crc); rec.mode = OM_U32_DEC; rec.has = 1; } }
         else d2_parse_and_size<1>(p, len, rec, crc_table);
     }
+}
+
+// A task of a tile that was not staged as a whole (the tile did not fit, or wraps the ring): pull this one
+// task into the warp's stage buffer with 16-byte loads. Returns the task's address there, or nullptr if
+// even the single task is larger than the buffer.
+__device__ __forceinline__ const uint8_t* stage_one_task(const uint8_t* __restrict__ payload, uint64_t goff, uint32_t len, uint8_t* sbuf, uint32_t in_cap, int lane) {
+    const uint32_t mis = (uint32_t)(goff & 15ull);
+    if (mis + len + 16u > in_cap) return nullptr;
+    const uint4* src = (const uint4*)(payload + goff - mis);
+    uint4* dst = (uint4*)sbuf;
+    const uint32_t nv = (mis + len + 15u) >> 4;
+    __syncwarp();                                                          // everybody is done with the previous task's bytes
+    for (uint32_t v = lane; v < nv; v += 32) dst[v] = __ldg(src + v);
+    __syncwarp();
+    return sbuf + mis;
 }
 
 // ------------------------------------------------------------------ vadd_f32, thread per task, in place in the stage buffer
@@ -610,7 +651,7 @@ constexpr uint32_t JSON_PRE_LEN = FRAME_PRE_LEN - 1, JSON_SUF_LEN = FRAME_SUF_LE
 
 // 1 = decided (*sum_out valid, task COMPLETE), 0 = not decided
 __device__ __forceinline__ int json_sum_coop(const uint8_t* __restrict__ p, uint32_t len, int lane, const uint8_t* cls_tab,
-                                             const unsigned long long* pow10, unsigned long long* sum_out) {
+                                             unsigned long long* sum_out) {
     if (len < JSON_PRE_LEN + JSON_SUF_LEN + 2u || len - JSON_PRE_LEN - JSON_SUF_LEN > JSON_COOP_MAX_DOC) return 0;
     bool okb = true;
     if (lane < (int)JSON_PRE_LEN) okb = p[lane] == FRAME_PRE[lane];
@@ -718,34 +759,38 @@ __device__ __forceinline__ int json_sum_coop(const uint8_t* __restrict__ p, uint
     const uint32_t cb_after = cb & after;
     const uint32_t ve = __reduce_min_sync(0xffffffffu, cb_after ? base + (uint32_t)(__ffs(cb_after) - 1) : 0xFFFFFFFFu);
 
-    // ---- 4b. Horner over my own digits; a number that runs into the next lane is finished there
-    unsigned long long sum = 0, val = 0, head_val = 0;
-    uint32_t rl = 0, head_len = 0, toolong = 0;
-    bool head = (p_dg >> 31) != 0u && (dg & 1u) != 0u;                  // my first byte continues the previous lane's number
+    // ---- 4b. Horner over the numbers that START in my chunk (a number cut by the chunk end is finished from
+    // the next lane's words); no data-dependent branch: run ends, the span and my head digits are masks
+    const uint32_t n_dg = __shfl_down_sync(0xffffffffu, dg, 1);        // lane 31 never has an open number: DOC ends with '}'
+    {   // a run of 16 or more digits lies inside some (previous chunk, this chunk) window
+        unsigned long long x = ((unsigned long long)dg << 32) | p_dg;
+        x &= x >> 1; x &= x >> 2; x &= x >> 4; x &= x >> 8;
+        if (__any_sync(0xffffffffu, x != 0ull)) return 0;
+    }
+    const uint32_t head_bits = (p_dg >> 31) ? (dg & ~(dg + 1u)) : 0u;   // my leading digits belong to the previous lane's number
+    const uint32_t lo_in = vs < base ? 0xFFFFFFFFu : (vs - base >= 31u ? 0u : (0xFFFFFFFFu << (vs - base + 1u)));      // pos > vs
+    const uint32_t hi_in = ve >= base + 32u ? 0xFFFFFFFFu : (ve <= base ? 0u : ((1u << (ve - base)) - 1u));             // pos < ve
+    const uint32_t mine_dg = dg & ~head_bits & lo_in & hi_in;           // digits of numbers that start here and lie in the array
+    const uint32_t ends = mine_dg & ~(mine_dg >> 1) & 0x7FFFFFFFu;     // last digit of a number, bit 31 excluded (finished below)
+    unsigned long long sum = 0, val = 0;
     #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFu;
-        if ((dg >> j) & 1u) { val = val * 10ull + c; ++rl; }
-        else if (rl) {
-            toolong |= rl > 15u;
-            const uint32_t pos = base + (uint32_t)j - 1u;               // the number's last digit
-            if (head) { head_val = val; head_len = rl; head = false; }
-            else if (pos > vs && pos < ve) sum += val;
-            val = 0; rl = 0;
-        }
+        val = ((mine_dg >> j) & 1u) ? val * 10ull + c : 0ull;
+        if ((ends >> j) & 1u) sum += val;
     }
-    // a number still open at the end of my chunk is finished by the next lane (DOC ends with '}': that lane exists)
-    const bool open_tail = rl != 0u;
-    if (open_tail && head) toolong = 1u;                                // 32 digits in a row
-    const unsigned long long tv = __shfl_up_sync(0xffffffffu, open_tail ? val : 0ull, 1);
-    const uint32_t tl = __shfl_up_sync(0xffffffffu, open_tail ? rl : 0u, 1);
-    if (lane && (p_dg >> 31)) {
-        // the previous lane's last byte is a digit: its number ends with my first head_len digits (possibly none)
-        toolong |= tl + head_len > 15u;
-        const unsigned long long full = tv * pow10[min(head_len, 15u)] + head_val;
-        if (base - 1u > vs && base - 1u < ve) sum += full;
+    // val != 0 or not, bit 31 tells whether a number is still open; its remaining digits are the next lane's leading ones
+    const uint32_t open = mine_dg >> 31;
+    const uint32_t more = open ? (uint32_t)__ffs((int)~n_dg) - 1u : 0u; // <= 15 (checked above); n_dg all ones cannot happen
+    uint32_t nw[4];
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) nw[i] = __shfl_down_sync(0xffffffffu, w[i], 1);
+    #pragma unroll
+    for (int j = 0; j < 15; ++j) {
+        const uint32_t c = (nw[j >> 2] >> (8 * (j & 3))) & 0xFu;
+        if ((uint32_t)j < more) val = val * 10ull + c;
     }
-    if (__any_sync(0xffffffffu, toolong != 0u)) return 0;
+    if (open) sum += val;
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
     *sum_out = sum;
@@ -870,7 +915,6 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
     __shared__ uint32_t s_crc_table[HANDLER == 1 ? 256 : 1];
     __shared__ __align__(128) uint8_t s_b64[HANDLER == 2 ? 320 : 4];
     __shared__ __align__(128) uint8_t s_jcls[HANDLER == 3 ? 256 : 4];
-    __shared__ unsigned long long s_pow10[HANDLER == 3 ? 16 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* const wbase = d3_smem + (size_t)warp * warp_stride;
     D3Warp<T>& W = *reinterpret_cast<D3Warp<T>*>(wbase);
@@ -880,7 +924,6 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
     if (HANDLER == 1) { for (int i = threadIdx.x; i < 256; i += D3_WARPS * 32) s_crc_table[i] = crc_table_entry(i); __syncthreads(); }
     if (HANDLER == 3) {
         for (int i = threadIdx.x; i < 256; i += D3_WARPS * 32) s_jcls[i] = json_cls_of((uint32_t)i);
-        if (threadIdx.x < 16) { unsigned long long pw = 1; for (int i = 0; i < (int)threadIdx.x; ++i) pw *= 10ull; s_pow10[threadIdx.x] = pw; }
         __syncthreads();
     }
     if (HANDLER == 2) {
@@ -962,18 +1005,20 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             // crc32: the whole warp works on one task at a time (tasks are long and of very different lengths)
             for (uint32_t kt = 0; kt < nt; ++kt) {
                 if (!((ready_mask_t >> kt) & 1u)) continue;
-                if (staged) crc_task_coop(sbuf + W.soff[kt], W.len[kt], lane, lane == (int)kt, s_crc_table, a.crc_shift_tabs, rec);
-                else        crc_task_coop(a.payload + W.goff[kt], W.len[kt], lane, lane == (int)kt, s_crc_table, a.crc_shift_tabs, rec);
+                const uint8_t* tp = staged ? (const uint8_t*)(sbuf + W.soff[kt]) : stage_one_task(a.payload, W.goff[kt], W.len[kt], sbuf, in_cap, lane);
+                if (tp) crc_task_coop(tp, true, W.len[kt], lane, lane == (int)kt, s_crc_table, a.crc_shift_tabs, rec);
+                else    crc_task_coop(a.payload + W.goff[kt], false, W.len[kt], lane, lane == (int)kt, s_crc_table, a.crc_shift_tabs, rec);
             }
         } else if (HANDLER == 3) {
             // json_sum: the whole warp parses one document at a time
             for (uint32_t kt = 0; kt < nt; ++kt) {
                 if (!((ready_mask_t >> kt) & 1u)) continue;
                 int done = 0; unsigned long long sum = 0;
-                if (staged) done = json_sum_coop(sbuf + W.soff[kt], W.len[kt], lane, s_jcls, s_pow10, &sum);
+                const uint8_t* tp = staged ? (const uint8_t*)(sbuf + W.soff[kt]) : stage_one_task(a.payload, W.goff[kt], W.len[kt], sbuf, in_cap, lane);
+                if (tp) done = json_sum_coop(tp, W.len[kt], lane, s_jcls, &sum);
                 if (lane == (int)kt) {
                     if (done) { if (sum) { rec.value = (long long)sum; rec.out_len = dec_len_u64(sum); rec.mode = OM_I64_DEC; rec.has = 1; } }
-                    else d2_parse_and_size<3>(staged ? (const uint8_t*)(sbuf + W.soff[kt]) : a.payload + W.goff[kt], W.len[kt], rec, nullptr);
+                    else d2_parse_and_size<3>(tp ? tp : a.payload + W.goff[kt], W.len[kt], rec, nullptr);
                 }
             }
         } else if (mine) {

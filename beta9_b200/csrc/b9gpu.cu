@@ -501,8 +501,13 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
         // second kernel: the tasks the main identity kernel deferred (escaped strings, foreign framing, ...)
         static int slow_per_sm = 0;
         if (!slow_per_sm) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slow_per_sm, drain_slow_kernel, DS_WARPS * 32, 0) != cudaSuccess || slow_per_sm < 1) slow_per_sm = 4; }
-        drain_slow_kernel<<<c->sm_count * slow_per_sm, DS_WARPS * 32, 0, s>>>(a);
-        le = cudaGetLastError();
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(c->sm_count * slow_per_sm)); cfg.blockDim = dim3(DS_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        le = cudaLaunchKernelEx(&cfg, drain_slow_kernel, a);
+        if (le == cudaSuccess) le = cudaGetLastError();
         if (le != cudaSuccess) return fail(B9_EIO, "drain_slow_kernel launch failed: %s", cudaGetErrorString(le));
         c->stats.kernel_launches++;
     }

@@ -174,10 +174,17 @@ __device__ __forceinline__ void group_copy(uint8_t* __restrict__ dst, const uint
 // ------------------------------------------------------------------ chunk-parallel string transcoding
 // body = the bytes between the frame's quotes. A "unit" is what Go's unquote consumes at once: a
 // plain byte, an escape, a \uXXXX (with its low surrogate partner), a UTF-8 sequence.
+// four hex digits -> their value, or -1; all four bytes at once (no per-digit branch: the callers sit in
+// code that runs one lane per escape)
 __device__ __forceinline__ int hex4(const uint8_t* __restrict__ b) {
-    int h0 = hexval(b[0]), h1 = hexval(b[1]), h2 = hexval(b[2]), h3 = hexval(b[3]);
-    if ((h0 | h1 | h2 | h3) < 0) return -1;
-    return (h0 << 12) | (h1 << 8) | (h2 << 4) | h3;
+    const uint32_t w = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+    const uint32_t H = 0x80808080u;
+    const uint32_t x = w & 0x7F7F7F7Fu, y = x | 0x20202020u;
+    const uint32_t isd = ((x + 0x50505050u) & ~(x + 0x46464646u)) & H;    // '0' <= x <= '9'
+    const uint32_t isl = ((y + 0x1F1F1F1Fu) & ~(y + 0x19191919u)) & H;    // 'a' <= (x | 0x20) <= 'f'
+    if ((isd | isl) != H || (w & H)) return -1;
+    const uint32_t nib = (x & 0x0F0F0F0Fu) + (isl >> 7) * 9u;
+    return (int)(((nib & 0xFu) << 12) | (((nib >> 8) & 0xFu) << 8) | (((nib >> 16) & 0xFu) << 4) | (nib >> 24));
 }
 __device__ __forceinline__ uint32_t bs_run_before(const uint8_t* __restrict__ b, uint32_t q) {   // backslashes ending at q-1
     uint32_t r = 0;
@@ -1077,6 +1084,9 @@ constexpr uint32_t DS_STAGE = 4096;          // payloads up to this size are pul
 __global__ void __launch_bounds__(DS_WARPS * 32) drain_slow_kernel(DrainArgs a) {
     __shared__ __align__(16) uint8_t s_stage[DS_WARPS][DS_STAGE + 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // launched with programmatic stream serialization: the grid is set up while the main kernel drains its
+    // last tiles; nothing of the main kernel's output is read before this returns
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t n_slow = a.ctl->n_slow;
     for (;;) {
         uint32_t i = 0;

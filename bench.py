@@ -152,11 +152,30 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _own_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything else a library prints there (NCCL's
+    version banner, for one) is sent to stderr by pointing fd 1 at fd 2 for the lifetime of the run."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     args = parse_args()
+    _own_stdout()
     if args.impl == "reference":
         return run_reference(args)
     rank, local_rank, world = dist_env()
@@ -351,7 +370,7 @@ def main():
             "rebalance": rebalance_info,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     for p in [x for t in pins for x in t] + [o_ids, o_st, o_has, o_off, o_len, o_pl]:
         p.free()
     dq.close()

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <deque>
 #include <mutex>
 #include <new>
@@ -775,17 +776,22 @@ int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
     void* comm = nullptr;
     NC(g_nccl.CommInitRank(&comm, world, id, rank));
     c->nccl_comm = comm; c->comm_rank = rank; c->comm_world = world;
-    // NCCL sets its point-to-point channels up lazily, on the first send/recv of every pair (seconds on an
-    // 8-GPU box): do that here, once, with a 16-byte all-to-all, so that b9_rebalance is never the first user
+    // NCCL sets its point-to-point channels up lazily, on the first send/recv of every pair and of every
+    // channel a message is spread over (seconds on an 8-GPU box): do that here, once, with an all-to-all
+    // large enough to touch all of them (B9_COMM_WARMUP_BYTES per peer, default 4 MiB), plus the
+    // all-gather b9_rebalance opens with, so that the first real exchange finds everything connected
     if (world > 1) {
+        size_t per = 4u << 20;
+        if (const char* e = getenv("B9_COMM_WARMUP_BYTES")) per = (size_t)std::max<long long>(16, atoll(e));
         uint8_t* d = nullptr;
-        CU(cudaMalloc(&d, (size_t)world * 32));
-        CU(cudaMemsetAsync(d, 0, (size_t)world * 32, c->stream));
+        CU(cudaMalloc(&d, (size_t)world * per * 2));
+        CU(cudaMemsetAsync(d, 0, (size_t)world * per * 2, c->stream));
+        NC(g_nccl.AllGather(d, d + per, 16, NCCL_U64, comm, c->stream));      // (world * 128 bytes <= per)
         NC(g_nccl.GroupStart());
         for (int p = 0; p < world; ++p) {
             if (p == rank) continue;
-            NC(g_nccl.Send(d + (size_t)p * 32, 16, NCCL_U8, p, comm, c->stream));
-            NC(g_nccl.Recv(d + (size_t)p * 32 + 16, 16, NCCL_U8, p, comm, c->stream));
+            NC(g_nccl.Send(d + (size_t)p * per * 2, per, NCCL_U8, p, comm, c->stream));
+            NC(g_nccl.Recv(d + (size_t)p * per * 2 + per, per, NCCL_U8, p, comm, c->stream));
         }
         NC(g_nccl.GroupEnd());
         CU(cudaStreamSynchronize(c->stream));
@@ -805,6 +811,15 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     CU(cudaSetDevice(c->device));
     const int W = c->comm_world, R = c->comm_rank;
     cudaStream_t s = c->stream;
+    static const bool trace = getenv("B9_REBALANCE_TRACE") != nullptr;       // phase wall times on stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto phase = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b9_rebalance rank %d] %-28s %8.3f ms\n", R, what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(s, sg.ready, 0));
     c->have_results = false;
     free_segments(c);
@@ -822,6 +837,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         if (prefix[n] != c->pending_bytes) return fail(B9_EIO, "b9_rebalance: ring bookkeeping inconsistent (%llu vs %llu bytes)",
                                                        (unsigned long long)prefix[n], (unsigned long long)c->pending_bytes);
     }
+    phase("slot words D2H + prefix");
     // ---- 1. all-gather (count, bytes)
     uint64_t* d_tab = nullptr; uint64_t* h_tab = nullptr;
     const size_t tab_words = (size_t)W * 2 + (size_t)W * W * 2;
@@ -835,6 +851,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     CU(cudaStreamSynchronize(s));
     std::vector<uint64_t> counts(W), bytes(W), lo(W), hi(W);
     for (int r = 0; r < W; ++r) { counts[r] = h_tab[2 + 2 * r]; bytes[r] = h_tab[3 + 2 * r]; }
+    phase("all-gather counts");
     // ---- 2. plan
     if (b9_plan_ranges((uint32_t)W, (uint32_t)R, counts.data(), bytes.data(), prefix.data(), n, lo.data(), hi.data()))
         return fail(B9_EIO, "b9_rebalance: plan failed");
@@ -849,6 +866,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     CU(cudaStreamSynchronize(s));
     auto M_tasks = [&](int src, int dst) { return mat[((size_t)src * W + dst) * 2]; };
     auto M_bytes = [&](int src, int dst) { return mat[((size_t)src * W + dst) * 2 + 1]; };
+    phase("plan + all-gather matrix");
     // ---- 4. pack what leaves, allocate what arrives
     std::vector<uint8_t*> s_meta(W, nullptr), s_pay(W, nullptr), r_meta(W, nullptr), r_pay(W, nullptr);
     uint64_t sent_tasks = 0, sent_bytes = 0, recv_tasks = 0, recv_bytes = 0;
@@ -880,6 +898,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     // capacity for what arrives (after what leaves is dropped)
     if (n - sent_tasks + recv_tasks > c->ring_tasks)
         return fail(B9_ENOSPC, "b9_rebalance: %llu incoming tasks do not fit the slot ring", (unsigned long long)recv_tasks);
+    phase("alloc + pack");
     // ---- 5. the exchange: one grouped send/recv
     NC(g_nccl.GroupStart());
     for (int d = 0; d < W; ++d) {
@@ -898,6 +917,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     }
     NC(g_nccl.GroupEnd());
     CU(cudaStreamSynchronize(s));
+    phase("grouped send/recv");
     // ---- 6. what left: a prefix of my FIFO went to lower ranks, a suffix to higher ranks
     {
         const uint64_t front = lo[R], back = n - hi[R];
@@ -932,6 +952,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         c->write_pos = start + ((pb + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
         c->tail_task += rk; c->pending_bytes += pb;
     }
+    phase("drop + append received");
     // ---- 8. cancelled tasks may have moved either way: recount over the new window
     {
         const uint64_t depth = c->tail_task - c->head_task;
@@ -941,6 +962,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         CU(cudaStreamSynchronize(s));
         c->cancelled_pending = *c->h_count;
     }
+    phase("recount cancelled");
     if (info) {
         info->world = (uint32_t)W; info->rank = (uint32_t)R;
         info->tasks_before = n; info->bytes_before = prefix[n];

@@ -176,6 +176,15 @@ template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes,
     const uint32_t ctas_needed = (a.n_tiles + D3_WARPS - 1) / D3_WARPS;
     const int grid = (int)std::min<uint32_t>(ctas_needed, (uint32_t)(per_sm * sm_count));
     *grid_out = grid;
+    // identity with nothing cancelled in the window has a uniform tile cost (its expensive tasks are deferred):
+    // all but the last round of a worker's tiles are assigned statically, measured 0.1915 -> 0.182 ms; the same
+    // switch made vadd_f32 slower (0.196 -> 0.212 ms), so it stays on pure work stealing like crc32 / json_sum.
+    // B9_STATIC_ROUNDS=0 turns it off.
+    static const bool allow_static = !(getenv("B9_STATIC_ROUNDS") && atoi(getenv("B9_STATIC_ROUNDS")) == 0);
+    if (allow_static && H == B9_H_IDENTITY && !a.count_mode) {
+        const uint64_t rounds = a.n_tiles / ((uint64_t)grid * D3_WARPS);
+        a.static_rounds = rounds > 1 ? (uint32_t)(rounds - 1) : 0u;
+    }
     drain3_kernel<H><<<grid, D3_WARPS * 32, smem, s>>>(a, in_cap, stride);
     return cudaGetLastError();
 }
@@ -475,6 +484,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.handler = handler;
     a.count_mode = c->cancelled_pending ? 1u : 0u;
     a.slow = c->d_slow; a.crc_shift_tabs = c->d_crc_shift;
+    a.static_rounds = 0;
     cudaStream_t s = c->stream;
     const bool v2 = c->drain_version == 2;
     if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;     // upper bound over the handlers' warp-tile sizes (state array memset)

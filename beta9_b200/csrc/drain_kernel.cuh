@@ -76,6 +76,7 @@ struct DrainArgs {
     uint32_t count_mode;            // v2: 0 = no pending task is cancelled (record index = task index), 1 = chain the ready counts
     SlowItem* slow;                 // v2 identity: [n_tasks] work list for the second kernel
     const uint32_t* crc_shift_tabs; // v2 crc32: [levels][4][256] "advance the CRC register over 2^k zero bytes" tables
+    uint32_t static_rounds;         // v2: a worker's first static_rounds tiles are worker + q * workers, the rest come from the ticket counter
 };
 
 // what phase A leaves for phase B, per task of the tile

@@ -458,8 +458,10 @@ __device__ __forceinline__ bool crc_scan_coop(LD ld, const uint8_t* __restrict__
             const uint32_t simple = bs & ((e == '"') | (e == '\\') | (e == '/'));
             const uint32_t plain = (c - 0x20u < 0x5Fu) & (c != '"') & (bs ^ 1u);
             if (plain | simple) {
+                const uint32_t e2 = ld(i + 2u);                            // (unconditional: cheaper than a branch; <= n + 1, inside the frame suffix)
                 r = crc_step(r, simple ? e : c, tab_s); ++dec;
-                if (simple) { i += 2u; c = ld(i); } else { i += 1u; c = e; }   // the look-ahead byte is the next byte
+                c = simple ? e2 : e;                                       // the look-ahead byte is the next byte
+                i += 1u + simple;
                 continue;
             }
             uint32_t ii = i;                                               // (by reference: keep the loop counter in a register)
@@ -501,7 +503,9 @@ __device__ __forceinline__ void crc_task_coop(const uint8_t* __restrict__ p, boo
     uint32_t crc = 0; bool done = false;
     if (framed) {
         const uint8_t* body = p + FRAME_PRE_LEN;
-        const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN, tab_s = smem_u32(crc_table);
+        const uint32_t n = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
+        uint32_t tab_s = smem_u32(crc_table);
+        asm volatile("mov.u32 %0, %0;" : "+r"(tab_s));                     // keep the address in a register (ptxas re-derives it per use otherwise)
         if (in_smem) { LdShared ld; ld.base = smem_u32(body); done = crc_scan_coop(ld, body, n, lane, tab_s, shift_tabs, &crc); }
         else         { LdGeneric ld; ld.p = body;             done = crc_scan_coop(ld, body, n, lane, tab_s, shift_tabs, &crc); }
     }

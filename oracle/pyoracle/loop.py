@@ -12,8 +12,11 @@ Restates, per task and strictly in the reference's order (SURVE
   result   sdk/src/beta9/runner/taskqueue.py:378              serialize_result(result) if result else None
            sdk/src/beta9/runner/common.py:484-489             json.dumps(result).encode("utf-8")
 
-The Python halves call the very same stdlib functions the reference calls (exact). The Go halves
-are restated in gojson.py/wire.py (PARITY UNPINNED, see those headers). Redis, Postgres, gRPC and
+The Python halves call the very same stdlib functions the reference calls, and are PINNED against
+the reference's own code: tests/golden/make_ref_runner_golden.py runs the unmodified
+TaskQueueWorker.process_tasks / FunctionHandler / serialize_result / _CallableWrapper.put over the
+golden wire records and tests/test_oracle_vs_ref_runner.py compares this module with what they did.
+The Go halves are restated in gojson.py/wire.py (PARITY UNPINNED, see those headers). Redis, Postgres, gRPC and
 the object store are omitted: they move bytes, they do not change them.
 """
 from __future__ import annotations

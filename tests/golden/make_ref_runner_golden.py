@@ -180,5 +180,56 @@ def main():
     print(path, n, "task executions through the reference runner")
 
 
+def fuzz(n_payloads: int, seed: int) -> int:
+    """Live check (no files written): random SDK-style payloads -> the oracle's wire records -> the
+    reference runner; every status / result must equal the oracle's. Returns the number of mismatches."""
+    import random
+    rt, rc = load_reference_runner()
+    from oracle.pyoracle import loop
+    rnd = random.Random(seed)
+    alphabet = ["a", "Z", "0", " ", '"', "\\", "/", "<", ">", "&", "\n", "\t", "\x01", "\x7f", "\u00e9", "\u2028", "\u20ac",
+                "\U0001f600", "\ud83d", "\udc00", "values", "=", "+"]
+
+    def rstr():
+        return "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 12)))
+
+    def rval(depth=0):
+        k = rnd.randint(0, 9 if depth < 2 else 5)
+        if k == 0: return None
+        if k == 1: return rnd.choice([True, False])
+        if k == 2: return rnd.randint(-10**rnd.randint(0, 17), 10**rnd.randint(0, 17))
+        if k == 3: return rnd.choice([0.0, 0.5, -1.25, 1e21, 1e-7, 3.14159, 2.0**60, 123456789.125])
+        if k in (4, 5): return rstr()
+        if k in (6, 7): return [rval(depth + 1) for _ in range(rnd.randint(0, 4))]
+        return {rstr(): rval(depth + 1) for _ in range(rnd.randint(0, 3))}
+
+    payloads = []
+    for i in range(n_payloads):
+        shape = rnd.randint(0, 5)
+        if shape == 0: args, kwargs = (rstr(),), {}
+        elif shape == 1: args, kwargs = ({"values": [rnd.randint(0, 10**6) for _ in range(rnd.randint(0, 6))], "id": i},), {}
+        elif shape == 2:
+            raw = bytes(rnd.randrange(256) for _ in range(8 * rnd.randint(0, 4)))
+            args, kwargs = (base64.b64encode(raw).decode(),), {}
+        elif shape == 3: args, kwargs = tuple(rval() for _ in range(rnd.randint(0, 3))), {}
+        else: args, kwargs = tuple(rval() for _ in range(rnd.randint(0, 2))), {rstr(): rval() for _ in range(rnd.randint(0, 2))}
+        payloads.append(loop.sdk_put_payload(*args, **kwargs))
+    ids = [rnd.randbytes(16) for _ in payloads]
+    bad = 0
+    for h in HANDLERS:
+        want = loop.run_task_loop(payloads, ids, h, keep_wire=True)
+        live = [w for w in want if w.wire is not None]
+        done = run_reference_worker(rt, rc, h, [w.wire for w in live])
+        assert len(done) == len(live)
+        for w, (task_id, status, result) in zip(live, done):
+            if w.status != str(status) or w.result != result:
+                bad += 1
+                sys.stderr.write(f"MISMATCH handler={h} wire={w.wire[:200]!r} oracle=({w.status},{w.result!r}) reference=({status},{result!r})\n")
+    print(f"fuzz: {n_payloads} payloads x {len(HANDLERS)} handlers through the reference runner, {bad} mismatches")
+    return bad
+
+
 if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--fuzz":
+        sys.exit(1 if fuzz(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0xB9) else 0)
     main()

@@ -69,3 +69,16 @@ def test_put_payload_equals_the_reference_sdks(goldens):
             assert loop.sdk_put_payload(*d["args"], **d["kwargs"]) == base64.b64decode(b64)
             n += 1
     assert n >= 100
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/sdk/src"), reason="the reference checkout is not mounted here")
+def test_live_fuzz_against_the_reference_runner():
+    """Where /root/reference exists (this container, not the GPU box): 1200 random SDK-style payloads
+    x 4 handlers through the reference's runner loop, in a subprocess (the harness sets a runner
+    container's environment variables), every completion compared with the oracle."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_ref_runner_golden.py"), "--fuzz", "1200", "20260921"],
+                       capture_output=True, text=True, timeout=600, cwd=os.path.dirname(HERE))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "0 mismatches" in r.stdout

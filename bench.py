@@ -104,6 +104,38 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Run this rank on the CPUs next to its GPU (NVML's ideal affinity), BEFORE any pinned buffer is
+    allocated: page-locked memory lands on the allocating thread's NUMA node, and a host<->device copy
+    that crosses sockets is slower — it matters for the end-to-end number when 8 ranks share one host."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus near gpu {local_rank}"
+    except Exception as e:                      # no NVML / no permission: keep the inherited affinity
+        return f"unchanged ({type(e).__name__})"
+    return "unchanged"
+
+
+def ncu_traffic(args, n_tasks):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this workload's drain kernel(s), from the
+    committed ncu capture of the same command (profiles/ncu_traffic.json, written from
+    scripts/gpu_profile_final.sh's reports). null when no capture of exactly this workload is committed."""
+    try:
+        table = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        return None
+    key = f"{args.handler}:{n_tasks}:{args.chars}:{args.adversarial}" if args.handler == "identity" else f"{args.handler}:{n_tasks}"
+    e = table.get(key)
+    return None if e is None else e.get("dram_bytes")
+
+
 def workload(args, rank):
     from beta9_b200 import synth
     n = args.tasks
@@ -183,6 +215,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the b200 arm has no CPU path")
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: inherited"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -358,9 +391,10 @@ def main():
                                     if args.handler == "identity" else f"{args.handler}: {n} tasks per GPU, {in_bytes / n:.0f} payload bytes per task on average, resident in HBM"),
                        "handler": args.handler, "tasks_per_gpu": n,
                        "parallelism": (f"shard{world}" + ("+nccl_rebalance" if rebalance else "")) if world > 1 else "single",
+                       "cpu_affinity": affinity,
                        "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": f"b9::drain3_kernel<{args.handler}>" + (" + drain_slow_kernel" if args.handler == "identity" else ""),
+                         "traffic": ncu_traffic(args, n), "kernel": f"b9::drain3_kernel<{args.handler}>" + (" + drain_slow_kernel" if args.handler == "identity" else ""),
                          "kernel_ms": k_ms, "algorithmic_bytes_per_task": algo / n, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "tasks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -654,154 +654,208 @@ __device__ __forceinline__ uint8_t json_cls_of(uint32_t c) {
 }
 __device__ __forceinline__ uint32_t prefix_xor32(uint32_t x) { x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; return x; }
 __device__ __forceinline__ uint32_t lane_prev(uint32_t m, int lane) { const uint32_t v = __shfl_up_sync(0xffffffffu, m, 1); return lane ? v : 0u; }
+// the mask of the lane below; lane 0 gets `carry` (the last lane's mask of the previous segment). Every lane executes the shuffle.
+__device__ __forceinline__ uint32_t lane_prev_carry(uint32_t m, int lane, uint32_t carry) { const uint32_t v = __shfl_up_sync(0xffffffffu, m, 1); return lane ? v : carry; }
 // parity of `bit` over the lanes below this one
 __device__ __forceinline__ uint32_t parity_below(bool bit, int lane) { return __popc(__ballot_sync(0xffffffffu, bit) & ((1u << lane) - 1u)) & 1u; }
 
-constexpr uint32_t JSON_COOP_MAX_DOC = 1024;
+constexpr uint32_t JSON_COOP_MAX_SEG = 4;                              // segments of 32 lanes x 32 bytes
+constexpr uint32_t JSON_COOP_MAX_DOC = 1024 * JSON_COOP_MAX_SEG;
 constexpr uint32_t JSON_PRE_LEN = FRAME_PRE_LEN - 1, JSON_SUF_LEN = FRAME_SUF_LEN - 1;     // the frame without the string quotes
 
-// 1 = decided (*sum_out valid, task COMPLETE), 0 = not decided
+// 32 bytes at q (any alignment) as eight little-endian words; reads up to 7 bytes past them
+__device__ __forceinline__ void json_load32(const uint8_t* __restrict__ q, uint32_t w[8]) {
+    const uint32_t mis = (uint32_t)((uintptr_t)q & 3u);
+    const uint32_t* qa = (const uint32_t*)(q - mis);
+    uint32_t t[9];
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) t[i] = qa[i];
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = __funnelshift_r(t[i], t[i + 1], 8u * mis);
+}
+__device__ __forceinline__ uint32_t sel4(uint32_t i, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) { return i == 0 ? a0 : i == 1 ? a1 : i == 2 ? a2 : a3; }
+
+// 1 = decided (*sum_out valid, task COMPLETE), 0 = not decided. MULTI = false is the instance for documents of
+// one segment (<= 1 KiB, the configuration's shape): no carries, and the words stay in registers for the second pass.
+template <bool MULTI>
 __device__ __forceinline__ int json_sum_coop(const uint8_t* __restrict__ p, uint32_t len, int lane, const uint8_t* cls_tab,
                                              unsigned long long* sum_out) {
-    if (len < JSON_PRE_LEN + JSON_SUF_LEN + 2u || len - JSON_PRE_LEN - JSON_SUF_LEN > JSON_COOP_MAX_DOC) return 0;
+    if (len < JSON_PRE_LEN + JSON_SUF_LEN + 2u || len - JSON_PRE_LEN - JSON_SUF_LEN > (MULTI ? JSON_COOP_MAX_DOC : 1024u)) return 0;
     bool okb = true;
     if (lane < (int)JSON_PRE_LEN) okb = p[lane] == FRAME_PRE[lane];
     else if (lane < (int)(JSON_PRE_LEN + JSON_SUF_LEN)) okb = p[len - JSON_SUF_LEN + (lane - JSON_PRE_LEN)] == FRAME_SUF[1 + lane - JSON_PRE_LEN];
     if (!__all_sync(0xffffffffu, okb)) return 0;
     const uint8_t* const D = p + JSON_PRE_LEN;
     const uint32_t n = len - JSON_PRE_LEN - JSON_SUF_LEN;
-    const uint32_t base = 32u * (uint32_t)lane;
-    const uint32_t cnt = base < n ? min(32u, n - base) : 0u;
-    const uint32_t inr = cnt == 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
-
-    // ---- 1. my 32 bytes -> class planes
-    uint32_t w[8];
-    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    if (cnt) {
-        const uint8_t* q = D + base;
-        const uint32_t mis = (uint32_t)((uintptr_t)q & 3u);
-        const uint32_t* qa = (const uint32_t*)(q - mis);
-        uint32_t t[9];
-        #pragma unroll
-        for (int i = 0; i < 9; ++i) t[i] = qa[i];                      // up to 3 + 4 bytes past my chunk: frame suffix / stage slack
-        #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = __funnelshift_r(t[i], t[i + 1], 8u * mis);
-        #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t cls = cls_tab[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu];
-            b0 = __funnelshift_r(b0, cls, 1); b1 = __funnelshift_r(b1, cls >> 1, 1);
-            b2 = __funnelshift_r(b2, cls >> 2, 1); b3 = __funnelshift_r(b3, cls >> 3, 1);
-        }
-        b0 &= inr; b1 &= inr; b2 &= inr; b3 &= inr;
-    } else {
-        #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = 0;
-    }
-    const uint32_t Q = ~b3 & ~b2 & ~b1 & b0, DG9 = ~b3 & ~b2 & b1 & ~b0, CM = ~b3 & ~b2 & b1 & b0, CL = ~b3 & b2 & ~b1 & ~b0;
-    const uint32_t SP = ~b3 & b2 & ~b1 & b0, OB = ~b3 & b2 & b1 & ~b0, CB = ~b3 & b2 & b1 & b0, LB = b3 & ~b2 & ~b1 & ~b0;
-    const uint32_t RB = b3 & ~b2 & ~b1 & b0, OTH = b3 & ~b2 & b1 & ~b0, ZR = b3 & ~b2 & b1 & b0, BAD = b3 & b2;
-    uint32_t v = BAD;                                                   // violations, any lane, any bit
-
-    // ---- 2. strings / arrays / object-level separators
-    const uint32_t qinc = prefix_xor32(Q) ^ (parity_below(__popc(Q) & 1u, lane) ? 0xFFFFFFFFu : 0u);   // quotes in [0, i], parity
-    const uint32_t OPENQ = Q & qinc, CLOSEQ = Q & ~qinc;
-    const uint32_t out = ~(qinc & ~Q) & inr;                            // not string content
-    v |= OTH & out;
-    const uint32_t dg = (DG9 | ZR) & out, zr = ZR & out, cm = CM & out, cl = CL & out, sp = SP & out;
-    const uint32_t ob = OB & out, cb = CB & out, lb = LB & out, rb = RB & out;
-    const uint32_t br = ob | cb;
-    const uint32_t binc = prefix_xor32(br) ^ (parity_below(__popc(br) & 1u, lane) ? 0xFFFFFFFFu : 0u);
-    v |= (ob & ~binc) | (cb & binc);                                    // '[' opens at depth 0 only, ']' closes
-    const uint32_t arr = binc & ~ob & inr;                              // strictly inside an array
-    v |= cl & arr;
-    const uint32_t sep = (cm | cl) & ~arr;
-    const uint32_t sinc = prefix_xor32(sep) ^ (parity_below(__popc(sep) & 1u, lane) ? 0xFFFFFFFFu : 0u);
-    v |= (cl & ~sinc) | (cm & ~arr & sinc);                             // object level: ':' ',' ':' ',' ... ':'
-    const uint32_t quotes_odd = __popc(__ballot_sync(0xffffffffu, __popc(Q) & 1u)) & 1u;
-    const uint32_t br_odd = __popc(__ballot_sync(0xffffffffu, __popc(br) & 1u)) & 1u;
-    const uint32_t sep_odd = __popc(__ballot_sync(0xffffffffu, __popc(sep) & 1u)) & 1u;
-
-    // ---- 3. the grammar, each byte against its predecessor (one optional space after ',' ':')
-    const uint32_t p_closeq = lane_prev(CLOSEQ, lane), p_openq = lane_prev(OPENQ, lane), p_dg = lane_prev(dg, lane), p_zr = lane_prev(zr, lane);
-    const uint32_t p_cm = lane_prev(cm, lane), p_cl = lane_prev(cl, lane), p_sp = lane_prev(sp, lane);
-    const uint32_t p_ob = lane_prev(ob, lane), p_cb = lane_prev(cb, lane);
+    const uint32_t nseg = MULTI ? (n + 1023u) >> 10 : 1u;
+    const uint32_t last = n - 1u;
+    uint32_t wk[8];                                                     // !MULTI: my chunk's words, kept for the second pass
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) wk[i] = 0;
     #define B9_P1(M, PM) (((M) << 1) | ((PM) >> 31))
     #define B9_P2(M, PM) (((M) << 2) | ((PM) >> 30))
-    const uint32_t a_closeq = B9_P1(CLOSEQ, p_closeq), a_dg = B9_P1(dg, p_dg), a_cm = B9_P1(cm, p_cm), a_cl = B9_P1(cl, p_cl);
-    const uint32_t a_sp = B9_P1(sp, p_sp), a_ob = B9_P1(ob, p_ob), a_cb = B9_P1(cb, p_cb), a_zr = B9_P1(zr, p_zr);
-    const uint32_t a_lb = (lb << 1);                                    // '{' is byte 0 (checked below): never a lane's last byte... unless n == 1
-    const uint32_t t_cm = a_cm | (a_sp & B9_P2(cm, p_cm)), t_cl = a_cl | (a_sp & B9_P2(cl, p_cl));   // previous token, through the space
-    const uint32_t ds = dg & ~a_dg;                                     // first digit of a number
-    v |= sp & ~(a_cm | a_cl);
-    v |= a_closeq & inr & ~(cl | cm | rb);
-    v |= a_dg & inr & ~dg & ~(cm | cb | rb);
-    v |= a_cb & inr & ~(cm | rb);
-    v |= dg & a_zr & ~B9_P2(dg, p_dg);                                  // a digit after a leading zero
-    v |= OPENQ & (arr | ~(a_lb | t_cm | t_cl));
-    v |= cl & ~a_closeq;
-    v |= cm & ~arr & ~(a_closeq | a_dg | a_cb);
-    v |= cm & arr & ~a_dg;
-    v |= ob & ~t_cl;
-    v |= cb & ~(a_ob | a_dg);
-    v |= ds & ((arr & ~(a_ob | t_cm)) | (~arr & ~t_cl));
-    v |= lb ^ (lane == 0 ? 1u : 0u);                                    // exactly one '{', at byte 0
-    const uint32_t last = n - 1u;
-    const uint32_t lastbit = (last >> 5) == (uint32_t)lane ? (1u << (last & 31u)) : 0u;
-    v |= rb ^ lastbit;                                                  // exactly one '}', at byte n-1
-    v |= rb & ~(a_lb | a_closeq | a_dg | a_cb);
-    if (rb && !(rb & a_lb) && !sep_odd) v |= 1u;                        // a non-empty object ends after "key": value
-    if (__any_sync(0xffffffffu, v != 0u) || quotes_odd || br_odd) return 0;
 
-    // ---- 4a. the last `"values":` key: ':' at J, '"' at J-1 and J-8
-    uint32_t cand = cl & a_closeq & ((OPENQ << 8) | (p_openq >> 24));
+    // state carried from one 1 KiB segment to the next (the same in every lane)
+    uint32_t c_quote = 0, c_br = 0, c_sep = 0;                          // parities so far
+    uint32_t l_closeq = 0, l_openq = 0, l_dg = 0, l_zr = 0, l_cm = 0, l_cl = 0, l_sp = 0, l_ob = 0, l_cb = 0;   // lane 31's masks of the previous segment
+    uint32_t dg0 = 0, dg1 = 0, dg2 = 0, dg3 = 0, cb0 = 0, cb1 = 0, cb2 = 0, cb3 = 0;   // per segment, for the second pass
+    uint32_t v = 0;                                                     // violations, any lane, any bit
     int bestJ = -1;
-    while (cand) {
-        const int j = 31 - __clz(cand);
-        const uint8_t* k = D + base + j - 7;
-        if (k[0] == 'v' && k[1] == 'a' && k[2] == 'l' && k[3] == 'u' && k[4] == 'e' && k[5] == 's') { bestJ = (int)base + j; break; }
-        cand &= ~(1u << j);
+
+    for (uint32_t seg = 0; seg < nseg; ++seg) {
+        const uint32_t base = (seg << 10) + 32u * (uint32_t)lane;       // my chunk's first byte in the document
+        const uint32_t cnt = base < n ? min(32u, n - base) : 0u;
+        const uint32_t inr = cnt == 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+        // ---- 1. my 32 bytes -> class planes
+        uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        if (cnt) {
+            uint32_t w[8];
+            json_load32(D + base, w);                                   // (over-read: frame suffix / stage slack)
+            if (!MULTI) {
+                #pragma unroll
+                for (int i = 0; i < 8; ++i) wk[i] = w[i];
+            }
+            #pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t cls = cls_tab[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu];
+                b0 = __funnelshift_r(b0, cls, 1); b1 = __funnelshift_r(b1, cls >> 1, 1);
+                b2 = __funnelshift_r(b2, cls >> 2, 1); b3 = __funnelshift_r(b3, cls >> 3, 1);
+            }
+            b0 &= inr; b1 &= inr; b2 &= inr; b3 &= inr;
+        }
+        const uint32_t Q = ~b3 & ~b2 & ~b1 & b0, DG9 = ~b3 & ~b2 & b1 & ~b0, CM = ~b3 & ~b2 & b1 & b0, CL = ~b3 & b2 & ~b1 & ~b0;
+        const uint32_t SP = ~b3 & b2 & ~b1 & b0, OB = ~b3 & b2 & b1 & ~b0, CB = ~b3 & b2 & b1 & b0, LB = b3 & ~b2 & ~b1 & ~b0;
+        const uint32_t RB = b3 & ~b2 & ~b1 & b0, OTH = b3 & ~b2 & b1 & ~b0, ZR = b3 & ~b2 & b1 & b0, BAD = b3 & b2;
+        v |= BAD;
+
+        // ---- 2. strings / arrays / object-level separators
+        const uint32_t qinc = prefix_xor32(Q) ^ ((parity_below(__popc(Q) & 1u, lane) ^ c_quote) ? 0xFFFFFFFFu : 0u);   // quotes in [0, i], parity
+        const uint32_t OPENQ = Q & qinc, CLOSEQ = Q & ~qinc;
+        const uint32_t out = ~(qinc & ~Q) & inr;                        // not string content
+        v |= OTH & out;
+        const uint32_t dg = (DG9 | ZR) & out, zr = ZR & out, cm = CM & out, cl = CL & out, sp = SP & out;
+        const uint32_t ob = OB & out, cb = CB & out, lb = LB & out, rb = RB & out;
+        const uint32_t br = ob | cb;
+        const uint32_t binc = prefix_xor32(br) ^ ((parity_below(__popc(br) & 1u, lane) ^ c_br) ? 0xFFFFFFFFu : 0u);
+        v |= (ob & ~binc) | (cb & binc);                                // '[' opens at depth 0 only, ']' closes
+        const uint32_t arr = binc & ~ob & inr;                          // strictly inside an array
+        v |= cl & arr;
+        const uint32_t sep = (cm | cl) & ~arr;
+        const uint32_t sinc = prefix_xor32(sep) ^ ((parity_below(__popc(sep) & 1u, lane) ^ c_sep) ? 0xFFFFFFFFu : 0u);
+        v |= (cl & ~sinc) | (cm & ~arr & sinc);                         // object level: ':' ',' ':' ',' ... ':'
+        c_quote ^= __popc(__ballot_sync(0xffffffffu, __popc(Q) & 1u)) & 1u;
+        c_br ^= __popc(__ballot_sync(0xffffffffu, __popc(br) & 1u)) & 1u;
+        c_sep ^= __popc(__ballot_sync(0xffffffffu, __popc(sep) & 1u)) & 1u;
+
+        // ---- 3. the grammar, each byte against its predecessor (one optional space after ',' ':')
+        #define B9_PREV(M, LM) lane_prev_carry((M), lane, (LM))
+        const uint32_t p_closeq = B9_PREV(CLOSEQ, l_closeq), p_openq = B9_PREV(OPENQ, l_openq), p_dg = B9_PREV(dg, l_dg), p_zr = B9_PREV(zr, l_zr);
+        const uint32_t p_cm = B9_PREV(cm, l_cm), p_cl = B9_PREV(cl, l_cl), p_sp = B9_PREV(sp, l_sp);
+        const uint32_t p_ob = B9_PREV(ob, l_ob), p_cb = B9_PREV(cb, l_cb);
+        #undef B9_PREV
+        const uint32_t a_closeq = B9_P1(CLOSEQ, p_closeq), a_dg = B9_P1(dg, p_dg), a_cm = B9_P1(cm, p_cm), a_cl = B9_P1(cl, p_cl);
+        const uint32_t a_sp = B9_P1(sp, p_sp), a_ob = B9_P1(ob, p_ob), a_cb = B9_P1(cb, p_cb), a_zr = B9_P1(zr, p_zr);
+        const uint32_t a_lb = (lb << 1);                                // '{' is byte 0 (checked below): never a chunk's last byte
+        const uint32_t t_cm = a_cm | (a_sp & B9_P2(cm, p_cm)), t_cl = a_cl | (a_sp & B9_P2(cl, p_cl));   // previous token, through the space
+        const uint32_t ds = dg & ~a_dg;                                 // first digit of a number
+        v |= sp & ~(a_cm | a_cl);
+        v |= a_closeq & inr & ~(cl | cm | rb);
+        v |= a_dg & inr & ~dg & ~(cm | cb | rb);
+        v |= a_cb & inr & ~(cm | rb);
+        v |= dg & a_zr & ~B9_P2(dg, p_dg);                              // a digit after a leading zero
+        v |= OPENQ & (arr | ~(a_lb | t_cm | t_cl));
+        v |= cl & ~a_closeq;
+        v |= cm & ~arr & ~(a_closeq | a_dg | a_cb);
+        v |= cm & arr & ~a_dg;
+        v |= ob & ~t_cl;
+        v |= cb & ~(a_ob | a_dg);
+        v |= ds & ((arr & ~(a_ob | t_cm)) | (~arr & ~t_cl));
+        v |= lb ^ (base == 0u ? 1u : 0u);                               // exactly one '{', at byte 0
+        const uint32_t lastbit = (last >= base && last < base + 32u) ? (1u << (last - base)) : 0u;
+        v |= rb ^ lastbit;                                              // exactly one '}', at byte n-1
+        v |= rb & ~(a_lb | a_closeq | a_dg | a_cb);
+        if (rb && !(rb & a_lb) && !c_sep) v |= 1u;                      // a non-empty object ends after "key": value
+        {   // a run of 16 or more digits lies inside some (previous chunk, this chunk) window
+            unsigned long long x = ((unsigned long long)dg << 32) | p_dg;
+            x &= x >> 1; x &= x >> 2; x &= x >> 4; x &= x >> 8;
+            v |= x != 0ull ? 1u : 0u;
+        }
+        // ---- 4a. the last `"values":` key so far: ':' at J, '"' at J-1 and J-8
+        uint32_t cand = cl & a_closeq & ((OPENQ << 8) | (p_openq >> 24));
+        while (cand) {
+            const int j = 31 - __clz(cand);
+            const uint8_t* k = D + base + j - 7;
+            if (k[0] == 'v' && k[1] == 'a' && k[2] == 'l' && k[3] == 'u' && k[4] == 'e' && k[5] == 's') { bestJ = max(bestJ, (int)base + j); break; }
+            cand &= ~(1u << j);
+        }
+        if (seg == 0) { dg0 = dg; cb0 = cb; } else if (seg == 1) { dg1 = dg; cb1 = cb; } else if (seg == 2) { dg2 = dg; cb2 = cb; } else { dg3 = dg; cb3 = cb; }
+        l_closeq = __shfl_sync(0xffffffffu, CLOSEQ, 31); l_openq = __shfl_sync(0xffffffffu, OPENQ, 31); l_dg = __shfl_sync(0xffffffffu, dg, 31);
+        l_zr = __shfl_sync(0xffffffffu, zr, 31); l_cm = __shfl_sync(0xffffffffu, cm, 31); l_cl = __shfl_sync(0xffffffffu, cl, 31);
+        l_sp = __shfl_sync(0xffffffffu, sp, 31); l_ob = __shfl_sync(0xffffffffu, ob, 31); l_cb = __shfl_sync(0xffffffffu, cb, 31);
     }
+    if (__any_sync(0xffffffffu, v != 0u) || c_quote || c_br) return 0;
     bestJ = __reduce_max_sync(0xffffffffu, bestJ);
     if (bestJ < 0) return 0;                                            // KeyError is the sequential path's to report
     uint32_t vs = (uint32_t)bestJ + 1u;
     if (D[vs] == ' ') ++vs;
     if (D[vs] != '[') return 0;                                         // sum() of a non-list
-    const uint32_t after = vs >= base + 32u ? 0u : (vs < base ? 0xFFFFFFFFu : (vs - base == 31u ? 0u : (0xFFFFFFFFu << (vs - base + 1u))));
-    const uint32_t cb_after = cb & after;
-    const uint32_t ve = __reduce_min_sync(0xffffffffu, cb_after ? base + (uint32_t)(__ffs(cb_after) - 1) : 0xFFFFFFFFu);
+    uint32_t ve = 0xFFFFFFFFu;
+    for (uint32_t seg = 0; seg < nseg; ++seg) {
+        const uint32_t base = (seg << 10) + 32u * (uint32_t)lane;
+        const uint32_t after = vs >= base + 32u ? 0u : (vs < base ? 0xFFFFFFFFu : (vs - base == 31u ? 0u : (0xFFFFFFFFu << (vs - base + 1u))));
+        const uint32_t cb_after = (MULTI ? sel4(seg, cb0, cb1, cb2, cb3) : cb0) & after;
+        if (cb_after) ve = min(ve, base + (uint32_t)(__ffs(cb_after) - 1));
+    }
+    ve = __reduce_min_sync(0xffffffffu, ve);
 
     // ---- 4b. Horner over the numbers that START in my chunk (a number cut by the chunk end is finished from
-    // the next lane's words); no data-dependent branch: run ends, the span and my head digits are masks
-    const uint32_t n_dg = __shfl_down_sync(0xffffffffu, dg, 1);        // lane 31 never has an open number: DOC ends with '}'
-    {   // a run of 16 or more digits lies inside some (previous chunk, this chunk) window
-        unsigned long long x = ((unsigned long long)dg << 32) | p_dg;
-        x &= x >> 1; x &= x >> 2; x &= x >> 4; x &= x >> 8;
-        if (__any_sync(0xffffffffu, x != 0ull)) return 0;
+    // the next chunk's words); no data-dependent branch: run ends, the span and my head digits are masks
+    unsigned long long sum = 0;
+    for (uint32_t seg = 0; seg < nseg; ++seg) {
+        const uint32_t base = (seg << 10) + 32u * (uint32_t)lane;
+        const uint32_t dg = MULTI ? sel4(seg, dg0, dg1, dg2, dg3) : dg0;
+        // neighbours' digit masks: the previous chunk (last lane of the previous segment for lane 0), the next chunk
+        const uint32_t up = __shfl_up_sync(0xffffffffu, dg, 1), dn = __shfl_down_sync(0xffffffffu, dg, 1);
+        const uint32_t prev_last = (MULTI && seg) ? __shfl_sync(0xffffffffu, sel4(seg - 1u, dg0, dg1, dg2, dg3), 31) : 0u;
+        const uint32_t next_first = (MULTI && seg + 1u < nseg) ? __shfl_sync(0xffffffffu, sel4(seg + 1u, dg0, dg1, dg2, dg3), 0) : 0u;
+        const uint32_t p_dg = lane ? up : prev_last, n_dg = lane < 31 ? dn : next_first;
+        if (MULTI && !__any_sync(0xffffffffu, dg != 0u)) continue;
+        uint32_t w[8];
+        if (MULTI && dg) json_load32(D + base, w);
+        else {
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = MULTI ? 0u : wk[i];
+        }
+        const uint32_t head_bits = (p_dg >> 31) ? (dg & ~(dg + 1u)) : 0u;   // my leading digits belong to the previous chunk's number
+        const uint32_t lo_in = vs < base ? 0xFFFFFFFFu : (vs - base >= 31u ? 0u : (0xFFFFFFFFu << (vs - base + 1u)));      // pos > vs
+        const uint32_t hi_in = ve >= base + 32u ? 0xFFFFFFFFu : (ve <= base ? 0u : ((1u << (ve - base)) - 1u));             // pos < ve
+        const uint32_t mine_dg = dg & ~head_bits & lo_in & hi_in;       // digits of numbers that start here and lie in the array
+        const uint32_t ends = mine_dg & ~(mine_dg >> 1) & 0x7FFFFFFFu; // last digit of a number, bit 31 excluded (finished below)
+        unsigned long long val = 0;
+        #pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFu;
+            val = ((mine_dg >> j) & 1u) ? val * 10ull + c : 0ull;
+            if ((ends >> j) & 1u) sum += val;
+        }
+        // bit 31 tells whether a number is still open; its remaining digits are the next chunk's leading ones
+        const uint32_t open = mine_dg >> 31;
+        const uint32_t more = open ? (uint32_t)__ffs((int)~n_dg) - 1u : 0u;     // <= 15 (checked above)
+        uint32_t nw[4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) nw[i] = __shfl_down_sync(0xffffffffu, w[i], 1);
+        if (MULTI && lane == 31 && open) {                              // the next chunk is the next segment's first one
+            const uint8_t* q = D + base + 32u;
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) nw[i] = (uint32_t)q[4 * i] | ((uint32_t)q[4 * i + 1] << 8) | ((uint32_t)q[4 * i + 2] << 16) | ((uint32_t)q[4 * i + 3] << 24);
+        }
+        #pragma unroll
+        for (int j = 0; j < 15; ++j) {
+            const uint32_t c = (nw[j >> 2] >> (8 * (j & 3))) & 0xFu;
+            if ((uint32_t)j < more) val = val * 10ull + c;
+        }
+        if (open) sum += val;
     }
-    const uint32_t head_bits = (p_dg >> 31) ? (dg & ~(dg + 1u)) : 0u;   // my leading digits belong to the previous lane's number
-    const uint32_t lo_in = vs < base ? 0xFFFFFFFFu : (vs - base >= 31u ? 0u : (0xFFFFFFFFu << (vs - base + 1u)));      // pos > vs
-    const uint32_t hi_in = ve >= base + 32u ? 0xFFFFFFFFu : (ve <= base ? 0u : ((1u << (ve - base)) - 1u));             // pos < ve
-    const uint32_t mine_dg = dg & ~head_bits & lo_in & hi_in;           // digits of numbers that start here and lie in the array
-    const uint32_t ends = mine_dg & ~(mine_dg >> 1) & 0x7FFFFFFFu;     // last digit of a number, bit 31 excluded (finished below)
-    unsigned long long sum = 0, val = 0;
-    #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFu;
-        val = ((mine_dg >> j) & 1u) ? val * 10ull + c : 0ull;
-        if ((ends >> j) & 1u) sum += val;
-    }
-    // val != 0 or not, bit 31 tells whether a number is still open; its remaining digits are the next lane's leading ones
-    const uint32_t open = mine_dg >> 31;
-    const uint32_t more = open ? (uint32_t)__ffs((int)~n_dg) - 1u : 0u; // <= 15 (checked above); n_dg all ones cannot happen
-    uint32_t nw[4];
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) nw[i] = __shfl_down_sync(0xffffffffu, w[i], 1);
-    #pragma unroll
-    for (int j = 0; j < 15; ++j) {
-        const uint32_t c = (nw[j >> 2] >> (8 * (j & 3))) & 0xFu;
-        if ((uint32_t)j < more) val = val * 10ull + c;
-    }
-    if (open) sum += val;
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
     *sum_out = sum;
@@ -1040,7 +1094,10 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                 if (!((ready_mask_t >> kt) & 1u)) continue;
                 int done = 0; unsigned long long sum = 0;
                 const uint8_t* tp = staged ? (const uint8_t*)(sbuf + W.soff[kt]) : stage_one_task(a.payload, W.goff[kt], W.len[kt], sbuf, in_cap, lane);
-                if (tp) done = json_sum_coop(tp, W.len[kt], lane, s_jcls, &sum);
+                if (tp) {                                                  // one 1 KiB segment (configs[4]) or up to four
+                    if (W.len[kt] <= 1024u + JSON_PRE_LEN + JSON_SUF_LEN) done = json_sum_coop<false>(tp, W.len[kt], lane, s_jcls, &sum);
+                    else done = json_sum_coop<true>(tp, W.len[kt], lane, s_jcls, &sum);
+                }
                 if (lane == (int)kt) {
                     if (done) { if (sum) { rec.value = (long long)sum; rec.out_len = dec_len_u64(sum); rec.mode = OM_I64_DEC; rec.has = 1; } }
                     else d2_parse_and_size<3>(tp ? tp : a.payload + W.goff[kt], W.len[kt], rec, nullptr);

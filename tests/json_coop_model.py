@@ -7,7 +7,7 @@ from __future__ import annotations
 
 PRE = b'{"args": ['
 SUF = b'], "kwargs": {}}'
-MAX_DOC = 1024
+MAX_DOC = 4096
 
 
 def _prefix_xor(m: int, n: int) -> int:

@@ -175,13 +175,17 @@ def test_json_sum_fast_path_boundaries_and_mutants(dq):
     """The warp-cooperative parser: numbers straddling every 32-byte lane boundary, documents around
     the 1 KiB limit, both separator styles, and single-character mutants of canonical documents."""
     import json
-    from tests.test_json_coop_model import _payloads
+    from tests.test_json_coop_model import _large_payloads, _payloads
     rng = np.random.default_rng(0xB9 + 7)
-    payloads = _payloads(rng, 800)
+    payloads = _payloads(rng, 800) + _large_payloads(rng, 400)
     for shift in range(0, 70):                     # slide a run of 15-digit and short numbers across the lane boundaries
         d = {"p": "x" * shift, "values": [999999999999999, 7, 123456789012345, 0, 10, 100000000000000] * 3, "q": 5}
         payloads.append(json.dumps({"args": [d], "kwargs": {}}).encode())
-    for size in (900, 1000, 1023, 1024, 1025, 1100, 2048, 5000):      # around JSON_COOP_MAX_DOC
+    for shift in range(940, 1080, 3):              # ... and across the 1 KiB segment boundary of longer documents
+        d = {"p": "x" * shift, "values": [999999999999999, 7, 123456789012345, 0, 10, 100000000000000] * 3, "q": "]", "values2": [1]}
+        payloads.append(json.dumps({"args": [d], "kwargs": {}}).encode())
+    n_canonical = 70 + len(range(940, 1080, 3)) + 14
+    for size in (900, 1000, 1023, 1024, 1025, 1100, 2047, 2048, 2049, 3000, 4095, 4096, 4097, 5000):      # around the segment and JSON_COOP_MAX_DOC limits
         vals = rng.integers(0, 10**6, size=60).tolist()
         d = {"id": size, "values": vals, "pad": ""}
         d["pad"] = "y" * max(0, size - len(json.dumps(d)))
@@ -193,7 +197,7 @@ def test_json_sum_fast_path_boundaries_and_mutants(dq):
     for i in np.flatnonzero(r.status == 4):        # declined only where the oracle's domain ends too, or on exotic numbers
         assert o.status[i] in (0, 3, 4), payloads[i]
     # the canonical documents must not be declined
-    assert int((r.status[-78:] == 4).sum()) == 0
+    assert int((r.status[-n_canonical:] == 4).sum()) == 0
 
 
 def test_wrong_handler_for_payload(dq):

@@ -26,6 +26,33 @@ def _canonical_docs(rng, k):
     return docs
 
 
+def _large_payloads(rng, k):
+    """Documents of 1-4 KiB (several 1 KiB segments on the device) and single-character mutants of them."""
+    out = []
+    for i in range(k):
+        nvals = int(rng.integers(20, 400))
+        vals = rng.integers(0, 10**int(rng.integers(1, 16)), size=nvals).tolist()
+        pad = "z" * int(rng.integers(0, 1500))
+        order = i % 3
+        if order == 0: d = {"pad": pad, "values": vals, "id": i}
+        elif order == 1: d = {"values": vals, "pad": pad, "tail": [1, 2, 3]}
+        else: d = {"a": [7] * int(rng.integers(0, 200)), "pad": pad, "values": vals}
+        p = bytearray(b'{"args": [' + json.dumps(d).encode() + b'], "kwargs": {}}')
+        if len(p) > 4200:
+            continue
+        out.append(bytes(p))
+        for _ in range(4):
+            m = bytearray(p)
+            pos = int(rng.integers(10, len(m) - 16))
+            op = int(rng.integers(0, 3))
+            ch = int(rng.choice(STRUCT))
+            if op == 0: m[pos] = ch
+            elif op == 1: del m[pos]
+            else: m[pos:pos] = bytes([ch])
+            out.append(bytes(m))
+    return out
+
+
 def _payloads(rng, k):
     out = []
     for d in _canonical_docs(rng, k):
@@ -54,7 +81,7 @@ def _payloads(rng, k):
 
 def test_model_decisions_agree_with_oracle():
     rng = np.random.default_rng(0xB9)
-    payloads = _payloads(rng, 1500)
+    payloads = _payloads(rng, 1500) + _large_payloads(rng, 250)
     b = synth.from_payloads(payloads)
     o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "json_sum", nthreads=8)
     decided = 0

@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--handler", default="identity")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cancelled", type=float, default=0.0, help="fraction of the resident tasks pushed with B9_TF_CANCELLED (the drain compacts them away: look-back path)")
     ap.add_argument("--skew", type=float, default=0.0, help="N>1: rank 0 pushes (1+skew)x the tasks and every step starts with the NCCL rebalance")
     ap.add_argument("--adversarial", type=float, default=0.01, help="share of tasks whose string needs escaping (SURVEY.md §8d: 1 %%)")
     return ap.parse_args()
@@ -215,7 +216,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the b200 arm has no CPU path")
     torch.cuda.set_device(local_rank)
-    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: inherited"
+    affinity = (bind_to_gpu_numa_node(local_rank) if world > 1 and not os.environ.get("B9_BENCH_NO_AFFINITY")
+                else "inherited")
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -257,7 +259,13 @@ def main():
         return float(t.item())
 
     # ------------------------------------------------------------------ device-resident steps
-    dq.push_batch(batch.task_ids, batch.payload, batch.offsets)
+    n_cancelled = 0
+    if args.cancelled > 0:
+        fl = (np.random.default_rng(5 + rank).random(batch.n) < args.cancelled).astype(np.uint8)
+        n_cancelled = int(fl.sum())
+        dq.push_batch(batch.task_ids, batch.payload, batch.offsets, flags=fl)
+    else:
+        dq.push_batch(batch.task_ids, batch.payload, batch.offsets)
     rebalance_info = None
     n_pushed = n
     if rebalance:
@@ -280,13 +288,18 @@ def main():
     sampler.start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        got = dq.drain_launch(args.handler, n, peek=True)
-        kernel_ms.append(dq.stats().last_drain_kernel_ms)
+        # B9_DRAIN_ASYNC: the K steps are enqueued back to back, as a host that pipelines its drains would;
+        # the barrier below (stream sync on every rank) closes the timed region
+        got = dq.drain_launch(args.handler, n, peek=True, wait=False)
+    dq.sync()
     barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop()
     launches = dq.stats().kernel_launches - launches0
     assert got == n, (got, n)
+    for _ in range(min(args.steps, 5)):             # per-step kernel time (CUDA events around one step's kernels), outside the timed region
+        dq.drain_launch(args.handler, n, peek=True)
+        kernel_ms.append(dq.stats().last_drain_kernel_ms)
     out_bytes = int(dq.stats().last_drain_out_bytes)
     elapsed = reduce_max(t1 - t0)
     value = n_total * args.steps / elapsed
@@ -294,7 +307,8 @@ def main():
     # drop the resident batch
     dq.drain_launch(args.handler, n, peek=False)
     res = dq.fetch()
-    assert res.n == n and dq.depth() == 0
+    assert res.n == n - (n_cancelled if not rebalance else 0) or rebalance, (res.n, n, n_cancelled)
+    assert dq.depth() == 0
     if rebalance:
         # the end-to-end leg below runs the un-skewed shard shape (the exchange is timed above)
         res_n_after = n
@@ -316,7 +330,7 @@ def main():
         pi.array[:] = batch.task_ids.reshape(-1); pp.array[:] = batch.payload
         po.view(np.uint64, n + 1)[:] = batch.offsets
         pins.append((pi, pp, po))
-    cap_bytes = out_bytes + 4096
+    cap_bytes = out_bytes + 4096 if not n_cancelled else max(out_bytes, int(in_bytes * 1.1)) + 4096     # (the e2e leg pushes every task live)
     o_ids = dq.pinned(n * 16); o_st = dq.pinned(n); o_has = dq.pinned(n); o_off = dq.pinned(n * 8); o_len = dq.pinned(n * 4); o_pl = dq.pinned(cap_bytes)
     resbuf = L.Results(o_ids.ptr, o_st.ptr, o_has.ptr, o_off.ptr, o_len.ptr, o_pl.ptr, n, cap_bytes, 0, 0, 0, 0)
     lib = L.load()
@@ -391,7 +405,7 @@ def main():
                                     if args.handler == "identity" else f"{args.handler}: {n} tasks per GPU, {in_bytes / n:.0f} payload bytes per task on average, resident in HBM"),
                        "handler": args.handler, "tasks_per_gpu": n,
                        "parallelism": (f"shard{world}" + ("+nccl_rebalance" if rebalance else "")) if world > 1 else "single",
-                       "cpu_affinity": affinity,
+                       "cpu_affinity": affinity, "cancelled_tasks_per_gpu": n_cancelled,
                        "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args, n), "kernel": f"b9::drain3_kernel<{args.handler}>" + (" + drain_slow_kernel" if args.handler == "identity" else ""),

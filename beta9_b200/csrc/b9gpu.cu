@@ -94,7 +94,11 @@ struct b9_ctx {
     uint32_t* d_crc_shift = nullptr;            // crc32: zero-byte shift tables
     uint64_t cancelled_pending = 0;            // pending tasks carrying B9_TF_CANCELLED (pushed so, or expired)
     DrainCtl* d_ctl = nullptr; uint64_t* d_tile_state = nullptr;
+    bool res_async = false;                    // the last launch returned before its kernels finished: finalize on fetch / sync
+    uint32_t res_async_n = 0; uint64_t res_async_in_bytes = 0; bool res_async_v2 = true;
     DrainCtl* h_ctl = nullptr;                 // pinned
+    uint8_t* d_xchg_send = nullptr; uint8_t* d_xchg_recv = nullptr; uint64_t xchg_send_cap = 0, xchg_recv_cap = 0;   // b9_rebalance staging, grow-only
+    uint64_t* h_scratch = nullptr; size_t h_scratch_words = 0;   // pinned, grown on demand (b9_rebalance's slot words + byte prefix)
     unsigned long long* d_count = nullptr; unsigned long long* h_count = nullptr;
     // results waiting on the device for b9_drain_fetch
     bool have_results = false, res_peek = false;
@@ -311,6 +315,8 @@ void b9_ctx_destroy(b9_ctx* c) {
     cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len); cudaFree(c->d_slow); cudaFree(c->d_wire_env); cudaFree(c->d_crc_shift);
     cudaFree(c->d_ctl); cudaFree(c->d_tile_state); cudaFree(c->d_count);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    cudaFree(c->d_xchg_send); cudaFree(c->d_xchg_recv);
     if (c->h_count) cudaFreeHost(c->h_count);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -450,6 +456,26 @@ int64_t b9_expire(b9_ctx* c, int64_t now_unix_ns) {
     return (int64_t)*c->h_count;
 }
 
+// Waits for the last launch and publishes its outcome (records, bytes, overflow) to the ctx. Caller holds c->mu.
+static int finish_launch(b9_ctx* c) {
+    if (!c->res_async) return B9_OK;
+    c->res_async = false;
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+    c->stats.last_drain_kernel_ms = ms;
+    if (c->h_ctl->overflow)
+        return fail(B9_ENOSPC, "b9_drain_launch: results exceed max_result_bytes (%llu); drain fewer tasks or enlarge the staging",
+                    (unsigned long long)c->max_result_bytes);
+    if (c->res_async_v2) { c->res_bytes = c->h_ctl->bytes; c->res_n = c->h_ctl->total_cnt; }
+    else { c->res_bytes = c->h_ctl->total >> 24; c->res_n = (uint32_t)(c->h_ctl->total & 0xFFFFFFu); }
+    c->res_popped = c->res_async_n;
+    c->res_in_bytes = c->res_async_in_bytes;
+    c->have_results = true;
+    c->stats.last_drain_in_bytes = c->res_async_in_bytes;
+    c->stats.last_drain_out_bytes = c->res_bytes;
+    return B9_OK;
+}
+
 int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     if (!c) return fail(B9_EINVAL, "b9_drain_launch: ctx is NULL");
     if (handler < 0 || handler >= B9_H_COUNT_) return fail(B9_ENOSYS, "b9_drain_launch: unknown handler %d", handler);
@@ -457,10 +483,11 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     CU(cudaSetDevice(c->device));
     // results of an earlier launch that were never fetched are dropped; their tasks are still
     // pending (a pop is committed by a successful fetch, never by a launch)
-    c->have_results = false;
+    c->have_results = false; c->res_async = false;
     const uint64_t depth = c->tail_task - c->head_task;
     const uint32_t n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
-    c->res_n = 0; c->res_popped = 0; c->res_bytes = 0; c->res_in_bytes = 0; c->res_peek = peek != 0;
+    c->res_n = 0; c->res_popped = 0; c->res_bytes = 0; c->res_in_bytes = 0; c->res_peek = (peek & B9_DRAIN_PEEK) != 0;
+    c->res_async = false;
     if (n == 0) { c->have_results = true; return 0; }
     // payload bytes of the window
     uint64_t in_bytes = 0;
@@ -489,7 +516,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     const bool v2 = c->drain_version == 2;
     if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;     // upper bound over the handlers' warp-tile sizes (state array memset)
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
-    CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));
+    if (!v2 || a.count_mode) CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));   // look-back state: v2 only reads it when slots are cancelled
     int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
     CU(cudaEventRecord(c->ev_a, s));
     cudaError_t le;
@@ -524,27 +551,19 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     }
     CU(cudaEventRecord(c->ev_b, s));
     CU(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(DrainCtl), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
-    c->stats.last_drain_kernel_ms = ms;
     c->stats.last_drain_tiles = (n + 127) / 128;   // (reported in units of 128 tasks)
     c->stats.drains++;
-    if (c->h_ctl->overflow)
-        return fail(B9_ENOSPC, "b9_drain_launch: results exceed max_result_bytes (%llu); drain fewer tasks or enlarge the staging",
-                    (unsigned long long)c->max_result_bytes);
-    if (v2) { c->res_bytes = c->h_ctl->bytes; c->res_n = c->h_ctl->total_cnt; }
-    else { c->res_bytes = c->h_ctl->total >> 24; c->res_n = (uint32_t)(c->h_ctl->total & 0xFFFFFFu); }
-    c->res_popped = n;
-    c->res_in_bytes = in_bytes;
-    c->have_results = true;
-    c->stats.last_drain_in_bytes = in_bytes;
-    c->stats.last_drain_out_bytes = c->res_bytes;
-    return (int64_t)c->res_n;
+    c->res_async = true; c->res_async_n = n; c->res_async_in_bytes = in_bytes; c->res_async_v2 = v2;
+    if (peek & B9_DRAIN_ASYNC) return (int64_t)n;  // records = n minus the cancelled slots: known after b9_sync / b9_drain_fetch
+    int rc = finish_launch(c);
+    return rc ? rc : (int64_t)c->res_n;
 }
 
 int64_t b9_drain_fetch(b9_ctx* c, b9_results* out) {
     if (!c || !out) return fail(B9_EINVAL, "b9_drain_fetch: NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    { int rc = finish_launch(c); if (rc) return rc; }
     if (!c->have_results) return fail(B9_EINVAL, "b9_drain_fetch: no drain results are waiting");
     out->n_results = c->res_n; out->n_popped = c->res_popped; out->n_bytes = c->res_bytes; out->need_bytes = c->res_bytes;
     if (c->res_n > out->cap_tasks || c->res_bytes > out->cap_bytes)
@@ -575,7 +594,7 @@ int64_t b9_drain_fetch(b9_ctx* c, b9_results* out) {
         c->cancelled_pending -= std::min<uint64_t>(c->cancelled_pending, (uint64_t)(c->res_popped - c->res_n));
         free_segments(c);
     }
-    c->have_results = false;
+    c->have_results = false; c->res_async = false;
     return (int64_t)n;
 }
 
@@ -618,7 +637,7 @@ int64_t b9_wire_encode(b9_ctx* c, const b9_wire_env* env, uint32_t max_tasks) {
     if (!c || !env || !env->workspace_name || !env->stub_id) return fail(B9_EINVAL, "b9_wire_encode: NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
-    c->have_results = false;
+    c->have_results = false; c->res_async = false;
     const uint64_t depth = c->tail_task - c->head_task;
     const uint32_t n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
     c->res_n = 0; c->res_popped = 0; c->res_bytes = 0; c->res_in_bytes = 0; c->res_peek = true;
@@ -786,6 +805,23 @@ int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
     void* comm = nullptr;
     NC(g_nccl.CommInitRank(&comm, world, id, rank));
     c->nccl_comm = comm; c->comm_rank = rank; c->comm_world = world;
+    // page-locked scratch for b9_rebalance's per-task bookkeeping, sized for a full slot ring, here and not on the first exchange
+    if (world > 1 && c->h_scratch_words < 2 * (size_t)c->ring_tasks + 2) {
+        if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    cudaFree(c->d_xchg_send); cudaFree(c->d_xchg_recv);
+        c->h_scratch = nullptr; c->h_scratch_words = 0;
+        CU(cudaHostAlloc(&c->h_scratch, (2 * (size_t)c->ring_tasks + 2) * sizeof(uint64_t), cudaHostAllocDefault));
+        c->h_scratch_words = 2 * (size_t)c->ring_tasks + 2;
+    }
+    // ... and the two device arenas the exchange stages through (they grow on demand; a first size here keeps
+    // cudaMalloc, milliseconds for hundreds of MB, off the first exchange)
+    if (world > 1) {
+        const uint64_t first = std::min<uint64_t>(c->ring_bytes / 4, 256ull << 20);
+        if (c->xchg_send_cap < first) { cudaFree(c->d_xchg_send); c->d_xchg_send = nullptr; c->xchg_send_cap = 0;
+                                        if (cudaMalloc(&c->d_xchg_send, first) == cudaSuccess) c->xchg_send_cap = first; else cudaGetLastError(); }
+        if (c->xchg_recv_cap < first) { cudaFree(c->d_xchg_recv); c->d_xchg_recv = nullptr; c->xchg_recv_cap = 0;
+                                        if (cudaMalloc(&c->d_xchg_recv, first) == cudaSuccess) c->xchg_recv_cap = first; else cudaGetLastError(); }
+    }
     // NCCL sets its point-to-point channels up lazily, on the first send/recv of every pair and of every
     // channel a message is spread over (seconds on an 8-GPU box): do that here, once, with an all-to-all
     // large enough to touch all of them (B9_COMM_WARMUP_BYTES per peer, default 4 MiB), plus the
@@ -831,17 +867,27 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         t_last = now;
     };
     for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(s, sg.ready, 0));
-    c->have_results = false;
+    c->have_results = false; c->res_async = false;
     free_segments(c);
     const uint64_t n = c->tail_task - c->head_task;
     // byte prefix of my pending tasks (host bookkeeping holds every batch's offsets)
-    std::vector<uint64_t> prefix(n + 1, 0);
+    // (page-locked scratch: the 8 bytes per task travel at PCIe speed in both directions)
+    if (c->h_scratch_words < 2 * n + 2) {
+        if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    cudaFree(c->d_xchg_send); cudaFree(c->d_xchg_recv);
+        c->h_scratch = nullptr; c->h_scratch_words = 0;
+        const size_t want = (size_t)(2 * n + 2) * 5 / 4;
+        CU(cudaHostAlloc(&c->h_scratch, want * sizeof(uint64_t), cudaHostAllocDefault));
+        c->h_scratch_words = want;
+    }
+    uint64_t* const hdrs = c->h_scratch;
+    uint64_t* const prefix = c->h_scratch + n;
+    prefix[0] = 0;
     if (n) {   // lengths come back from the slot ring (the host keeps no per-task index)
-        std::vector<uint64_t> hdrs(n);
         const uint32_t slot0 = (uint32_t)(c->head_task & c->slot_mask);
         const uint64_t first = std::min<uint64_t>(n, c->ring_tasks - slot0);
-        CU(cudaMemcpyAsync(hdrs.data(), c->d_hdr + slot0, first * 8, cudaMemcpyDeviceToHost, s));
-        if (first < n) CU(cudaMemcpyAsync(hdrs.data() + first, c->d_hdr, (n - first) * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(hdrs, c->d_hdr + slot0, first * 8, cudaMemcpyDeviceToHost, s));
+        if (first < n) CU(cudaMemcpyAsync(hdrs + first, c->d_hdr, (n - first) * 8, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         for (uint64_t i = 0; i < n; ++i) prefix[i + 1] = prefix[i] + hdr_len(hdrs[i]);
         if (prefix[n] != c->pending_bytes) return fail(B9_EIO, "b9_rebalance: ring bookkeeping inconsistent (%llu vs %llu bytes)",
@@ -863,7 +909,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     for (int r = 0; r < W; ++r) { counts[r] = h_tab[2 + 2 * r]; bytes[r] = h_tab[3 + 2 * r]; }
     phase("all-gather counts");
     // ---- 2. plan
-    if (b9_plan_ranges((uint32_t)W, (uint32_t)R, counts.data(), bytes.data(), prefix.data(), n, lo.data(), hi.data()))
+    if (b9_plan_ranges((uint32_t)W, (uint32_t)R, counts.data(), bytes.data(), prefix, n, lo.data(), hi.data()))
         return fail(B9_EIO, "b9_rebalance: plan failed");
     // ---- 3. all-gather of the send matrix rows (tasks, bytes per destination)
     uint64_t* row = h_tab;   // reuse
@@ -877,18 +923,40 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     auto M_tasks = [&](int src, int dst) { return mat[((size_t)src * W + dst) * 2]; };
     auto M_bytes = [&](int src, int dst) { return mat[((size_t)src * W + dst) * 2 + 1]; };
     phase("plan + all-gather matrix");
-    // ---- 4. pack what leaves, allocate what arrives
+    // ---- 4. pack what leaves, make room for what arrives (two grow-only device arenas kept in the ctx: a
+    // cudaMalloc per peer and call cost more than the exchange itself)
     std::vector<uint8_t*> s_meta(W, nullptr), s_pay(W, nullptr), r_meta(W, nullptr), r_pay(W, nullptr);
     uint64_t sent_tasks = 0, sent_bytes = 0, recv_tasks = 0, recv_bytes = 0;
+    auto al = [](uint64_t x) { return (x + 255ull) & ~255ull; };
+    uint64_t need_s = 0, need_r = 0;
+    for (int d = 0; d < W; ++d) {
+        if (d == R) continue;
+        const uint64_t k = hi[d] - lo[d];
+        if (k) need_s += al(meta_layout(k).total) + al(prefix[hi[d]] - prefix[lo[d]] + 16);
+        const uint64_t rk = M_tasks(d, R);
+        if (rk) need_r += al(meta_layout(rk).total) + al(M_bytes(d, R) + 16);
+    }
+    auto ensure = [&](uint8_t*& buf, uint64_t& cap, uint64_t need) -> cudaError_t {
+        if (need <= cap) return cudaSuccess;
+        if (buf) cudaFree(buf);
+        buf = nullptr; cap = 0;
+        const uint64_t want = need + need / 4;
+        cudaError_t e = cudaMalloc(&buf, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    };
+    CU(ensure(c->d_xchg_send, c->xchg_send_cap, need_s));
+    CU(ensure(c->d_xchg_recv, c->xchg_recv_cap, need_r));
+    uint64_t so = 0, ro = 0;
     for (int d = 0; d < W; ++d) {
         if (d == R) continue;
         const uint64_t k = hi[d] - lo[d];
         if (k) {
             const MetaLayout ml = meta_layout(k);
             const uint64_t pb = prefix[hi[d]] - prefix[lo[d]];
-            CU(cudaMalloc(&s_meta[d], ml.total)); cl.bufs.push_back(s_meta[d]);
-            CU(cudaMalloc(&s_pay[d], pb + 16)); cl.bufs.push_back(s_pay[d]);
-            CU(cudaMemcpyAsync(s_meta[d] + ml.rel, prefix.data() + lo[d], (k + 1) * 8, cudaMemcpyHostToDevice, s));
+            s_meta[d] = c->d_xchg_send + so; so += al(ml.total);
+            s_pay[d] = c->d_xchg_send + so; so += al(pb + 16);
+            CU(cudaMemcpyAsync(s_meta[d] + ml.rel, prefix + lo[d], (k + 1) * 8, cudaMemcpyHostToDevice, s));
             const uint32_t blocks = (uint32_t)((k * 32 + 255) / 256);
             gather_tasks_kernel<<<blocks, 256, 0, s>>>(c->d_payload, c->d_off, c->d_hdr, c->d_ids, c->d_ts, c->d_exp, c->slot_mask,
                                                        c->head_task + lo[d], (uint32_t)k, (const uint64_t*)(s_meta[d] + ml.rel), s_pay[d],
@@ -900,8 +968,8 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         }
         const uint64_t rk = M_tasks(d, R);
         if (rk) {
-            CU(cudaMalloc(&r_meta[d], meta_layout(rk).total)); cl.bufs.push_back(r_meta[d]);
-            CU(cudaMalloc(&r_pay[d], M_bytes(d, R) + 16)); cl.bufs.push_back(r_pay[d]);
+            r_meta[d] = c->d_xchg_recv + ro; ro += al(meta_layout(rk).total);
+            r_pay[d] = c->d_xchg_recv + ro; ro += al(M_bytes(d, R) + 16);
             recv_tasks += rk; recv_bytes += M_bytes(d, R);
         }
     }
@@ -994,7 +1062,8 @@ int b9_sync(b9_ctx* c) {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream_in));
     CU(cudaStreamSynchronize(c->stream));
-    return B9_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return finish_launch(c);
 }
 
 int b9_task_queue_scale(int64_t queue_length, int64_t tasks_per_container, int64_t max_containers, int64_t max_replicas, int* valid) {

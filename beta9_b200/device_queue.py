@@ -144,10 +144,12 @@ class DeviceQueue:
         n = self._check(self._lib.b9_drain_launch(self._ctx, h, max_tasks, 0))
         return self._fetch(n, cap_bytes)
 
-    def drain_launch(self, handler: str, max_tasks: int = 1 << 22, peek: bool = False) -> int:
-        return self._check(self._lib.b9_drain_launch(self._ctx, HANDLERS[handler], max_tasks, 1 if peek else 0))
+    def drain_launch(self, handler: str, max_tasks: int = 1 << 22, peek: bool = False, wait: bool = True) -> int:
+        """wait=False (B9_DRAIN_ASYNC): returns once the kernels are enqueued; `sync()` or `fetch()` completes it."""
+        return self._check(self._lib.b9_drain_launch(self._ctx, HANDLERS[handler], max_tasks, (1 if peek else 0) | (0 if wait else 2)))
 
     def fetch(self, cap_bytes: Optional[int] = None) -> DrainResult:
+        self.sync()                                  # completes a wait=False launch: its byte count sizes the buffers below
         st = self.stats()
         return self._fetch(None, cap_bytes if cap_bytes is not None else int(st.last_drain_out_bytes))
 

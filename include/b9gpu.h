@@ -182,10 +182,15 @@ int64_t  b9_expire(b9_ctx *ctx, int64_t now_unix_ns);
  * on the device and `b9_drain_fetch` can collect them with larger buffers. */
 int64_t  b9_drain(b9_ctx *ctx, int handler, uint32_t max_tasks, b9_results *out);
 
-/* Two-step form: run the kernel only (results stay in device staging), then fetch. `peek` != 0
- * leaves the tasks in the queue, so the same resident batch can be drained again (used by the
- * benchmark's device-resident timing and by retry-on-device-failure). */
-int64_t  b9_drain_launch(b9_ctx *ctx, int handler, uint32_t max_tasks, int peek);
+/* Two-step form: run the kernel only (results stay in device staging), then fetch. `flags`:
+ * B9_DRAIN_PEEK leaves the tasks in the queue, so the same resident batch can be drained again (the
+ * benchmark's device-resident timing, retry-on-device-failure). B9_DRAIN_ASYNC returns as soon as
+ * the kernels are enqueued, with the number of tasks in the window; the record count, byte count and
+ * a result-staging overflow (B9_ENOSPC) are reported by the next b9_drain_fetch or b9_sync. A host that
+ * pipelines drains (launch k+1 while it post-processes k) keeps the GPU busy back to back this way. */
+#define B9_DRAIN_PEEK  1
+#define B9_DRAIN_ASYNC 2
+int64_t  b9_drain_launch(b9_ctx *ctx, int handler, uint32_t max_tasks, int flags);
 int64_t  b9_drain_fetch(b9_ctx *ctx, b9_results *out);
 
 /* ---- queue wire records ------------------------------------------------------------------------

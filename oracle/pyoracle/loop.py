@@ -28,6 +28,7 @@ from typing import Any, Callable, Iterable, List, Optional, Sequence, Tuple
 
 from .gojson import GoJSONError, go_unmarshal_task_payload
 from .handlers import HANDLERS
+from .httpserialize import InvalidRequestPayload, serialize_http_payload
 from .wire import QueueEnv, build_task_message, format_uuid
 
 # Task status strings, sdk/src/beta9/type.py TaskStatus / pkg/types/backend.go TaskStatus*
@@ -63,8 +64,14 @@ def serialize_result(result: Any) -> Optional[bytes]:
 def run_task_loop(payloads: Sequence[bytes], task_ids: Sequence[bytes],
                   handler: "str | Callable[..., Any]", env: Optional[QueueEnv] = None,
                   now_unix_ns: int = 1_789_970_992_573_161_412,
-                  keep_wire: bool = False) -> List[TaskResult]:
-    """Push the whole batch, then drain it FIFO through one runner (workers=1)."""
+                  keep_wire: bool = False, http_body: bool = False) -> List[TaskResult]:
+    """Push the whole batch, then drain it FIFO through one runner (workers=1).
+
+    http_body=False: `payloads` are TaskQueuePutRequest.payload bytes (the SDK's put), decoded by
+    json.Unmarshal into TaskPayload (taskqueue.go:213-214). http_body=True: they are HTTP request
+    bodies of the task-queue endpoint (taskqueue/http.go:38-78), turned into a TaskPayload by
+    SerializeHttpPayload (pkg/task/serialize.go:16-101; no query string here); a body that is refused
+    ("invalid request payload", HTTP 400) never becomes a task: REJECTED."""
     env = env or QueueEnv()
     fn = HANDLERS[handler] if isinstance(handler, str) else handler
     queue: deque = deque()
@@ -72,8 +79,11 @@ def run_task_loop(payloads: Sequence[bytes], task_ids: Sequence[bytes],
     # ---- producer side: one TaskQueuePut per payload
     for i, (p, tid) in enumerate(zip(payloads, task_ids)):
         try:
-            args, kwargs = go_unmarshal_task_payload(bytes(p))
-        except GoJSONError:
+            if http_body:
+                args, kwargs = serialize_http_payload(bytes(p))
+            else:
+                args, kwargs = go_unmarshal_task_payload(bytes(p))
+        except (GoJSONError, InvalidRequestPayload):
             results[i] = TaskResult(bytes(tid), REJECTED, None)
             continue
         tm = build_task_message(env, format_uuid(tid), args, kwargs, now_unix_ns)

@@ -200,6 +200,21 @@ def test_json_sum_fast_path_boundaries_and_mutants(dq):
     assert int((r.status[-n_canonical:] == 4).sum()) == 0
 
 
+def test_async_launch_then_fetch(dq):
+    """B9_DRAIN_ASYNC: launches return at once; sync / fetch publish the same records a blocking launch gives."""
+    b = synth.strings_batch(50_000, 64, adversarial_frac=0.05, seed=9)
+    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "identity", nthreads=8)
+    dq.push_batch(b.task_ids, b.payload, b.offsets)
+    for _ in range(3):                                           # back to back on the same resident window
+        assert dq.drain_launch("identity", b.n, peek=True, wait=False) == b.n
+    dq.sync()
+    assert dq.depth() == b.n                                     # peeked: still pending
+    assert dq.drain_launch("identity", b.n, peek=False, wait=False) == b.n
+    r = dq.fetch()                                               # completes the launch, then pops
+    assert dq.depth() == 0 and r.n_popped == b.n
+    assert_matches_oracle(b, r, o)
+
+
 def test_wrong_handler_for_payload(dq):
     # every handler over every config's payloads: type errors must come out as ERROR exactly like the oracle
     for b in (synth.strings_batch(2000, 64, adversarial_frac=0.2), synth.vadd_batch(1000), synth.json_batch(200)):

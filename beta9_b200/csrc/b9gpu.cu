@@ -238,7 +238,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     if (c->max_drain_tasks > c->ring_tasks) c->max_drain_tasks = c->ring_tasks;
     c->max_result_bytes = o.max_result_bytes ? o.max_result_bytes : (1ull << 30);
     if (c->max_result_bytes >= (1ull << 38)) c->max_result_bytes = (1ull << 38) - 1;
-    c->max_task_bytes = o.max_task_bytes ? o.max_task_bytes : (1u << 20);
+    c->max_task_bytes = o.max_task_bytes ? std::min<uint32_t>(o.max_task_bytes, (1u << 30) - 1u) : (1u << 20);   // (two bits of a 32-bit length word carry flags)
 
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     int rc_ = fail(e_ == cudaErrorMemoryAllocation ? B9_ENOMEM : B9_EIO, "%s failed: %s", #call, cudaGetErrorString(e_)); \

@@ -489,7 +489,7 @@ __device__ __forceinline__ bool crc_scan_coop(LD ld, const uint8_t* __restrict__
     return true;
 }
 
-template <int HANDLER> __device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, TaskRec& rec, const uint32_t* crc_table);
+template <int HANDLER> __device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, TaskRec& rec, const uint32_t* crc_table, bool http = false);
 // one crc32 task with the whole warp; the owner lane keeps the record. `in_smem`: p points into this warp's stage buffer.
 __device__ __forceinline__ void crc_task_coop(const uint8_t* __restrict__ p, bool in_smem, uint32_t len, int lane, bool owner, const uint32_t* crc_table,
                                               const uint32_t* __restrict__ shift_tabs, TaskRec& rec) {
@@ -890,6 +890,7 @@ struct D3Warp {
     uint64_t goff[T];              // physical ring offset of each task's payload
     uint32_t soff[T];              // offset inside the stage buffer (when staged)
     uint32_t len[T];
+    uint8_t  flg[T];               // slot flags (B9_TF_*)
     uint32_t esc_info[2][32];      // per-lane chunk sizes of up to two escaped strings (phase A -> phase B)
     alignas(8) uint64_t mbar;
 };
@@ -951,25 +952,13 @@ template <int G>
 __device__ __noinline__ void group_copy_generic(uint8_t* dst, const uint8_t* src, uint32_t n, int sub) { group_copy<G>(dst, src, n, sub); }
 
 template <int HANDLER>
-__device__ __forceinline__ void d2_phase_b_task(const uint8_t* __restrict__ p, const TaskRec& rec, uint8_t* __restrict__ o) {
-    if (rec.mode == OM_VADD) vadd_write(p, rec.src_off, rec.src_len, o);
-    else if (rec.mode == OM_U32_DEC || rec.mode == OM_I64_DEC) {
-        long long v = rec.value; uint32_t l = rec.out_len;
-        if (v < 0) { *o++ = '-'; --l; v = -v; }
-        write_dec(o, (unsigned long long)v, l);
-    } else if (rec.mode == OM_STR_ESC) {                          // string the sequential parser sized (non-canonical frame)
-        uint32_t i = rec.src_off + 1, end = rec.src_off + rec.src_len - 1;
-        *o++ = '"';
-        while (i < end) o += py_emit(next_cp(p, i, end), o);
-        *o = '"';
-    }
-}
+__device__ __forceinline__ void d2_phase_b_task(const uint8_t* __restrict__ p, const TaskRec& rec, uint8_t* __restrict__ o) { seq_emit(p, rec, o); }
 
 // the sequential validating parser + handler sizing, out of line: rare for identity, and it keeps the
 // hot loops' registers and instruction-cache footprint small
 template <int HANDLER>
-__device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, TaskRec& rec, const uint32_t* crc_table) {
-    Parsed pr = parse_payload(p, len);
+__device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, TaskRec& rec, const uint32_t* crc_table, bool http) {
+    Parsed pr = parse_payload(p, len, http);
     handler_phase_a(HANDLER, p, pr, rec, crc_table);
 }
 
@@ -1038,7 +1027,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         const uint64_t gs = __shfl_sync(0xffffffffu, m_off, 0);
         const uint64_t ge = __shfl_sync(0xffffffffu, m_end, (int)nt - 1);
         uint32_t staged = 0;
-        if (valid) { W.goff[lane] = m_off; W.len[lane] = m_len; }
+        if (valid) { W.goff[lane] = m_off; W.len[lane] = m_len; W.flg[lane] = (uint8_t)hdr_flags(mregs.hdr); }
         if (contig) {
             const uint64_t as = gs & ~15ull;
             const uint64_t bytes = ((ge + 15ull) & ~15ull) - as;
@@ -1065,6 +1054,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         const uint32_t my_len = mine ? W.len[k] : 0u;
         const uint32_t my_soff = (mine && staged) ? W.soff[k] : 0u;
         const uint64_t my_goff = mine ? W.goff[k] : 0ull;
+        const bool my_http = mine && (W.flg[k] & B9_TF_HTTP_BODY_BIT) != 0;
         TaskRec rec; rec.ready = mine; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
         bool clobbered = false;
         if (HANDLER == 0) {
@@ -1079,11 +1069,16 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                     const uint32_t tok = my_len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
                     if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
                 } else { rec.mode = OM_DEFER; rec.value = (long long)(q & 1u); }
+                if (my_http) { rec.has = 0; rec.out_len = 0; rec.mode = OM_DEFER; rec.value = 0; }   // an HTTP body: the map rules decide (second kernel)
             }
         } else if (HANDLER == 1) {
             // crc32: the whole warp works on one task at a time (tasks are long and of very different lengths)
             for (uint32_t kt = 0; kt < nt; ++kt) {
                 if (!((ready_mask_t >> kt) & 1u)) continue;
+                if (W.flg[kt] & B9_TF_HTTP_BODY_BIT) {                      // an HTTP body: the sequential parser with the map rules
+                    if (lane == (int)kt) d2_parse_and_size<1>(staged ? (const uint8_t*)(sbuf + W.soff[kt]) : a.payload + W.goff[kt], W.len[kt], rec, s_crc_table, true);
+                    continue;
+                }
                 const uint8_t* tp = staged ? (const uint8_t*)(sbuf + W.soff[kt]) : stage_one_task(a.payload, W.goff[kt], W.len[kt], sbuf, in_cap, lane);
                 if (tp) crc_task_coop(tp, true, W.len[kt], lane, lane == (int)kt, s_crc_table, a.crc_shift_tabs, rec);
                 else    crc_task_coop(a.payload + W.goff[kt], false, W.len[kt], lane, lane == (int)kt, s_crc_table, a.crc_shift_tabs, rec);
@@ -1092,6 +1087,10 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             // json_sum: the whole warp parses one document at a time
             for (uint32_t kt = 0; kt < nt; ++kt) {
                 if (!((ready_mask_t >> kt) & 1u)) continue;
+                if (W.flg[kt] & B9_TF_HTTP_BODY_BIT) {
+                    if (lane == (int)kt) d2_parse_and_size<3>(staged ? (const uint8_t*)(sbuf + W.soff[kt]) : a.payload + W.goff[kt], W.len[kt], rec, nullptr, true);
+                    continue;
+                }
                 int done = 0; unsigned long long sum = 0;
                 const uint8_t* tp = staged ? (const uint8_t*)(sbuf + W.soff[kt]) : stage_one_task(a.payload, W.goff[kt], W.len[kt], sbuf, in_cap, lane);
                 if (tp) {                                                  // one 1 KiB segment (configs[4]) or up to four
@@ -1105,11 +1104,11 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             }
         } else if (mine) {
             int fr = 0;
-            if (HANDLER == 2 && staged) fr = vadd_fast(sbuf + my_soff, my_len, s_b64, rec);
+            if (HANDLER == 2 && staged && !my_http) fr = vadd_fast(sbuf + my_soff, my_len, s_b64, rec);
             if (fr != 1) {
                 clobbered = fr == 2;                                       // stage bytes overwritten: read the ring instead
                 const uint8_t* p = (staged && !clobbered) ? (const uint8_t*)(sbuf + my_soff) : a.payload + my_goff;
-                d2_parse_and_size<HANDLER>(p, my_len, rec, s_crc_table);
+                d2_parse_and_size<HANDLER>(p, my_len, rec, s_crc_table, my_http);
             }
         }
 
@@ -1133,7 +1132,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                 const uint32_t j = base_cnt + ex_cnt;
                 a.out_ids[j] = __ldg(a.ids + slot);
                 if (HANDLER == 0 && rec.mode == OM_DEFER) {                // the second kernel writes the rest of the record
-                    SlowItem it; it.goff = my_goff; it.len = my_len | (rec.value ? 0x80000000u : 0u); it.j = j;
+                    SlowItem it; it.goff = my_goff; it.len = my_len | (rec.value ? 0x80000000u : 0u) | (my_http ? 0x40000000u : 0u); it.j = j;
                     a.slow[atomicAdd(&a.ctl->n_slow, 1u)] = it;
                 } else { a.out_off[j] = fits ? ob : 0; a.out_len[j] = rec.out_len; a.out_status[j] = rec.status; a.out_has[j] = rec.has; }
             }
@@ -1169,7 +1168,8 @@ __global__ void __launch_bounds__(DS_WARPS * 32) drain_slow_kernel(DrainArgs a) 
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n_slow) break;
         const SlowItem it = a.slow[i];
-        const uint32_t len = it.len & 0x7FFFFFFFu;
+        const uint32_t len = it.len & 0x3FFFFFFFu;
+        const bool http = (it.len & 0x40000000u) != 0;
         const uint8_t* p = a.payload + it.goff;
         if (len <= DS_STAGE) {
             // the walks below are chains of dependent byte loads: run them against shared memory
@@ -1193,7 +1193,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) drain_slow_kernel(DrainArgs a) 
             if (par) { rec.has = 1; rec.mode = OM_STR_PAR; rec.src_off = FRAME_PRE_LEN; rec.src_len = nbody; rec.out_len = ol; }
         }
         if (!par) {                                                        // the sequential validating parser decides
-            if (lane == 0) d2_parse_and_size<0>(p, len, rec, nullptr);
+            if (lane == 0) d2_parse_and_size<0>(p, len, rec, nullptr, http);
             rec.src_off = __shfl_sync(0xffffffffu, rec.src_off, 0); rec.src_len = __shfl_sync(0xffffffffu, rec.src_len, 0);
             rec.out_len = __shfl_sync(0xffffffffu, rec.out_len, 0);
             const uint32_t w = __shfl_sync(0xffffffffu, (uint32_t)rec.status | ((uint32_t)rec.has << 8) | ((uint32_t)rec.mode << 16), 0);

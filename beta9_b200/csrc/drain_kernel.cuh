@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include "json_device.cuh"
 #include "handlers_device.cuh"
+#include "handler_seq.cuh"
 
 namespace b9 {
 
@@ -29,6 +30,7 @@ __host__ __device__ __forceinline__ uint64_t hdr_pack(uint32_t len, uint8_t flag
 }
 __host__ __device__ __forceinline__ uint32_t hdr_len(uint64_t h) { return (uint32_t)h; }
 __host__ __device__ __forceinline__ uint32_t hdr_flags(uint64_t h) { return (uint32_t)(h >> 32) & 0xFFu; }
+constexpr uint32_t B9_TF_HTTP_BODY_BIT = 0x02u;      // == B9_TF_HTTP_BODY (include/b9gpu.h)
 
 // tile look-back word: status:2 | bytes:38 | count:24
 constexpr uint64_t LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_STATUS = 3ull << 62;
@@ -79,18 +81,6 @@ struct DrainArgs {
     uint32_t static_rounds;         // v2: a worker's first static_rounds tiles are worker + q * workers, the rest come from the ticket counter
 };
 
-// what phase A leaves for phase B, per task of the tile
-enum OutMode : uint8_t { OM_NONE = 0, OM_COPY, OM_STR_ESC /* one thread walks the token */, OM_U32_DEC, OM_I64_DEC, OM_VADD,
-                         OM_STR_PAR /* warp transcodes the framed body in 32 chunks (drain2) */,
-                         OM_DEFER /* identity main kernel: left to drain_slow_kernel */ };
-struct TaskRec {
-    uint32_t src_off;    // OM_COPY / OM_STR_ESC / OM_VADD: byte offset inside the payload
-    uint32_t src_len;
-    uint32_t out_len;
-    uint8_t  status, has, mode, ready;
-    long long value;     // OM_U32_DEC / OM_I64_DEC
-};
-
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) { *(volatile uint64_t*)p = v; }
 
@@ -123,13 +113,6 @@ __device__ inline void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __res
     if (lane < (int)tail) dst[done + lane] = src[done + lane];
 }
 
-__device__ __forceinline__ uint32_t dec_len_u64(unsigned long long v) {
-    uint32_t l = 1; while (v >= 10) { v /= 10; ++l; } return l;
-}
-__device__ inline void write_dec(uint8_t* o, unsigned long long v, uint32_t len) {
-    for (uint32_t k = len; k-- > 0;) { o[k] = (uint8_t)('0' + v % 10); v /= 10; }
-}
-
 // ---- the SDK's canonical frame around one string argument ------------------------------------
 // json.dumps({"args": (s,), "kwargs": {}})  ->  {"args": ["<body>"], "kwargs": {}}
 __device__ __constant__ uint8_t FRAME_PRE[11] = {'{', '"', 'a', 'r', 'g', 's', '"', ':', ' ', '[', '"'};
@@ -157,82 +140,6 @@ __device__ inline Quick quick_frame(const uint8_t* __restrict__ p, uint32_t len,
     }
     if (__any_sync(0xffffffffu, special)) q.maybe_framed = true; else q.framed = true;
     return q;
-}
-
-// String token p[s..e) (quotes included, validated): does the Python-escaped form equal a plain
-// copy?  Computes the json.dumps length either way. One thread.
-__device__ inline uint32_t py_string_len(const uint8_t* __restrict__ p, uint32_t s, uint32_t e) {
-    uint32_t i = s + 1, end = e - 1, out = 2;
-    while (i < end) out += py_escaped_len(next_cp(p, i, end));
-    return out;
-}
-
-// Lane 0: classify args[0] for the handler and fill the record. `pr` is the parse of the payload.
-__device__ inline void handler_phase_a(int handler, const uint8_t* __restrict__ p, const Parsed& pr, TaskRec& rec,
-                                       const uint32_t* __restrict__ crc_table = nullptr) {
-    rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
-    if (pr.status != ST_OK) { rec.status = pr.status; return; }
-    // handler(*args, **kwargs) with a positional-only one-parameter handler
-    if (pr.nargs != 1 || pr.kwargs_nonempty) { rec.status = 1 /* ERROR: TypeError */; return; }
-    rec.status = 0;
-    switch (handler) {
-    case 0: {   // identity: result = args[0]; `serialize_result(result) if result else None`
-        switch (pr.a0_kind) {
-        case AK_STR:
-            if (pr.a0_len == 2) return;                                     // "" is falsy
-            rec.src_off = pr.a0_off; rec.src_len = pr.a0_len; rec.has = 1;
-            if (!(pr.a0_flags & (SF_ESC | SF_NONPRINT))) { rec.mode = OM_COPY; rec.out_len = pr.a0_len; }
-            else { rec.mode = OM_STR_ESC; rec.out_len = py_string_len(p, pr.a0_off, pr.a0_off + pr.a0_len); }
-            return;
-        case AK_NULL: case AK_FALSE: case AK_ARR_EMPTY: case AK_OBJ_EMPTY: return;   // falsy
-        case AK_TRUE: rec.src_off = pr.a0_off; rec.src_len = 4; rec.out_len = 4; rec.mode = OM_COPY; rec.has = 1; return;
-        case AK_INT: {
-            // float64 integer -> Go prints the digits -> Python int -> same digits; "-0"/"0" falsy
-            bool zero = true;
-            for (uint32_t k = 0; k < pr.a0_len; ++k) { uint8_t c = p[pr.a0_off + k]; if (c != '-' && c != '0') zero = false; }
-            if (zero) return;
-            rec.src_off = pr.a0_off; rec.src_len = pr.a0_len; rec.out_len = pr.a0_len; rec.mode = OM_COPY; rec.has = 1; return;
-        }
-        default: rec.status = ST_UNSUPPORTED; return;                       // floats / non-empty containers
-        }
-    }
-    case 1: {   // crc32: zlib.crc32(s.encode()); a non-str has no .encode -> AttributeError
-        if (pr.a0_kind != AK_STR) { rec.status = 1; return; }
-        uint32_t c = crc32_of_string_token(p, pr.a0_off, pr.a0_off + pr.a0_len, pr.a0_flags, crc_table);
-        if (c == 0) return;                                                 // 0 is falsy
-        rec.value = (long long)c; rec.out_len = dec_len_u64(c); rec.mode = OM_U32_DEC; rec.has = 1;
-        return;
-    }
-    case 2: {   // vadd_f32: base64 -> fp32 a||b -> a+b -> base64
-        if (pr.a0_kind != AK_STR) { rec.status = 1; return; }               // TypeError
-        if (pr.a0_flags & SF_NONPRINT) { rec.status = 1; return; }          // non-ASCII / DEL: ValueError / binascii.Error
-        if (pr.a0_flags & SF_ESC) {
-            // escaped text: any decoded character outside the base64 alphabet is an error for sure;
-            // a fully valid escaped base64 string (only "\/" can do that) is not produced by the SDK
-            uint32_t i = pr.a0_off + 1, end = pr.a0_off + pr.a0_len - 1;
-            while (i < end) { uint32_t cp = next_cp(p, i, end); if (cp >= 0x80 || (b64_val((uint8_t)cp) < 0 && cp != '=')) { rec.status = 1; return; } }
-            rec.status = ST_UNSUPPORTED; return;
-        }
-        int64_t rn = b64_decoded_len(p, pr.a0_off + 1, pr.a0_off + pr.a0_len - 1);
-        if (rn < 0 || (rn % 8)) { rec.status = 1; return; }
-        uint32_t n = (uint32_t)(rn / 8);
-        if (n == 0) return;                                                 // "" is falsy
-        rec.src_off = pr.a0_off + 1; rec.src_len = n; rec.out_len = 2 + b64_encoded_len(4 * n); rec.mode = OM_VADD; rec.has = 1;
-        return;
-    }
-    case 3: {   // json_sum: sum(obj["values"])
-        if (pr.a0_kind != AK_OBJ) { rec.status = 1; return; }               // TypeError, or KeyError for {}
-        long long sum = 0;
-        int st = json_sum_object(p, pr.a0_off, pr.a0_off + pr.a0_len, &sum);
-        if (st) { rec.status = (uint8_t)st; return; }
-        if (sum == 0) return;
-        rec.value = sum; rec.mode = OM_I64_DEC; rec.has = 1;
-        rec.out_len = dec_len_u64((unsigned long long)(sum < 0 ? -sum : sum)) + (sum < 0 ? 1u : 0u);
-        return;
-    }
-    default:
-        rec.status = ST_UNSUPPORTED; return;
-    }
 }
 
 template <int HANDLER>
@@ -266,7 +173,7 @@ __global__ void __launch_bounds__(DRAIN_THREADS, 2) drain_kernel(DrainArgs a) {
                 rec.src_off = 0; rec.src_len = 0; rec.value = 0;
                 if (rec.ready) {
                     const uint8_t* p = a.payload + __ldg(a.off + slot);
-                    Parsed pr = parse_payload(p, hdr_len(h));
+                    Parsed pr = parse_payload(p, hdr_len(h), (hdr_flags(h) & B9_TF_HTTP_BODY_BIT) != 0);
                     handler_phase_a(HANDLER, p, pr, rec, s_crc_table);
                 }
                 s_rec[k] = rec;
@@ -281,15 +188,16 @@ __global__ void __launch_bounds__(DRAIN_THREADS, 2) drain_kernel(DrainArgs a) {
             rec.src_off = 0; rec.src_len = 0; rec.value = 0;
             if (ready) {
                 const uint8_t* p = a.payload + __ldg(a.off + slot);
+                const bool http = (hdr_flags(h) & B9_TF_HTTP_BODY_BIT) != 0;
                 Quick q = quick_frame(p, len, lane);
-                if (q.framed && HANDLER == 0) {
+                if (q.framed && HANDLER == 0 && !http) {
                     // args == [body], kwargs == {}; body is printable ASCII without '"' or '\\':
                     // json.dumps(body) is the token itself
                     uint32_t tok = len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
                     if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
                 } else {
                     if (lane == 0) {
-                        Parsed pr = parse_payload(p, len);
+                        Parsed pr = parse_payload(p, len, http);
                         handler_phase_a(HANDLER, p, pr, rec);
                     }
                 }

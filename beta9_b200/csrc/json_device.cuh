@@ -301,6 +301,24 @@ __device__ inline int match_payload_key(const uint8_t* __restrict__ p, uint32_t 
     return 0;
 }
 
+// map-key matching for an HTTP body decoded into map[string]interface{} (pkg/task/serialize.go:19-23,48-57):
+// the DECODED key must be exactly "args" / "kwargs" — no case folding, that is a struct-field rule.
+__device__ inline int match_exact_key(const uint8_t* __restrict__ p, uint32_t s, uint32_t e) {
+    const char A[] = "args", K[] = "kwargs";
+    bool ma = true, mk = true;
+    uint32_t k = 0, i = s;
+    while (i < e) {
+        const uint32_t cp = next_cp(p, i, e);
+        if (k >= 4 || cp != (uint32_t)A[k]) ma = false;
+        if (k >= 6 || cp != (uint32_t)K[k]) mk = false;
+        if (!ma && !mk) return 0;
+        ++k;
+    }
+    if (ma && k == 4) return 1;
+    if (mk && k == 6) return 2;
+    return 0;
+}
+
 __device__ inline bool only_ws(const uint8_t* __restrict__ p, uint32_t s, uint32_t e) {
     for (uint32_t i = s; i < e; ++i) if (!is_ws(p[i])) return false;
     return true;
@@ -308,13 +326,21 @@ __device__ inline bool only_ws(const uint8_t* __restrict__ p, uint32_t s, uint32
 
 // Full, sequential (one thread) parse of a payload. The warp-level fast path in the drain kernel
 // recognises the SDK's canonical frame without calling this; everything else lands here.
-__device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n) {
+//
+// http = false: TaskQueuePutRequest.payload, json.Unmarshal into the TaskPayload STRUCT (taskqueue.go:213-214).
+// http = true (B9_TF_HTTP_BODY): an HTTP request body, SerializeHttpPayload (pkg/task/serialize.go:16-101) —
+//   decoded into a MAP first: exact keys; "args" counts only if it is a list, "kwargs" only if it is an object,
+//   otherwise every remaining key of the body becomes a keyword argument; an empty body is an empty payload;
+//   every number of the document is converted (an overflow anywhere refuses the request).
+__device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n, bool http = false) {
     Parsed r; r.status = ST_OK; r.a0_kind = AK_NONE; r.kwargs_nonempty = 0; r.a0_flags = 0; r.nargs = 0; r.a0_off = 0; r.a0_len = 0;
     r.args_off = r.args_len = r.kw_off = r.kw_len = 0; r.kw_merged = 0;
     uint32_t i = 0, sub_flags = 0;
+    // http: does the body's map still hold keys once "args" (a list) and "kwargs" (an object) are taken out?
+    bool args_left = false, kwargs_left = false, others_left = false, kw_is_dict = false;
 #define B9_REJECT() do { r.status = (sub_flags & SF_DEEP) ? ST_UNSUPPORTED : ST_REJECTED; return r; } while (0)
     while (i < n && is_ws(p[i])) ++i;
-    if (i >= n) B9_REJECT();
+    if (i >= n) { if (http) return r; B9_REJECT(); }            // serialize.go:22-25 tolerates io.EOF: empty payload
     if (p[i] != '{') {
         // top-level null is a no-op for Unmarshal; any other value is a type or syntax error
         if (p[i] == 'n' && scan_literal(p, i, n) == (int64_t)i + 4) {
@@ -334,7 +360,7 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
         uint32_t ks = i;
         int64_t e = scan_string(p, i, n, kf); if (e < 0) B9_REJECT();
         i = (uint32_t)e;
-        int which = match_payload_key(p, ks + 1, i - 1);
+        int which = http ? match_exact_key(p, ks + 1, i - 1) : match_payload_key(p, ks + 1, i - 1);
         while (i < n && is_ws(p[i])) ++i;
         if (i >= n || p[i] != ':') B9_REJECT();
         ++i;
@@ -380,6 +406,14 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
                     B9_REJECT();
                 }
                 r.nargs = cnt; r.args_off = arr_start; r.args_len = i - arr_start;
+                args_left = false;
+            } else if (http) {                              // "args" that is not a list stays in the map (a later "args" replaces it)
+                uint32_t ef = 0;
+                int64_t ee = skip_value(p, i, n, ef);
+                sub_flags |= ef & (SF_F64_OVER | SF_DEEP);
+                if (ee < 0) B9_REJECT();
+                i = (uint32_t)ee;
+                r.nargs = 0; r.a0_kind = AK_NONE; r.args_len = 0; args_left = true;
             } else if (p[i] == 'n' && scan_literal(p, i, n) >= 0) {
                 i += 4; r.nargs = 0; r.a0_kind = AK_NONE; r.args_len = 0;
             } else B9_REJECT();                             // UnmarshalTypeError or syntax error
@@ -391,17 +425,26 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
                 if (ee < 0) B9_REJECT();
                 i = (uint32_t)ee;
                 if (!only_ws(p, vs + 1, i - 1)) r.kwargs_nonempty = 1;   // a non-nil map is merged into
-                if (r.kw_len) r.kw_merged = 1;
+                if (http) { r.kwargs_nonempty = only_ws(p, vs + 1, i - 1) ? 0 : 1; kw_is_dict = true; kwargs_left = false; }   // map value: the last one wins
+                else if (r.kw_len) r.kw_merged = 1;
                 r.kw_off = vs; r.kw_len = i - vs;
+            } else if (http) {                              // "kwargs" that is not an object stays in the map
+                uint32_t ef = 0;
+                int64_t ee = skip_value(p, i, n, ef);
+                sub_flags |= ef & (SF_F64_OVER | SF_DEEP);
+                if (ee < 0) B9_REJECT();
+                i = (uint32_t)ee;
+                kw_is_dict = false; kwargs_left = true; r.kw_len = 0;
             } else if (p[i] == 'n' && scan_literal(p, i, n) >= 0) {
                 i += 4; r.kwargs_nonempty = 0; r.kw_len = 0; r.kw_merged = 0;
             } else B9_REJECT();
         } else {
             uint32_t ef = 0;
             int64_t ee = skip_value(p, i, n, ef);
-            sub_flags |= ef & SF_DEEP;                      // numbers under ignored keys are never converted
+            sub_flags |= ef & (http ? (SF_DEEP | SF_F64_OVER) : SF_DEEP);   // struct: numbers under ignored keys are never converted; map: all are
             if (ee < 0) B9_REJECT();
             i = (uint32_t)ee;
+            others_left = true;
         }
         while (i < n && is_ws(p[i])) ++i;
         if (i >= n) B9_REJECT();
@@ -413,6 +456,7 @@ __device__ inline Parsed parse_payload(const uint8_t* __restrict__ p, uint32_t n
     if (i != n) B9_REJECT();
 #undef B9_REJECT
     if (sub_flags & SF_F64_OVER) r.status = ST_REJECTED;     // "number out of range": Unmarshal error -> Ok:false
+    if (http && !kw_is_dict) r.kwargs_nonempty = (args_left || kwargs_left || others_left) ? 1 : 0;   // serialize.go:57-60
     return r;
 }
 

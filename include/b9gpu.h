@@ -75,6 +75,14 @@ enum b9_status {
 #define B9_TF_CANCELLED 0x01u  /* task already completed/cancelled/expired: TaskQueuePop skips it
                                   (taskqueue.go:261-265); the drain compacts it away           */
 
+#define B9_TF_HTTP_BODY 0x02u  /* the payload is an HTTP request body of the task-queue endpoint
+                                  (pkg/abstractions/taskqueue/http.go:38-78), not the SDK's put payload:
+                                  args / kwargs follow SerializeHttpPayload (pkg/task/serialize.go:16-101) —
+                                  a MAP decode: exact keys, "args" only if a list, "kwargs" only if an object,
+                                  otherwise the body's remaining keys are the keyword arguments; an empty body
+                                  is an empty payload; B9_ST_REJECTED = HTTP 400 "invalid request payload".
+                                  (Query-string arguments are the host's to merge before the push.)            */
+
 typedef struct b9_ctx b9_ctx;
 
 typedef struct b9_opts {

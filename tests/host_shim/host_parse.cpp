@@ -1,0 +1,39 @@
+// TEST INFRASTRUCTURE: compiles the DEVICE's sequential path — the JSON parser (json_device.cuh), the
+// handlers (handlers_device.cuh) and what a parsed payload means to each handler (handler_seq.cuh), all plain
+// C++ behind CUDA qualifiers — for the host, so that its decisions and result bytes can be fuzzed against the
+// oracle on a CPU (tests/test_device_parser_on_host.py). Nothing in the product links or loads this; the
+// warp-cooperative fast paths (drain2.cuh) are GPU-only and covered by tests/test_gpu_parity.py.
+#include <stdint.h>
+#include <string.h>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __constant__ static const
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __fadd_rn(float a, float b) { volatile float z = a + b; return z; }     // IEEE binary32, round to nearest even
+#include "../../beta9_b200/csrc/handler_seq.cuh"
+
+extern "C" int b9_host_parse(const uint8_t* p, uint32_t n, int http, uint32_t* out /* [8] */) {
+    const b9::Parsed r = b9::parse_payload(p, n, http != 0);
+    out[0] = r.status; out[1] = r.nargs; out[2] = r.kwargs_nonempty; out[3] = r.a0_kind;
+    out[4] = r.a0_off; out[5] = r.a0_len; out[6] = r.a0_flags; out[7] = r.kw_merged;
+    return 0;
+}
+
+// the whole sequential path for one task: parse -> handler (phase A) -> result bytes (phase B).
+// Returns the result length (0 with *has == 0: no result bytes), or -1 if `cap` is too small.
+extern "C" long b9_host_run(const uint8_t* p, uint32_t n, int http, int handler, uint8_t* status, uint8_t* has, uint8_t* out, uint32_t cap) {
+    static uint32_t table[256];
+    static bool have = false;
+    if (!have) { for (uint32_t i = 0; i < 256; ++i) table[i] = b9::crc_table_entry(i); have = true; }
+    const b9::Parsed pr = b9::parse_payload(p, n, http != 0);
+    b9::TaskRec rec; memset(&rec, 0, sizeof rec); rec.ready = 1;
+    b9::handler_phase_a(handler, p, pr, rec, table);
+    *status = rec.status; *has = rec.has;
+    if (!rec.has) return 0;
+    if (rec.out_len > cap) return -1;
+    if (rec.mode == b9::OM_COPY) memcpy(out, p + rec.src_off, rec.src_len);
+    else b9::seq_emit(p, rec, out);
+    return (long)rec.out_len;
+}

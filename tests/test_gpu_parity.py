@@ -215,6 +215,77 @@ def test_async_launch_then_fetch(dq):
     assert_matches_oracle(b, r, o)
 
 
+def _http_bodies():
+    """HTTP request bodies for B9_TF_HTTP_BODY: the reference's own SerializeHttpPayload cases
+    (pkg/task/serialize_test.go:39-173, those without a query string), map-rule corner cases, SDK-framed
+    payloads (valid bodies too), and single-character mutants."""
+    import json
+    from tests.test_oracle_reference_answers import SERIALIZE_CASES
+    bodies = [c[1].encode() for c in SERIALIZE_CASES if not c[2]]
+    bodies += [b'{"args": ["abc"]}', b'{"args": ["abc"], "kwargs": {}}', b'{"x": 1}', b'', b'  \n', b'null', b'[1]', b'"s"', b'7',
+               b'{"args": "notalist"}', b'{"args": null}', b'{"args": ["a"], "kwargs": 5}', b'{"args": ["a"], "kwargs": null}',
+               b'{"args": ["a"], "other": [1e999]}', b'{"args": ["a"], "other": 1e400, "kwargs": {}}', b'{"\\u0061rgs": ["esc"]}',
+               b'{"Args": ["folded?"]}', b'{"ARGS": ["x"], "KWARGS": {}}', b'{"args": ["a"], "args": 1}', b'{"args": 1, "args": ["last"]}',
+               b'{"args": ["x"], "kwargs": {"a": 1}}', b' {"args":["ws"]} ', b'{"kwargs": {}, "args": ["order"]}', b'{"kwargs": {"k": 1}, "kwargs": {}, "args": ["dup kw"]}',
+               b'{"kwargs": {}, "kwargs": {"k": 1}, "args": ["dup kw 2"]}', b'{"args": ["x"], "kwargs": {}, "extra": true}', b'{"args": ["x"], "extra": true}',
+               b'{"args": []}', b'{"args": ["a", "b"]}', b'{"args": [""]}', b'{"args": [0]}', b'{"args": [123]}', b'{"args": [{"values": [1, 2, 3]}]}',
+               b'{"args": [{"values": [1, 2, 3]}], "kwargs": {}}', b'{"args": ["QUJDRA=="]}', b'{"args": ["AACAPwAAgD8="]}', b'{}', b'{"args": ["x"]} trailing',
+               b'{"args": ["\\ud83d\\ude00 \\u00e9"]}', b'{"args": ["a\\/b"]}', b'{"k\\u0077args": {}, "args": ["esc key"]}']
+    rng = np.random.default_rng(4242)
+    sdk = synth.strings_batch(60, 40, adversarial_frac=0.3, seed=77)
+    bodies += [sdk.task(i) for i in range(sdk.n)]
+    jb = synth.json_batch(6, doc_bytes=300)
+    bodies += [jb.task(i) for i in range(jb.n)]
+    vb = synth.vadd_batch(6, floats_per_vec=4)
+    bodies += [vb.task(i) for i in range(vb.n)]
+    base = list(bodies)
+    alphabet = list(b'{}[],:" 01e.-nulltrackwgs\\')
+    for b in base:
+        if len(b) < 4:
+            continue
+        for _ in range(3):
+            m = bytearray(b)
+            pos = int(rng.integers(0, len(m)))
+            op = int(rng.integers(0, 3))
+            ch = int(rng.choice(alphabet))
+            if op == 0: m[pos] = ch
+            elif op == 1: del m[pos]
+            else: m[pos:pos] = bytes([ch])
+            bodies.append(bytes(m))
+    return bodies
+
+
+@pytest.mark.parametrize("handler", HANDLERS)
+def test_http_body_mode(dq, handler):
+    """B9_TF_HTTP_BODY: args / kwargs by SerializeHttpPayload's map rules, against the Python oracle
+    (its serialize_http_payload is pinned to the reference's 15 known answers)."""
+    from oracle.pyoracle import loop
+    bodies = _http_bodies()
+    b = synth.from_payloads(bodies)
+    assert dq.depth() == 0
+    dq.push_batch(b.task_ids, b.payload, b.offsets, flags=np.full(b.n, 2, np.uint8))
+    r = dq.drain(handler, max_tasks=b.n)
+    assert r.n == b.n and dq.depth() == 0
+    want = loop.run_task_loop(bodies, [bytes(x) for x in b.task_ids], handler, http_body=True)
+    code = {"COMPLETE": 0, "ERROR": 1, "RETRY": 2, "REJECTED": 3}
+    declined = 0
+    for i, w in enumerate(want):
+        if r.status[i] == 4:                       # floats etc.: the device declines, never guesses
+            assert not r.has_result[i]
+            assert w.status in ("COMPLETE", "ERROR", "REJECTED"), bodies[i]
+            declined += 1
+            continue
+        assert r.status[i] == code[w.status], (bodies[i], int(r.status[i]), w.status)
+        assert r.result(i) == w.result, (bodies[i], r.result(i), w.result)
+    assert declined <= len(bodies) // 10
+    # the same bytes WITHOUT the flag follow the struct rules: e.g. an empty body is refused, unknown keys are ignored
+    plain = [b'', b'{"args": ["x"], "extra": true}', b'{"Args": ["folded"]}']
+    pb = synth.from_payloads(plain)
+    dq.push_batch(pb.task_ids, pb.payload, pb.offsets)
+    r2 = dq.drain("identity", max_tasks=pb.n)
+    assert list(r2.status) == [3, 0, 0] and r2.result(1) == b'"x"' and r2.result(2) == b'"folded"'
+
+
 def test_wrong_handler_for_payload(dq):
     # every handler over every config's payloads: type errors must come out as ERROR exactly like the oracle
     for b in (synth.strings_batch(2000, 64, adversarial_frac=0.2), synth.vadd_batch(1000), synth.json_batch(200)):

@@ -16,7 +16,11 @@
 // One thread per task: a sizing walk, one cursor add per warp, an emitting walk.
 #pragma once
 #include <stdint.h>
+#ifdef B9_WIRE_ENCODE_HELPERS_ONLY      // tests/host_shim builds the value encoders below for the host
+#include "json_device.cuh"
+#else
 #include "drain_kernel.cuh"
+#endif
 
 namespace b9 {
 
@@ -164,6 +168,7 @@ __device__ inline uint32_t put_dec_ll(uint8_t* o, long long v) {
     return n + l;
 }
 
+#ifndef B9_WIRE_ENCODE_HELPERS_ONLY
 struct WireArgs {
     const uint8_t* payload; const uint64_t* off; const uint64_t* hdr; const uint4* ids; const int64_t* ts; const int64_t* exp;
     uint32_t slot_mask; uint64_t first_task; uint32_t n_tasks;
@@ -264,5 +269,7 @@ __global__ void __launch_bounds__(128) wire_encode_kernel(WireArgs a, const Wire
     o += put_dec_ll(o, ts);
     *o++ = '}';
 }
+
+#endif
 
 }  // namespace b9

@@ -13,11 +13,14 @@ static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); re
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float __fadd_rn(float a, float b) { volatile float z = a + b; return z; }     // IEEE binary32, round to nearest even
 #include "../../beta9_b200/csrc/handler_seq.cuh"
+#define B9_WIRE_ENCODE_HELPERS_ONLY 1
+#include "../../beta9_b200/csrc/wire_encode.cuh"
 
-extern "C" int b9_host_parse(const uint8_t* p, uint32_t n, int http, uint32_t* out /* [8] */) {
+extern "C" int b9_host_parse(const uint8_t* p, uint32_t n, int http, uint32_t* out /* [12] */) {
     const b9::Parsed r = b9::parse_payload(p, n, http != 0);
     out[0] = r.status; out[1] = r.nargs; out[2] = r.kwargs_nonempty; out[3] = r.a0_kind;
     out[4] = r.a0_off; out[5] = r.a0_len; out[6] = r.a0_flags; out[7] = r.kw_merged;
+    out[8] = r.args_off; out[9] = r.args_len; out[10] = r.kw_off; out[11] = r.kw_len;
     return 0;
 }
 
@@ -37,3 +40,13 @@ extern "C" long b9_host_run(const uint8_t* p, uint32_t n, int http, int handler,
     else b9::seq_emit(p, rec, out);
     return (long)rec.out_len;
 }
+
+// Go re-encoding of one validated JSON value (the args list / kwargs object of a TaskMessage): bytes written, or -1
+// when the device encoder declines (unsorted or duplicate keys, non-integer numbers), -2 if `cap` is too small.
+extern "C" long b9_host_go_transcode(const uint8_t* p, uint32_t n, uint8_t* out, uint32_t cap) {
+    const int64_t need = b9::go_transcode(p, 0, n, nullptr);
+    if (need < 0) return -1;
+    if ((uint64_t)need > cap) return -2;
+    return (long)b9::go_transcode(p, 0, n, out);
+}
+extern "C" long b9_host_rfc3339nano(long long unix_ns, uint8_t* out) { return (long)b9::rfc3339nano(unix_ns, out); }

@@ -33,7 +33,7 @@ def parser():
     lib.b9_host_run.restype = C.c_long
 
     def parse(b: bytes, http: bool):
-        out = (C.c_uint32 * 8)()
+        out = (C.c_uint32 * 12)()
         lib.b9_host_parse(b, len(b), 1 if http else 0, out)
         return list(out)
 
@@ -43,7 +43,21 @@ def parser():
         n = lib.b9_host_run(b, len(b), 1 if http else 0, handler, C.byref(st), C.byref(has), buf, len(buf))
         assert n >= 0
         return int(st.value), (buf.raw[:n] if has.value else None)
-    parse.run = run
+    lib.b9_host_go_transcode.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
+    lib.b9_host_go_transcode.restype = C.c_long
+    lib.b9_host_rfc3339nano.argtypes = [C.c_longlong, C.c_char_p]
+    lib.b9_host_rfc3339nano.restype = C.c_long
+
+    def transcode(tok: bytes):
+        buf = C.create_string_buffer(8 * len(tok) + 64)
+        n = lib.b9_host_go_transcode(tok, len(tok), buf, len(buf))
+        return None if n < 0 else buf.raw[:n]
+
+    def rfc3339(ns: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        n = lib.b9_host_rfc3339nano(ns, buf)               # (call first: `buf.raw` is a snapshot)
+        return buf.raw[:n]
+    parse.run, parse.transcode, parse.rfc3339 = run, transcode, rfc3339
     return parse
 
 
@@ -90,7 +104,7 @@ def test_device_parser_agrees_with_the_oracle(parser, http):
     payloads = _payloads()
     checked = declined = 0
     for b in payloads:
-        status, nargs, kw_nonempty, a0_kind, a0_off, a0_len, a0_flags, kw_merged = parser(b, http)
+        status, nargs, kw_nonempty, a0_kind, a0_off, a0_len, a0_flags, kw_merged = parser(b, http)[:8]
         want = _oracle(b, http)
         if status == 4:                                   # nesting deeper than the device stack: declined, never decided
             declined += 1
@@ -135,3 +149,33 @@ def test_device_sequential_path_agrees_with_the_oracle(parser, handler, http):
         assert st == code[w.status], (b, st, w.status)
         assert res == w.result, (b, res, w.result)
     assert declined < len(payloads) // 5
+
+
+def test_device_go_value_encoder_agrees_with_the_oracle(parser):
+    """go_transcode (wire_encode.cuh): the args list / kwargs object of a TaskMessage re-encoded by Go's rules, and
+    the RFC3339Nano `expires`. Wherever the device encoder does not decline, its bytes are the oracle's."""
+    from oracle.pyoracle.gojson import go_marshal, go_time_rfc3339nano
+    done = declined = 0
+    for b in _payloads():
+        try:
+            args, kwargs = go_unmarshal_task_payload(b)
+        except GoJSONError:
+            continue
+        # the value tokens as they sit in the payload (the spans the device parser reports)
+        st = parser(b, False)
+        if st[0] != 0 or st[7]:
+            continue
+        for val, off, ln in ((args, st[8], st[9]), (kwargs, st[10], st[11])):
+            if val is None or ln == 0:
+                continue
+            tok = b[off:off + ln]
+            got = parser.transcode(tok)
+            if got is None:
+                declined += 1
+                continue
+            assert got == go_marshal(val).encode(), (tok, got, go_marshal(val))
+            done += 1
+    assert done > 100
+    for ns in (0, 1, 999_999_999, 1_000_000_000, 1_789_970_992_573_161_412, 1_709_210_096_000_000_000, 4_102_444_800_000_000_000,
+               951_782_400_123_000_000, 1_718_000_000_120_000_000):
+        assert parser.rfc3339(ns) == go_time_rfc3339nano(ns).encode(), ns

@@ -94,6 +94,7 @@ struct b9_ctx {
     uint32_t* d_crc_shift = nullptr;            // crc32: zero-byte shift tables
     uint64_t cancelled_pending = 0;            // pending tasks carrying B9_TF_CANCELLED (pushed so, or expired)
     DrainCtl* d_ctl = nullptr; uint64_t* d_tile_state = nullptr;
+    bool burst_open = false; cudaEvent_t ev_burst = nullptr;   // B9_DRAIN_ASYNC launches since the last completion: timed as one burst
     bool res_async = false;                    // the last launch returned before its kernels finished: finalize on fetch / sync
     uint32_t res_async_n = 0; uint64_t res_async_in_bytes = 0; bool res_async_v2 = true;
     DrainCtl* h_ctl = nullptr;                 // pinned
@@ -249,6 +250,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->ev_burst));
     CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b)); CUC(cudaEventCreate(&c->ev_c)); CUC(cudaEventCreate(&c->ev_d));
     const uint32_t rt = c->ring_tasks, md = c->max_drain_tasks;
     CUC(cudaMalloc(&c->d_payload, c->ring_bytes + RING_SLACK));
@@ -318,6 +320,7 @@ void b9_ctx_destroy(b9_ctx* c) {
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     cudaFree(c->d_xchg_send); cudaFree(c->d_xchg_recv);
     if (c->h_count) cudaFreeHost(c->h_count);
+    if (c->ev_burst) cudaEventDestroy(c->ev_burst);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->ev_c) cudaEventDestroy(c->ev_c);
@@ -461,7 +464,9 @@ static int finish_launch(b9_ctx* c) {
     if (!c->res_async) return B9_OK;
     c->res_async = false;
     CU(cudaStreamSynchronize(c->stream));
-    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+    // one launch: the time around its kernels; a burst of B9_DRAIN_ASYNC launches: from the first one's start to the last one's end
+    float ms = 0; cudaEventElapsedTime(&ms, c->burst_open ? c->ev_burst : c->ev_a, c->ev_b);
+    c->burst_open = false;
     c->stats.last_drain_kernel_ms = ms;
     if (c->h_ctl->overflow)
         return fail(B9_ENOSPC, "b9_drain_launch: results exceed max_result_bytes (%llu); drain fewer tasks or enlarge the staging",
@@ -482,7 +487,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     // results of an earlier launch that were never fetched are dropped; their tasks are still
-    // pending (a pop is committed by a successful fetch, never by a launch)
+    // pending (a pop is committed by a successful fetch, never by a launch). (An open burst of async launches stays open.)
     c->have_results = false; c->res_async = false;
     const uint64_t depth = c->tail_task - c->head_task;
     const uint32_t n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
@@ -518,6 +523,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
     if (!v2 || a.count_mode) CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));   // look-back state: v2 only reads it when slots are cancelled
     int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
+    if (!c->burst_open) CU(cudaEventRecord(c->ev_burst, s));
     CU(cudaEventRecord(c->ev_a, s));
     cudaError_t le;
     if (v2) {
@@ -554,7 +560,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     c->stats.last_drain_tiles = (n + 127) / 128;   // (reported in units of 128 tasks)
     c->stats.drains++;
     c->res_async = true; c->res_async_n = n; c->res_async_in_bytes = in_bytes; c->res_async_v2 = v2;
-    if (peek & B9_DRAIN_ASYNC) return (int64_t)n;  // records = n minus the cancelled slots: known after b9_sync / b9_drain_fetch
+    if (peek & B9_DRAIN_ASYNC) { c->burst_open = true; return (int64_t)n; }   // records = n minus the cancelled slots: known after b9_sync / b9_drain_fetch
     int rc = finish_launch(c);
     return rc ? rc : (int64_t)c->res_n;
 }
@@ -594,7 +600,7 @@ int64_t b9_drain_fetch(b9_ctx* c, b9_results* out) {
         c->cancelled_pending -= std::min<uint64_t>(c->cancelled_pending, (uint64_t)(c->res_popped - c->res_n));
         free_segments(c);
     }
-    c->have_results = false; c->res_async = false;
+    c->have_results = false; c->res_async = false; c->burst_open = false;
     return (int64_t)n;
 }
 
@@ -637,7 +643,7 @@ int64_t b9_wire_encode(b9_ctx* c, const b9_wire_env* env, uint32_t max_tasks) {
     if (!c || !env || !env->workspace_name || !env->stub_id) return fail(B9_EINVAL, "b9_wire_encode: NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
-    c->have_results = false; c->res_async = false;
+    c->have_results = false; c->res_async = false; c->burst_open = false;
     const uint64_t depth = c->tail_task - c->head_task;
     const uint32_t n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
     c->res_n = 0; c->res_popped = 0; c->res_bytes = 0; c->res_in_bytes = 0; c->res_peek = true;
@@ -867,7 +873,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         t_last = now;
     };
     for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(s, sg.ready, 0));
-    c->have_results = false; c->res_async = false;
+    c->have_results = false; c->res_async = false; c->burst_open = false;
     free_segments(c);
     const uint64_t n = c->tail_task - c->head_task;
     // byte prefix of my pending tasks (host bookkeeping holds every batch's offsets)

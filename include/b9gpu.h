@@ -130,7 +130,8 @@ typedef struct b9_stats {
     uint64_t kernel_launches;        /* kernels launched by this library since ctx creation      */
     uint64_t drains;
     float    last_push_h2d_ms;       /* CUDA-event time of the last push's H2D copies            */
-    float    last_drain_kernel_ms;   /* CUDA-event time around the last drain's kernel(s)        */
+    float    last_drain_kernel_ms;   /* CUDA-event time around the last drain's kernel(s); after a burst of
+                                        B9_DRAIN_ASYNC launches: from the first one's start to the last one's end */
     float    last_drain_d2h_ms;      /* CUDA-event time of the last drain's D2H copies           */
     uint32_t last_drain_tiles;
     uint32_t sm_count;

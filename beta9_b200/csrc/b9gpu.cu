@@ -186,7 +186,14 @@ template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes,
     // switch made vadd_f32 slower (0.196 -> 0.212 ms), so it stays on pure work stealing like crc32 / json_sum.
     // B9_STATIC_ROUNDS=0 turns it off.
     static const bool allow_static = !(getenv("B9_STATIC_ROUNDS") && atoi(getenv("B9_STATIC_ROUNDS")) == 0);
-    if (allow_static && H == B9_H_IDENTITY && !a.count_mode) {
+    if (a.count_mode) {                                                    // cancelled slots in the window: ready-count prefix per warp-tile
+        const uint32_t warps = (a.n_tasks + 31u) / 32u;
+        tile_count_kernel<<<(warps * 32u + 255u) / 256u, 256, 0, s>>>(a.hdr, a.slot_mask, a.first_task, a.n_tasks, (uint32_t)T, (uint32_t*)a.tile_base);
+        tile_scan_kernel<<<1, 1024, 0, s>>>((uint32_t*)a.tile_base, a.n_tiles);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (allow_static && H == B9_H_IDENTITY) {
         const uint64_t rounds = a.n_tiles / ((uint64_t)grid * D3_WARPS);
         a.static_rounds = rounds > 1 ? (uint32_t)(rounds - 1) : 0u;
     }
@@ -513,7 +520,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     a.payload = c->d_payload; a.off = c->d_off; a.hdr = c->d_hdr; a.ids = c->d_ids; a.slot_mask = c->slot_mask;
     a.first_task = c->head_task; a.n_tasks = n; a.n_tiles = (n + TILE_TASKS - 1) / TILE_TASKS;
     a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_ids = c->d_out_ids;
-    a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.handler = handler;
+    a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.tile_base = (const uint32_t*)c->d_tile_state; a.handler = handler;
     a.count_mode = c->cancelled_pending ? 1u : 0u;
     a.slow = c->d_slow; a.crc_shift_tabs = c->d_crc_shift;
     a.static_rounds = 0;
@@ -521,7 +528,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     const bool v2 = c->drain_version == 2;
     if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;     // upper bound over the handlers' warp-tile sizes (state array memset)
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
-    if (!v2 || a.count_mode) CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));   // look-back state: v2 only reads it when slots are cancelled
+    if (!v2) CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));   // v1's look-back words (v2 writes its tile prefix itself)
     int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
     if (!c->burst_open) CU(cudaEventRecord(c->ev_burst, s));
     CU(cudaEventRecord(c->ev_a, s));
@@ -540,7 +547,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     default:            le = launch_drain<3>(a, grid, s); break;
     }
     if (le != cudaSuccess) return fail(B9_EIO, "drain kernel launch failed: %s", cudaGetErrorString(le));
-    c->stats.kernel_launches++;
+    c->stats.kernel_launches += (v2 && a.count_mode) ? 3 : 1;              // (+ tile_count_kernel and tile_scan_kernel)
     if (v2 && handler == B9_H_IDENTITY) {
         // second kernel: the tasks the main identity kernel deferred (escaped strings, foreign framing, ...)
         static int slow_per_sm = 0;

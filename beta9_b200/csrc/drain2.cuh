@@ -907,27 +907,49 @@ __device__ __forceinline__ void d3_load_meta(const DrainArgs& a, unsigned long l
     }
 }
 
-// the rare count chain (some pending task is cancelled): decoupled look-back over warp-tiles
-__device__ __noinline__ uint32_t d3_count_lookback(const DrainArgs& a, unsigned long long tile, uint32_t rc, int lane) {
-    uint64_t excl = 0;
-    if (tile == 0) { if (lane == 0) st_volatile_u64(a.tile_state + 0, LB_INC | rc); return 0; }
-    if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_AGG | rc);
-    long long look = (long long)tile - 1;
-    for (;;) {
-        const long long idx = look - lane;
-        uint64_t w = (idx >= 0) ? ld_volatile_u64(a.tile_state + idx) : LB_INC;
-        while (__any_sync(0xffffffffu, (w & LB_STATUS) == 0)) { if ((w & LB_STATUS) == 0) w = ld_volatile_u64(a.tile_state + idx); }
-        const uint32_t inc_mask = __ballot_sync(0xffffffffu, (w & LB_STATUS) == LB_INC);
-        uint64_t v = lb_value(w);
-        if (inc_mask) { const int first = __ffs(inc_mask) - 1; if (lane > first) v = 0; }
-        #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        excl += v;
-        if (inc_mask) break;
-        look -= 32;
+// Windows that hold cancelled slots (TaskQueuePop's skip loop, taskqueue.go:243-271): a task's record index is no
+// longer its task index. Two small kernels ahead of the drain turn the slot flags (8 B per task) into the number of
+// ready tasks before every warp-tile, so the drain itself stays free of any inter-tile dependency:
+//   tile_count_kernel   a warp per 32 slots: ready bits by ballot, one count per tile of T (= 4, 8 or 32) slots
+//   tile_scan_kernel    one CTA: in-place prefix over the per-tile counts; base[i] = ready tasks before tile i
+// (An earlier version chained the counts through a decoupled look-back inside the drain: 0.32 ms instead of 0.18 ms
+// for 1M tasks as soon as ONE slot of the window was cancelled.)
+__global__ void __launch_bounds__(256) tile_count_kernel(const uint64_t* __restrict__ hdr, uint32_t slot_mask, uint64_t first_task, uint32_t n_tasks,
+                                                         uint32_t T, uint32_t* __restrict__ base /* [n_tiles + 1] */) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // 32 slots per warp
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = w * 32u + (uint32_t)lane;
+    if (w * 32u >= n_tasks) return;
+    const bool ready = t < n_tasks && !(hdr_flags(__ldg(hdr + (uint32_t)((first_task + t) & slot_mask))) & 1u);
+    const uint32_t m = __ballot_sync(0xffffffffu, ready);
+    const uint32_t per = 32u / T;                                        // tiles inside these 32 slots
+    if ((uint32_t)lane < per) {
+        const uint32_t tile = w * per + (uint32_t)lane;
+        if (tile * T < n_tasks) base[tile + 1u] = __popc(T == 32u ? m : ((m >> (lane * T)) & ((1u << T) - 1u)));
     }
-    if (lane == 0) st_volatile_u64(a.tile_state + tile, LB_INC | (excl + rc));
-    return (uint32_t)excl;
+    if (w == 0 && lane == 0) base[0] = 0;
+}
+__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ base, uint32_t n_tiles) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (n_tiles + 1023u) / 1024u;
+    const uint32_t lo = min(n_tiles, tid * per), hi = min(n_tiles, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += base[i + 1u];
+    uint32_t inc = sum;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += v; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t x = s_warp[lane], y = x;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, y, d); if ((int)lane >= d) y += v; }
+        s_warp[lane] = y - x;                                            // exclusive over warps
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + inc - sum;                             // ready tasks before my first tile
+    for (uint32_t i = lo; i < hi; ++i) { run += base[i + 1u]; base[i + 1u] = run; }   // base[i+1] = ready tasks before tile i+1
 }
 
 // scattered tile (it spans pushes): one bulk copy per task, each widened to 16-byte boundaries
@@ -1040,7 +1062,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         // record indices: ready counts are known from the slot words alone
         const uint32_t ready_mask_t = __ballot_sync(0xffffffffu, m_ready);       // bit = task index
         const uint32_t rc = __popc(ready_mask_t);
-        const uint32_t base_cnt = a.count_mode ? d3_count_lookback(a, tile, rc, lane) : t0;
+        const uint32_t base_cnt = a.count_mode ? __ldg(a.tile_base + tile) : t0;   // (count_mode: prefix written by tile_scan_kernel)
         if (lane == 0 && tile == a.n_tiles - 1) a.ctl->total_cnt = base_cnt + rc;
         // advance the ticket pipeline (loads/atomics issued here are consumed one iteration later)
         t_cur = __shfl_sync(0xffffffffu, t_raw, 0);

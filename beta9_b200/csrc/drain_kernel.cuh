@@ -73,9 +73,10 @@ struct DrainArgs {
     uint8_t*  out_has;              // [n_tasks]
     // control
     DrainCtl* ctl;
-    uint64_t* tile_state;           // [n_tiles], zeroed before launch
+    uint64_t* tile_state;           // v1: [n_tiles] look-back words, zeroed before launch
+    const uint32_t* tile_base;      // v2, count_mode: [n_tiles + 1] ready tasks before each warp-tile (tile_scan_kernel)
     int handler;
-    uint32_t count_mode;            // v2: 0 = no pending task is cancelled (record index = task index), 1 = chain the ready counts
+    uint32_t count_mode;            // v2: 0 = no pending task is cancelled (record index = task index), 1 = record index from tile_base
     SlowItem* slow;                 // v2 identity: [n_tasks] work list for the second kernel
     const uint32_t* crc_shift_tabs; // v2 crc32: [levels][4][256] "advance the CRC register over 2^k zero bytes" tables
     uint32_t static_rounds;         // v2: a worker's first static_rounds tiles are worker + q * workers, the rest come from the ticket counter

@@ -358,6 +358,29 @@ def test_cancelled_and_expired_tasks_are_compacted_away(dq):
         assert int(r.status[j]) == int(o.status[i]) and r.result(j) == o.result(i)
 
 
+@pytest.mark.parametrize("handler,make", [("identity", lambda: synth.strings_batch(70_001, 48, adversarial_frac=0.02, seed=31)),
+                                          ("crc32", lambda: synth.crc_batch(3001, seed=32)),
+                                          ("vadd_f32", lambda: synth.vadd_batch(9007, seed=33)),
+                                          ("json_sum", lambda: synth.json_batch(1203, doc_bytes=400, seed=34))])
+def test_cancelled_slots_every_handler(dq, handler, make):
+    """Record indices with cancelled slots in the window (tile_count_kernel / tile_scan_kernel ahead of the drain),
+    for every warp-tile size (32, 4 and 8 slots), odd task counts, runs of cancelled slots, a single one, all but one."""
+    b = make()
+    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, handler, nthreads=8)
+    rng = np.random.default_rng(b.n)
+    patterns = [rng.random(b.n) < 0.07, np.arange(b.n) == b.n // 3, np.arange(b.n) != 5,
+                (np.arange(b.n) // 97) % 3 == 0, np.arange(b.n) < 40, np.arange(b.n) >= b.n - 33]
+    for gone in patterns:
+        dq.push_batch(b.task_ids, b.payload, b.offsets, flags=gone.astype(np.uint8))
+        r = dq.drain(handler)
+        keep = np.flatnonzero(~gone)
+        assert r.n_popped == b.n and r.n == keep.size and dq.depth() == 0
+        assert np.array_equal(r.task_ids, b.task_ids[keep])
+        assert np.array_equal(r.status, o.status[keep]) and np.array_equal(r.has_result, o.has[keep])
+        for j in list(range(min(50, keep.size))) + list(range(max(0, keep.size - 50), keep.size)) + list(rng.integers(0, keep.size, 200)):
+            assert r.result(int(j)) == o.result(int(keep[int(j)])), (handler, int(j))
+
+
 def test_result_capacity_errors_do_not_consume():
     from beta9_b200.device_queue import DeviceQueue
     from beta9_b200 import _lib as L

@@ -187,9 +187,9 @@ template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes,
     // B9_STATIC_ROUNDS=0 turns it off.
     static const bool allow_static = !(getenv("B9_STATIC_ROUNDS") && atoi(getenv("B9_STATIC_ROUNDS")) == 0);
     if (a.count_mode) {                                                    // cancelled slots in the window: ready-count prefix per warp-tile
-        const uint32_t warps = (a.n_tasks + 31u) / 32u;
-        tile_count_kernel<<<(warps * 32u + 255u) / 256u, 256, 0, s>>>(a.hdr, a.slot_mask, a.first_task, a.n_tasks, (uint32_t)T, (uint32_t*)a.tile_base);
-        tile_scan_kernel<<<1, 1024, 0, s>>>((uint32_t*)a.tile_base, a.n_tiles);
+        const uint32_t blocks = (a.n_tasks + TC_SLOTS - 1u) / TC_SLOTS;
+        tile_count_kernel<<<blocks, TC_SLOTS, 0, s>>>(a.hdr, a.slot_mask, a.first_task, a.n_tasks, (uint32_t)T, (uint32_t*)a.tile_base, (uint32_t*)a.block_base);
+        tile_scan_kernel<<<1, 1024, 0, s>>>((uint32_t*)a.block_base, blocks);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -520,7 +520,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     a.payload = c->d_payload; a.off = c->d_off; a.hdr = c->d_hdr; a.ids = c->d_ids; a.slot_mask = c->slot_mask;
     a.first_task = c->head_task; a.n_tasks = n; a.n_tiles = (n + TILE_TASKS - 1) / TILE_TASKS;
     a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_ids = c->d_out_ids;
-    a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.tile_base = (const uint32_t*)c->d_tile_state; a.handler = handler;
+    a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.tile_base = (const uint32_t*)c->d_tile_state; a.block_base = (const uint32_t*)c->d_tile_state + ((size_t)c->max_drain_tasks / D2_THREADS + 2); a.handler = handler;
     a.count_mode = c->cancelled_pending ? 1u : 0u;
     a.slow = c->d_slow; a.crc_shift_tabs = c->d_crc_shift;
     a.static_rounds = 0;

@@ -74,7 +74,8 @@ struct DrainArgs {
     // control
     DrainCtl* ctl;
     uint64_t* tile_state;           // v1: [n_tiles] look-back words, zeroed before launch
-    const uint32_t* tile_base;      // v2, count_mode: [n_tiles + 1] ready tasks before each warp-tile (tile_scan_kernel)
+    const uint32_t* tile_base;      // v2, count_mode: [n_tiles] ready tasks before each warp-tile inside its 256-slot block (tile_count_kernel)
+    const uint32_t* block_base;     // v2, count_mode: [n / 256 + 1] ready tasks before each 256-slot block (tile_scan_kernel); last = window total
     int handler;
     uint32_t count_mode;            // v2: 0 = no pending task is cancelled (record index = task index), 1 = record index from tile_base
     SlowItem* slow;                 // v2 identity: [n_tasks] work list for the second kernel

@@ -57,6 +57,15 @@ def parser():
         buf = C.create_string_buffer(64)
         n = lib.b9_host_rfc3339nano(ns, buf)               # (call first: `buf.raw` is a snapshot)
         return buf.raw[:n]
+    lib.b9_host_vadd_fast.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
+    lib.b9_host_vadd_fast.restype = C.c_long
+
+    def vadd_fast(b: bytes):
+        buf = C.create_string_buffer(len(b) + 64)
+        n = lib.b9_host_vadd_fast(b, len(b), buf, len(buf))
+        assert n >= -1, n                                # -2..-5: the fast path contradicted itself
+        return None if n < 0 else buf.raw[:n]
+    parse.vadd_fast = vadd_fast
     parse.run, parse.transcode, parse.rfc3339 = run, transcode, rfc3339
     return parse
 
@@ -179,3 +188,37 @@ def test_device_go_value_encoder_agrees_with_the_oracle(parser):
     for ns in (0, 1, 999_999_999, 1_000_000_000, 1_789_970_992_573_161_412, 1_709_210_096_000_000_000, 4_102_444_800_000_000_000,
                951_782_400_123_000_000, 1_718_000_000_120_000_000):
         assert parser.rfc3339(ns) == go_time_rfc3339nano(ns).encode(), ns
+
+
+def test_vadd_fast_path_agrees_with_the_oracle(parser):
+    """vadd_f32's branch-free, in-place fast path (vadd_fast.cuh) on the host: every float count 1..70 (all base64
+    phases of a, of b and of the padding), raw bit patterns (NaN payloads, inf - inf, denormals), every task
+    alignment; whatever it decides must be the oracle's bytes, and canonical payloads must be decided."""
+    from beta9_b200 import synth
+    payloads, canonical = [], 0
+    for fpv in list(range(1, 71)) + [100, 333]:
+        for b in (synth.vadd_batch(6, floats_per_vec=fpv, seed=fpv), synth.vadd_special_batch(6, floats_per_vec=fpv, seed=fpv)):
+            payloads += [b.task(i) for i in range(b.n)]
+    canonical = len(payloads)
+    rng = np.random.default_rng(5)
+    for p in list(payloads[::7]):                         # corrupted text: must be left to the sequential path or still be right
+        m = bytearray(p)
+        pos = int(rng.integers(11, len(m) - 17))
+        m[pos] = int(rng.choice(list(b"=!-_ \"\\\x7f\xc3")))
+        payloads.append(bytes(m))
+        m = bytearray(p); del m[pos]; payloads.append(bytes(m))
+    # expected bytes: the C oracle (it spells out "a NaN operand comes back quieted, the first one winning"; numpy, the
+    # reference's arithmetic, agrees except when BOTH operands are NaN, where its answer depends on the element's position
+    # in its SIMD loop: tests/test_oracle_c_vs_py.py::test_vadd_two_nan_operands)
+    from oracle import coracle
+    b = synth.from_payloads(payloads)
+    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "vadd_f32")
+    decided = 0
+    for i, p in enumerate(payloads):
+        got = parser.vadd_fast(p)
+        if got is None:
+            assert i >= canonical, p                      # a canonical payload must take the fast path
+            continue
+        decided += 1
+        assert int(o.status[i]) == 0 and got == o.result(i), (p, got, o.result(i))
+    assert decided >= canonical

@@ -43,10 +43,38 @@ def test_crc_zipf():
 def test_vadd():
     compare(synth.vadd_batch(2000), "vadd_f32")
     compare(synth.vadd_batch(300, floats_per_vec=5, seed=1), "vadd_f32")
-    # NaN payloads, infinities, denormals: the C restatement spells out the x86 rules, numpy (the
-    # reference's arithmetic, on this x86-64 host) is the judge
-    for fpv in (1, 2, 3, 32):
-        compare(synth.vadd_special_batch(400, floats_per_vec=fpv, seed=fpv), "vadd_f32")
+    # (NaN payloads, infinities, denormals: test_vadd_two_nan_operands)
+
+
+def test_vadd_two_nan_operands():
+    """What the reference's arithmetic (numpy `a + b` on this x86-64 host) leaves open: when BOTH operands of an
+    element are NaN, the quieted payload that survives is the first operand's inside numpy's SIMD body and the second's
+    in its scalar tail, i.e. it depends on the element's position and the vector length. Everything else — one NaN
+    operand, inf + -inf, denormals, overflow — is position-independent. The C oracle (and the device) always return the
+    first operand, quieted; this test pins exactly that much: equal to numpy everywhere except two-NaN elements, where
+    numpy's answer must be one of the two quieted operands."""
+    import base64
+    import json as _json
+    from oracle.pyoracle import handlers
+    two_nan = differing = 0
+    for fpv in list(range(1, 41)) + [64, 100]:
+        b = synth.vadd_special_batch(8, floats_per_vec=fpv, seed=1000 + fpv)
+        o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "vadd_f32")
+        for i in range(b.n):
+            s = _json.loads(b.task(i))["args"][0]
+            raw = np.frombuffer(base64.b64decode(s), "<u4")
+            n = raw.size // 2
+            x, y = raw[:n], raw[n:]
+            ref = np.frombuffer(base64.b64decode(handlers.vadd_f32(s)), "<u4")           # numpy
+            got = np.frombuffer(base64.b64decode(o.result(i)[1:-1]), "<u4")              # C oracle
+            xn, yn = (x & 0x7FFFFFFF) > 0x7F800000, (y & 0x7FFFFFFF) > 0x7F800000
+            both = xn & yn
+            assert np.array_equal(got[~both], ref[~both]), (fpv, i)
+            assert np.array_equal(got[both], x[both] | 0x00400000)
+            assert np.all((ref[both] == (x[both] | 0x00400000)) | (ref[both] == (y[both] | 0x00400000)))
+            two_nan += int(both.sum())
+            differing += int((got[both] != ref[both]).sum())
+    assert two_nan > 100            # (differing may be 0 on a host whose numpy has no scalar tail; here it is not)
 
 
 def test_json_sum():

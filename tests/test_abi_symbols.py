@@ -67,3 +67,28 @@ def test_no_device_fails_loudly(so_path):
     with pytest.raises(L.B9Error) as e:
         DeviceQueue()
     assert e.value.code == L.B9_ENODEV and "no CPU path" in str(e.value)
+
+
+def test_header_is_plain_c99_and_the_c_example_links(so_path, tmp_path):
+    """include/b9gpu.h must be usable from C (cgo compiles it as C): examples/c_api_demo.c under -std=c99 -pedantic
+    -Werror, then linked against the library. Without a GPU the program must stop at b9_ctx_create with the
+    "no CPU path" message; with one it prints three records."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "examples", "c_api_demo.c")
+    inc = os.path.join(root, "include")
+    r = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = str(tmp_path / "c_api_demo")
+    libdir = os.path.dirname(so_path)
+    r = subprocess.run([cc, "-std=c99", "-I" + inc, src, "-L" + libdir, "-lb9gpu", "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if r.returncode != 0:
+        assert "no CPU path" in r.stderr, r.stderr               # CPU-only host: fails loudly, as designed
+    else:
+        assert "hello" in r.stdout and "from an HTTP body" in r.stdout and "caf\\u00e9" in r.stdout, r.stdout

@@ -691,11 +691,15 @@ static int run_one(scratch_t *sc, const env_t *env, const uint8_t *id, const uin
     else {
         for (size_t i = 0; i < doc->n; i++) {
             val_t *k = doc->keys[i], *v = doc->items[i];
+            /* decode.go converts every number of a DECODED value and keeps the first conversion error (saveError):
+             * an overflow inside any occurrence of args / kwargs refuses the payload, whatever a later duplicate
+             * of the key does. Values of the wrong kind are skipped after the type error, unknown keys too. */
             if (fold_eq(k, "args")) {
-                if (v->t == T_NULL) args = NULL; else if (v->t == T_ARR) args = v; else type_err = 1;
+                if (v->t == T_NULL) args = NULL; else if (v->t == T_ARR) { args = v; if (has_overflow(v)) type_err = 1; } else type_err = 1;
             } else if (fold_eq(k, "kwargs")) {
                 if (v->t == T_NULL) kwargs = NULL;
                 else if (v->t == T_OBJ) {
+                    if (has_overflow(v)) type_err = 1;
                     if (!kwargs) kwargs = v;
                     else {  /* decoding into a non-nil map keeps existing entries: merge */
                         val_t *m = (val_t *)arena_alloc(ar, sizeof(val_t)); *m = *kwargs;

@@ -53,6 +53,9 @@ class _Parser:
     def __init__(self, data: bytes):
         self.d = data
         self.i = 0
+        # number literals ParseFloat refused (ErrRange), in source order. decode.go keeps the FIRST conversion error
+        # (saveError) and goes on; Unmarshal returns it at the end even if a later duplicate key overwrote the value.
+        self.overflows: List[str] = []
         self.n = len(data)
 
     def err(self, msg: str) -> GoJSONError:
@@ -190,6 +193,7 @@ class _Parser:
             # decode.go convertNumber: ParseFloat ErrRange -> UnmarshalTypeError{"number " + s}.
             # Only raised when the literal is actually stored (values under ignored struct keys
             # are skipped without conversion), so hand back a marker and let the caller decide.
+            self.overflows.append(text)
             return _Overflow(text)
         return f
 
@@ -311,7 +315,10 @@ def _decode_rune(d: bytes, i: int, n: int) -> Tuple[int, int]:
 
 def go_unmarshal(data: bytes) -> Any:
     """`json.Unmarshal(data, &v)` with `v interface{}`: dict / list / str / float / bool / None."""
-    v = _Parser(bytes(data)).parse_document()
+    p = _Parser(bytes(data))
+    v = p.parse_document()
+    if p.overflows:                 # anywhere in the document, overwritten by a duplicate key or not (decode.go saveError)
+        raise GoJSONError(f"json: cannot unmarshal number {p.overflows[0]} into Go value of type float64")
     _check_overflow(v)
     return v
 
@@ -345,17 +352,24 @@ def go_unmarshal_task_payload(data: bytes) -> Tuple[Optional[List[Any]], Optiona
     args: Optional[List[Any]] = None
     kwargs: Optional[Dict[str, Any]] = None
     type_err: Optional[str] = None
-    for key, val in _top_level_pairs(bytes(data)):
+    for key, val, overflowed in _top_level_pairs(bytes(data)):
         # exact match wins over folded match, but both names are distinct under folding, so a key
         # can match at most one field
-        if key == "args" or (key != "kwargs" and go_fold_equal(key, "args")):
+        is_args = key == "args" or (key != "kwargs" and go_fold_equal(key, "args"))
+        is_kwargs = not is_args and (key == "kwargs" or go_fold_equal(key, "kwargs"))
+        if (is_args or is_kwargs) and overflowed and isinstance(val, (list, dict)):
+            # a number inside a DECODED value failed to convert: the error is saved and returned at the end, whatever a
+            # later duplicate of the key does (decode.go literalInterface -> saveError). Values under unknown keys, and
+            # values of the wrong kind for the field (skipped after the type error), are never converted.
+            type_err = type_err or f"json: cannot unmarshal number {overflowed} into Go value of type float64"
+        if is_args:
             if val is None:
                 args = None
             elif isinstance(val, list):
                 args = val            # slice is re-filled from scratch
             else:
                 type_err = type_err or "json: cannot unmarshal into Go struct field TaskPayload.args of type []interface {}"
-        elif key == "kwargs" or go_fold_equal(key, "kwargs"):
+        elif is_kwargs:
             if val is None:
                 kwargs = None
             elif isinstance(val, dict):
@@ -373,7 +387,8 @@ def go_unmarshal_task_payload(data: bytes) -> Tuple[Optional[List[Any]], Optiona
 
 
 def _top_level_pairs(data: bytes):
-    """(key, value) pairs of the top-level object, in source order, duplicates kept."""
+    """(key, value, first overflowing number literal inside the value or None) of the top-level object, in source
+    order, duplicates kept."""
     p = _Parser(data)
     p.skip_ws()
     assert p.d[p.i] == 0x7B
@@ -387,8 +402,9 @@ def _top_level_pairs(data: bytes):
         p.skip_ws()
         p.i += 1  # ':'
         p.skip_ws()
+        seen = len(p.overflows)
         v = p.parse_value(1)
-        yield k, v
+        yield k, v, (p.overflows[seen] if len(p.overflows) > seen else None)
         p.skip_ws()
         c = p.d[p.i]
         p.i += 1

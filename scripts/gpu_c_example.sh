@@ -1,2 +1,2 @@
 set -x
-timeout 200 python -m pytest tests/test_gpu_c_example.py -m gpu -x -q 2>&1 | tail -5
+timeout 250 python -m pytest tests/test_gpu_parity.py tests/test_gpu_wire.py -m gpu -x -q -k "golden or handcrafted or wire" 2>&1 | tail -5

@@ -103,6 +103,10 @@ HANDCRAFTED = [
     b'{"args": ["AA=="]}', b'{"args": ["A==="]}', b'{"args": ["AAA"]}', b'{"args": ["AA\\nAA"]}', b'{"args": ["=AAA"]}',
     b'{"args": ["AAAAAAAAAAA="]}', b'{"args": ["AAAAAAAAAAAAAAAAAAAAAA=="]}', b'{"args": ["AB==AAAA"]}',
     b'{"args": ["A-AA"]}', b'{"args": ["\\u00e9AAA"]}', b'{"args": ["QUJDREVGR0g="]}', b'{"args": ["AAAAAAAAAAB="]}',
+    # a number that overflows float64 inside a DECODED value refuses the payload even if a later duplicate of the key
+    # overwrites it (decode.go keeps the first conversion error); under an unknown key it is never converted
+    b'{"args": [1e999], "args": ["x"]}', b'{"args": [{"k": 5e08858}], "\\u0061rgs": []}', b'{"kwargs": {"a": 1e999, "a": 1}, "args": ["x"]}',
+    b'{"args": ["x"], "kwargs": {"a": 1e999}, "kwargs": {"a": 2}}', b'{"args": ["x"], "other": 1e999, "other": 1}', b'{"args": 1e999, "args": ["x"]}',
 ]
 
 

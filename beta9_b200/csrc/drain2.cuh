@@ -8,12 +8,12 @@
 //   * a warp-tile's payload bytes are ONE contiguous range of the ring in the common case; lane 0
 //     pulls it into the warp's stage buffer with a single bulk async copy (cp.async.bulk / TMA 1-D,
 //     completion on the warp's mbarrier);
-//   * G lanes share a task (G = 2 for identity): 16-byte shared loads, SWAR classification of the
-//     string body, 16-byte global stores;
+//   * thread per task for identity and vadd_f32 (G = 1): 16-byte shared loads, SWAR classification of
+//     the string body, 16-byte global stores; the whole warp per task for crc32 and json_sum;
 //   * result RECORDS (id, status, has, offset, length) are FIFO-dense: record j belongs to the j-th
 //     ready task. When no pending task is cancelled (the host knows) j is plain arithmetic on the
-//     ticket; otherwise the per-tile ready counts — known from the slot words alone — go through a
-//     decoupled look-back;
+//     tile number; otherwise it is read from a ready-count prefix that two small kernels build from the
+//     slot flags ahead of the drain (tile_count_kernel / tile_scan_kernel): no tile ever waits on another;
 //   * result BYTES are placed by ONE atomicAdd per warp-tile on a byte cursor: dense, but in
 //     completion order (v1 chained the byte prefix through an in-order look-back; ncu showed the
 //     whole grid in lockstep behind it, 32 tiles resolved per L2 round trip — profiles/r1_v2a_*);
@@ -776,7 +776,7 @@ template <int HANDLER> struct D3Cfg {
     // with the whole warp, so its tiles are small: 4 tasks keep the stage buffer at ~5 KB, which leaves L1 room for the shift tables.
     static constexpr int T = (HANDLER == 1) ? 4 : (HANDLER == 3) ? 8 : 32 / G;
 };
-constexpr int D2_THREADS = 4;                // host: tasks per look-back slot (smallest warp-tile)
+constexpr int D2_THREADS = 4;                // host: the smallest warp-tile (sizes the per-tile count arrays)
 
 template <int T>
 struct D3Warp {

@@ -129,6 +129,15 @@ class _CallableWrapper:
         return [Task(id=str(i)) for i in ids]
 
     @staticmethod
+    def _format_args(args: Any) -> List[Any]:
+        """sdk/src/beta9/abstractions/function.py:246-251."""
+        if isinstance(args, tuple):
+            return list(args)
+        if not isinstance(args, list):
+            return [args]
+        return args
+
+    @staticmethod
     def _normalise(c: Any):
         if isinstance(c, tuple) and len(c) == 2 and isinstance(c[0], (tuple, list)) and isinstance(c[1], dict):
             return tuple(c[0]), c[1]
@@ -152,7 +161,9 @@ class _CallableWrapper:
     def map(self, inputs: Sequence[Any]) -> Iterator[Any]:
         """Fan out: one task per input, one push, one drain; yields each task's result (None for a task
         that failed or produced no result, as function.py:266-268 does)."""
-        tasks = self.put_batch(list(inputs))
+        # Function.map spreads each input as positional arguments after `_format_args` (function.py:246-251):
+        # a tuple or list IS the argument list, anything else is the single argument; never keyword arguments
+        tasks = self.put_batch([(tuple(self._format_args(x)), {}) for x in inputs])
         if len(tasks) != len(inputs):
             raise RuntimeError("Failed to enqueue tasks")
         done = {t.id: t for t in self.process_tasks(max_tasks=len(inputs))}

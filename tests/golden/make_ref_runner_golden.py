@@ -174,6 +174,15 @@ def main():
                 continue
             out["put"].setdefault(gname, {})[str(i)] = base64.b64encode(reference_put_payload(d["args"], d["kwargs"])).decode()
             n += 1
+    # Function.map's input formatting (sdk/src/beta9/abstractions/function.py:246-251), for the SDK mirror's map()
+    import beta9.abstractions.function as fn
+    samples = [{"t": "value", "v": 5}, {"t": "value", "v": "s"}, {"t": "tuple", "v": [1, 2]}, {"t": "list", "v": [3, 4]},
+               {"t": "tuple", "v": [[1], {"k": 2}]}, {"t": "value", "v": {"d": 1}}, {"t": "value", "v": None},
+               {"t": "tuple", "v": []}, {"t": "list", "v": []}, {"t": "tuple", "v": [[1, 2]]}, {"t": "list", "v": [[1, 2], 3]}]
+    out["format_args"] = []
+    for smp in samples:
+        x = tuple(smp["v"]) if smp["t"] == "tuple" else smp["v"]
+        out["format_args"].append({"in": smp, "out": fn._CallableWrapper._format_args(None, x)})
     path = os.path.join(ROOT, "tests", "golden", "ref_runner_golden.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)

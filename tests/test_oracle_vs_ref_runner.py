@@ -71,6 +71,16 @@ def test_put_payload_equals_the_reference_sdks(goldens):
     assert n >= 100
 
 
+def test_map_input_formatting_equals_the_reference_sdks(goldens):
+    """beta9_b200.taskqueue's map() spreads inputs like the reference's Function._format_args."""
+    from beta9_b200.taskqueue import _CallableWrapper
+    _, ref = goldens
+    assert len(ref["format_args"]) >= 10
+    for case in ref["format_args"]:
+        x = tuple(case["in"]["v"]) if case["in"]["t"] == "tuple" else case["in"]["v"]
+        assert _CallableWrapper._format_args(x) == case["out"], case
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/sdk/src"), reason="the reference checkout is not mounted here")
 def test_live_fuzz_against_the_reference_runner():
     """Where /root/reference exists (this container, not the GPU box): 1200 random SDK-style payloads

@@ -90,3 +90,33 @@ def test_map_yields_one_result_per_input():
         return 1998
     assert list(test_func.map([1, 2, 3])) == [1998, 1998, 1998]                # test_function.py:84-88
     assert q.push_batch.call_count == 1 and q.drain.call_count == 1
+
+
+def test_map_formats_inputs_like_function_format_args():
+    """function.py:246-251 `_format_args`: a tuple or a list IS the positional argument list, anything else is one
+    argument; `.map()` never produces keyword arguments — not even for an (args-looking, dict) pair."""
+    q = fake_queue()
+    seen = {}
+
+    def push(ids, blob, offsets, **kw):
+        off = np.asarray(offsets, dtype=np.int64)
+        raw = np.asarray(blob).tobytes()
+        seen["payloads"] = [json.loads(raw[off[i]:off[i + 1]]) for i in range(off.size - 1)]
+        seen["ids"] = ids.copy()
+    q.push_batch.side_effect = push
+
+    def drain(handler, max_tasks):
+        r = MagicMock()
+        r.n = seen["ids"].shape[0]; r.task_ids = seen["ids"]; r.status = np.zeros(r.n, np.uint8); r.result = lambda i: b"0"
+        return r
+    q.drain.side_effect = drain
+
+    @task_queue(queue=q, max_pending_tasks=100)
+    def f(*a):
+        return 0
+    inputs = [5, "s", (1, 2), [3, 4], ([1], {"k": 2}), {"d": 1}, None, (), []]
+    list(f.map(inputs))
+    assert seen["payloads"] == [
+        {"args": [5], "kwargs": {}}, {"args": ["s"], "kwargs": {}}, {"args": [1, 2], "kwargs": {}}, {"args": [3, 4], "kwargs": {}},
+        {"args": [[1], {"k": 2}], "kwargs": {}},            # two positional arguments, as the reference would pass them
+        {"args": [{"d": 1}], "kwargs": {}}, {"args": [None], "kwargs": {}}, {"args": [], "kwargs": {}}, {"args": [], "kwargs": {}}]

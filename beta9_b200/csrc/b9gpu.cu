@@ -24,6 +24,7 @@
 #include "drain_kernel.cuh"
 #include "drain2.cuh"
 #include "rebalance_plan.h"
+#include "ring_place.h"
 #include "wire_encode.cuh"
 
 #include <dlfcn.h>
@@ -55,7 +56,7 @@ struct Segment {             // one push = one contiguous byte range of the payl
 };
 
 constexpr uint64_t RING_SLACK = 256;   // readable bytes past the ring end (vector loads may over-read)
-constexpr uint64_t SEG_ALIGN  = 256;
+constexpr uint64_t SEG_ALIGN  = B9_SEG_ALIGN;
 
 }  // namespace
 
@@ -134,20 +135,11 @@ int task_phys_off(b9_ctx* c, const Segment& sg, uint64_t idx, uint64_t* out) {
     return B9_OK;
 }
 
-// where can a segment of `bytes` go? returns false when the ring cannot take it now
+// where can a segment of `bytes` go? returns false when the ring cannot take it now (ring_place.h)
 bool place_segment(b9_ctx* c, uint64_t bytes, uint64_t* start) {
-    uint64_t need = (bytes + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1);
-    if (need > c->ring_bytes) return false;
-    if (c->segs.empty()) { *start = 0; return true; }
-    uint64_t oldest = c->segs.front().phys_start;
-    uint64_t wp = c->write_pos;
-    if (wp >= oldest) {                      // live data is [oldest, wp)
-        if (wp + need <= c->ring_bytes) { *start = wp; return true; }
-        if (need <= oldest) { *start = 0; return true; }     // wrap, leaving the tail gap unused
-        return false;
-    }
-    if (wp + need <= oldest) { *start = wp; return true; }   // wrapped already: free is [wp, oldest)
-    return false;
+    uint64_t live = 0;
+    for (const Segment& sg : c->segs) live += sg.bytes;
+    return b9_ring_place(c->ring_bytes, !c->segs.empty(), c->segs.empty() ? 0 : c->segs.front().phys_start, c->write_pos, live, bytes, start) != 0;
 }
 
 template <int H> cudaError_t launch_drain(const DrainArgs& a, int grid, cudaStream_t s) {
@@ -815,13 +807,13 @@ int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     B9NcclId id; memcpy(id.internal, id128, 128);
+    if (c->nccl_comm) { nccl_comm_destroy(c->nccl_comm); c->nccl_comm = nullptr; }   // re-init: the old communicator is not leaked
     void* comm = nullptr;
     NC(g_nccl.CommInitRank(&comm, world, id, rank));
     c->nccl_comm = comm; c->comm_rank = rank; c->comm_world = world;
     // page-locked scratch for b9_rebalance's per-task bookkeeping, sized for a full slot ring, here and not on the first exchange
     if (world > 1 && c->h_scratch_words < 2 * (size_t)c->ring_tasks + 2) {
         if (c->h_scratch) cudaFreeHost(c->h_scratch);
-    cudaFree(c->d_xchg_send); cudaFree(c->d_xchg_recv);
         c->h_scratch = nullptr; c->h_scratch_words = 0;
         CU(cudaHostAlloc(&c->h_scratch, (2 * (size_t)c->ring_tasks + 2) * sizeof(uint64_t), cudaHostAllocDefault));
         c->h_scratch_words = 2 * (size_t)c->ring_tasks + 2;
@@ -887,7 +879,6 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     // (page-locked scratch: the 8 bytes per task travel at PCIe speed in both directions)
     if (c->h_scratch_words < 2 * n + 2) {
         if (c->h_scratch) cudaFreeHost(c->h_scratch);
-    cudaFree(c->d_xchg_send); cudaFree(c->d_xchg_recv);
         c->h_scratch = nullptr; c->h_scratch_words = 0;
         const size_t want = (size_t)(2 * n + 2) * 5 / 4;
         CU(cudaHostAlloc(&c->h_scratch, want * sizeof(uint64_t), cudaHostAllocDefault));

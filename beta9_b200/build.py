@@ -57,5 +57,22 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> str:
     return SO
 
 
+def build_variant(name: str, defines: List[str]) -> str:
+    """An alternative build for A/B timing on one box: ab_builds/<name>.so compiled with extra -D switches
+    (selected at run time with B9GPU_LIB=...). ab_builds/ is git-ignored but travels with gpurun."""
+    out_dir = os.path.join(ROOT, "ab_builds")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, name + ".so")
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:          # python -m beta9_b200.build --variant NAME [-DX=1 ...]
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv[i + 2:] if a.startswith("-D")]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose_ptxas="--ptxas-v" in sys.argv))

@@ -63,8 +63,6 @@ constexpr uint64_t SEG_ALIGN  = B9_SEG_ALIGN;
 struct b9_ctx {
     int device = 0;
     int sm_count = 0;
-    int resident_ctas = 0;             // drain kernel (v1) CTAs that fit per SM x SMs
-    int drain_version = 2;             // B9_DRAIN_KERNEL=1 selects the first-generation kernel (A/B checks)
     uint32_t stage_bytes_override = 0; // B9_STAGE_BYTES: force the v2 stage-buffer size
     cudaStream_t stream = nullptr;             // drain kernels + D2H
     cudaStream_t stream_in = nullptr;          // H2D + ingest kernel (so that pushes overlap drains: PCIe is full duplex)
@@ -97,7 +95,7 @@ struct b9_ctx {
     DrainCtl* d_ctl = nullptr; uint64_t* d_tile_state = nullptr;
     bool burst_open = false; cudaEvent_t ev_burst = nullptr;   // B9_DRAIN_ASYNC launches since the last completion: timed as one burst
     bool res_async = false;                    // the last launch returned before its kernels finished: finalize on fetch / sync
-    uint32_t res_async_n = 0; uint64_t res_async_in_bytes = 0; bool res_async_v2 = true;
+    uint32_t res_async_n = 0; uint64_t res_async_in_bytes = 0;
     DrainCtl* h_ctl = nullptr;                 // pinned
     uint8_t* d_xchg_send = nullptr; uint8_t* d_xchg_recv = nullptr; uint64_t xchg_send_cap = 0, xchg_recv_cap = 0;   // b9_rebalance staging, grow-only
     uint64_t* h_scratch = nullptr; size_t h_scratch_words = 0;   // pinned, grown on demand (b9_rebalance's slot words + byte prefix)
@@ -142,12 +140,7 @@ bool place_segment(b9_ctx* c, uint64_t bytes, uint64_t* start) {
     return b9_ring_place(c->ring_bytes, !c->segs.empty(), c->segs.empty() ? 0 : c->segs.front().phys_start, c->write_pos, live, bytes, start) != 0;
 }
 
-template <int H> cudaError_t launch_drain(const DrainArgs& a, int grid, cudaStream_t s) {
-    drain_kernel<H><<<grid, DRAIN_THREADS, 0, s>>>(a);
-    return cudaGetLastError();
-}
-
-// v2 (warp-autonomous): every warp owns a slice of dynamic shared memory = control block + one stage buffer.
+// every warp owns a slice of dynamic shared memory = control block + one stage buffer.
 template <int H> uint32_t drain3_warp_stride(uint32_t in_cap) {
     const size_t ctl = (sizeof(D3Warp<D3Cfg<H>::T>) + 127u) & ~(size_t)127u;
     return (uint32_t)(ctl + (((size_t)in_cap + 64u + 127u) & ~(size_t)127u));
@@ -291,12 +284,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     CUC(cudaMalloc(&c->d_count, sizeof(unsigned long long)));
     CUC(cudaHostAlloc(&c->h_ctl, sizeof(DrainCtl), cudaHostAllocDefault));
     CUC(cudaHostAlloc(&c->h_count, sizeof(unsigned long long), cudaHostAllocDefault));
-    int per_sm = 0;
-    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drain_kernel<0>, DRAIN_THREADS, 0));
-    if (per_sm < 1) per_sm = 1;
-    c->resident_ctas = per_sm * c->sm_count;
     c->stats.sm_count = (uint32_t)c->sm_count;
-    if (const char* v = getenv("B9_DRAIN_KERNEL")) c->drain_version = atoi(v) == 1 ? 1 : 2;
     if (const char* v = getenv("B9_STAGE_BYTES")) c->stage_bytes_override = ((uint32_t)atoi(v) + 1023u) & ~1023u;
 #undef CUC
     *out = c;
@@ -470,8 +458,7 @@ static int finish_launch(b9_ctx* c) {
     if (c->h_ctl->overflow)
         return fail(B9_ENOSPC, "b9_drain_launch: results exceed max_result_bytes (%llu); drain fewer tasks or enlarge the staging",
                     (unsigned long long)c->max_result_bytes);
-    if (c->res_async_v2) { c->res_bytes = c->h_ctl->bytes; c->res_n = c->h_ctl->total_cnt; }
-    else { c->res_bytes = c->h_ctl->total >> 24; c->res_n = (uint32_t)(c->h_ctl->total & 0xFFFFFFu); }
+    c->res_bytes = c->h_ctl->bytes; c->res_n = c->h_ctl->total_cnt;
     c->res_popped = c->res_async_n;
     c->res_in_bytes = c->res_async_in_bytes;
     c->have_results = true;
@@ -510,37 +497,28 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     }
     DrainArgs a{};
     a.payload = c->d_payload; a.off = c->d_off; a.hdr = c->d_hdr; a.ids = c->d_ids; a.slot_mask = c->slot_mask;
-    a.first_task = c->head_task; a.n_tasks = n; a.n_tiles = (n + TILE_TASKS - 1) / TILE_TASKS;
+    a.first_task = c->head_task; a.n_tasks = n; a.n_tiles = 0;             // (set per handler by launch_drain3)
     a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_ids = c->d_out_ids;
-    a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_state = c->d_tile_state; a.tile_base = (const uint32_t*)c->d_tile_state; a.block_base = (const uint32_t*)c->d_tile_state + ((size_t)c->max_drain_tasks / D2_THREADS + 2); a.handler = handler;
+    a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_base = (const uint32_t*)c->d_tile_state; a.block_base = (const uint32_t*)c->d_tile_state + ((size_t)c->max_drain_tasks / D2_THREADS + 2); a.handler = handler;
     a.count_mode = c->cancelled_pending ? 1u : 0u;
     a.slow = c->d_slow; a.crc_shift_tabs = c->d_crc_shift;
-    a.static_rounds = 0;
+    a.static_rounds = 0; a.one = 1u;
     cudaStream_t s = c->stream;
-    const bool v2 = c->drain_version == 2;
-    if (v2) a.n_tiles = (n + D2_THREADS - 1) / D2_THREADS;     // upper bound over the handlers' warp-tile sizes (state array memset)
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
-    if (!v2) CU(cudaMemsetAsync(c->d_tile_state, 0, (size_t)a.n_tiles * sizeof(uint64_t), s));   // v1's look-back words (v2 writes its tile prefix itself)
-    int grid = (int)std::min<uint32_t>(a.n_tiles, (uint32_t)c->resident_ctas);
+    int grid = 0;
     if (!c->burst_open) CU(cudaEventRecord(c->ev_burst, s));
     CU(cudaEventRecord(c->ev_a, s));
     cudaError_t le;
-    if (v2) {
-        switch (handler) {
-        case B9_H_IDENTITY: le = launch_drain3<0>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
-        case B9_H_CRC32:    le = launch_drain3<1>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
-        case B9_H_VADD_F32: le = launch_drain3<2>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
-        default:            le = launch_drain3<3>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
-        }
-    } else switch (handler) {
-    case B9_H_IDENTITY: le = launch_drain<0>(a, grid, s); break;
-    case B9_H_CRC32:    le = launch_drain<1>(a, grid, s); break;
-    case B9_H_VADD_F32: le = launch_drain<2>(a, grid, s); break;
-    default:            le = launch_drain<3>(a, grid, s); break;
+    switch (handler) {
+    case B9_H_IDENTITY: le = launch_drain3<0>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
+    case B9_H_CRC32:    le = launch_drain3<1>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
+    case B9_H_VADD_F32: le = launch_drain3<2>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
+    default:            le = launch_drain3<3>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
     }
     if (le != cudaSuccess) return fail(B9_EIO, "drain kernel launch failed: %s", cudaGetErrorString(le));
-    c->stats.kernel_launches += (v2 && a.count_mode) ? 3 : 1;              // (+ tile_count_kernel and tile_scan_kernel)
-    if (v2 && handler == B9_H_IDENTITY) {
+    c->stats.kernel_launches += a.count_mode ? 3 : 1;                      // (+ tile_count_kernel and tile_scan_kernel)
+    static const bool dbg_skip_slow = getenv("B9_DEBUG_SKIP_SLOW") != nullptr;   // timing experiments only: deferred tasks get no record
+    if (handler == B9_H_IDENTITY && !dbg_skip_slow) {
         // second kernel: the tasks the main identity kernel deferred (escaped strings, foreign framing, ...)
         static int slow_per_sm = 0;
         if (!slow_per_sm) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slow_per_sm, drain_slow_kernel, DS_WARPS * 32, 0) != cudaSuccess || slow_per_sm < 1) slow_per_sm = 4; }
@@ -558,7 +536,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     CU(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(DrainCtl), cudaMemcpyDeviceToHost, s));
     c->stats.last_drain_tiles = (n + 127) / 128;   // (reported in units of 128 tasks)
     c->stats.drains++;
-    c->res_async = true; c->res_async_n = n; c->res_async_in_bytes = in_bytes; c->res_async_v2 = v2;
+    c->res_async = true; c->res_async_n = n; c->res_async_in_bytes = in_bytes;
     if (peek & B9_DRAIN_ASYNC) { c->burst_open = true; return (int64_t)n; }   // records = n minus the cancelled slots: known after b9_sync / b9_drain_fetch
     int rc = finish_launch(c);
     return rc ? rc : (int64_t)c->res_n;

@@ -26,6 +26,7 @@
 // Reference behaviour realised: see drain_kernel.cuh's header (pop, decode, loads, call, result).
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 #include "drain_kernel.cuh"
 #include "vadd_fast.cuh"
 
@@ -56,12 +57,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // any byte of the four words outside printable ASCII, or equal to '"' or '\\'?
 // Exactness: a false positive can only occur in a group that also holds a byte >= 0x80, which is
 // "special" anyway (carries out of a byte need a byte >= 0x80 / 0xA0 below them).
-__device__ __forceinline__ bool swar_special16(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+// `one` is the integer 1 as a run-time value (DrainArgs.one): x * one + K is an IMAD on the FMA pipe, where x + K would
+// be an IADD3 on the ALU pipe with all the logic ops — the scan is ALU-pipe bound (profiles/r2_s1_*), and the two pipes
+// issue independently (B9_SWAR_IMAD=0 keeps plain adds for A/B timing).
+#ifndef B9_SWAR_IMAD
+#define B9_SWAR_IMAD 0
+#endif
+__device__ __forceinline__ uint32_t add_k(uint32_t x, uint32_t k, uint32_t one) {
+#if B9_SWAR_IMAD
+    return x * one + k;
+#else
+    (void)one; return x + k;
+#endif
+}
+__device__ __forceinline__ bool swar_special16(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t one) {
     const uint32_t K1 = 0x01010101u, K60 = 0x60606060u, K7F = 0x7F7F7F7Fu, Q = 0x22222222u, S = 0x5C5C5C5Cu, H = 0x80808080u;
-    uint32_t hi = (x | y | z | w) | ((x + K1) | (y + K1) | (z + K1) | (w + K1));          // >= 0x7F
-    uint32_t lo = (x + K60) & (y + K60) & (z + K60) & (w + K60);                          // bit7 clear: < 0x20
-    uint32_t eq = ((x ^ Q) + K7F) & ((y ^ Q) + K7F) & ((z ^ Q) + K7F) & ((w ^ Q) + K7F)   // bit7 clear: == '"'
-                & ((x ^ S) + K7F) & ((y ^ S) + K7F) & ((z ^ S) + K7F) & ((w ^ S) + K7F);  //            == '\\'
+    uint32_t hi = (x | y | z | w) | (add_k(x, K1, one) | add_k(y, K1, one) | add_k(z, K1, one) | add_k(w, K1, one));          // >= 0x7F
+    uint32_t lo = add_k(x, K60, one) & add_k(y, K60, one) & add_k(z, K60, one) & add_k(w, K60, one);                          // bit7 clear: < 0x20
+    uint32_t eq = add_k(x ^ Q, K7F, one) & add_k(y ^ Q, K7F, one) & add_k(z ^ Q, K7F, one) & add_k(w ^ Q, K7F, one)           // bit7 clear: == '"'
+                & add_k(x ^ S, K7F, one) & add_k(y ^ S, K7F, one) & add_k(z ^ S, K7F, one) & add_k(w ^ S, K7F, one);          //            == '\\'
     return ((hi | ~lo | ~eq) & H) != 0;
 }
 __device__ __forceinline__ bool byte_special(uint32_t c) { return c < 0x20u || c >= 0x7Fu || c == '"' || c == '\\'; }
@@ -78,7 +92,7 @@ __device__ __forceinline__ uint32_t byte_range_mask(uint32_t word, uint32_t lo, 
 // clean, identical on all G lanes. Must be called by all 32 lanes of the warp (`active` masks the
 // loads of lanes whose task does not exist).
 template <int G>
-__device__ __forceinline__ uint32_t quick_clean_framed(const uint8_t* __restrict__ p, uint32_t len, int sub, bool active) {
+__device__ __forceinline__ uint32_t quick_clean_framed(const uint8_t* __restrict__ p, uint32_t len, int sub, bool active, uint32_t one) {
     uint32_t bad_frame = 0, special = 0;
     if (active && len >= FRAME_PRE_LEN + FRAME_SUF_LEN) {
         // frame: 11 + 17 bytes compared as 32-bit words ("{\"ar" "gs\":" " [\""  /  "\"], " "\"kwa" "rgs\"" ": {}" "}")
@@ -113,7 +127,7 @@ __device__ __forceinline__ uint32_t quick_clean_framed(const uint8_t* __restrict
                 m = byte_range_mask(2, lo, hi); v.z = (v.z & m) | (A & ~m);
                 m = byte_range_mask(3, lo, hi); v.w = (v.w & m) | (A & ~m);
             }
-            special |= swar_special16(v.x, v.y, v.z, v.w) ? 1u : 0u;
+            special |= swar_special16(v.x, v.y, v.z, v.w, one) ? 1u : 0u;
         }
     } else bad_frame = 1;
     uint32_t bits = bad_frame | (special << 1);
@@ -778,14 +792,21 @@ template <int HANDLER> struct D3Cfg {
 };
 constexpr int D2_THREADS = 4;                // host: the smallest warp-tile (sizes the per-tile count arrays)
 
+// Tables of the coalesced tile copy (d3_copy_tile): which copied task does an aligned 16-byte vector of the
+// tile's output start in, and where do its bytes sit in the stage buffer. Only thread-per-task handlers copy.
+struct D3CopyTab {
+    alignas(16) uint4 ent[33];     // per copied task r: {first output byte, end, source offset - output offset, the same of task r+1}
+    uint2 bp[32];                  // per block of 32 vectors: {bit v set = some task r >= 1 starts in vector v, tasks started before the block}
+};
+struct D3NoTab {};
 template <int T>
 struct D3Warp {
     uint64_t goff[T];              // physical ring offset of each task's payload
     uint32_t soff[T];              // offset inside the stage buffer (when staged)
     uint32_t len[T];
     uint8_t  flg[T];               // slot flags (B9_TF_*)
-    uint32_t esc_info[2][32];      // per-lane chunk sizes of up to two escaped strings (phase A -> phase B)
     alignas(8) uint64_t mbar;
+    typename std::conditional<T == 32, D3CopyTab, D3NoTab>::type ct;
 };
 
 struct D3MetaRegs { uint64_t off, hdr; };
@@ -875,7 +896,9 @@ __device__ __noinline__ uint32_t d3_stage_scattered(const DrainArgs& a, uint64_t
 
 // out-of-line generic-pointer versions for tiles that could not be staged (and other cold paths)
 template <int G>
-__device__ __noinline__ uint32_t quick_clean_framed_generic(const uint8_t* p, uint32_t len, int sub, bool active) { return quick_clean_framed<G>(p, len, sub, active); }
+__device__ __noinline__ uint32_t quick_clean_framed_generic(const uint8_t* p, uint32_t len, int sub, bool active) { return quick_clean_framed<G>(p, len, sub, active, 1u); }
+template <int G>
+__device__ __noinline__ void group_copy_staged(uint8_t* dst, const uint8_t* src, uint32_t n, int sub) { group_copy<G>(dst, src, n, sub); }   // (tiles the coalesced copy does not take)
 template <int G>
 __device__ __noinline__ void group_copy_generic(uint8_t* dst, const uint8_t* src, uint32_t n, int sub) { group_copy<G>(dst, src, n, sub); }
 
@@ -888,6 +911,233 @@ template <int HANDLER>
 __device__ __noinline__ void d2_parse_and_size(const uint8_t* p, uint32_t len, TaskRec& rec, const uint32_t* crc_table, bool http) {
     Parsed pr = parse_payload(p, len, http);
     handler_phase_a(HANDLER, p, pr, rec, crc_table);
+}
+
+// ------------------------------------------------------------------ coalesced tile copy
+// The results of a warp-tile are ONE dense byte range of the output (a single cursor add), and when every
+// result is a plain copy out of the stage buffer (identity's clean strings, vadd_f32's in-place records) that
+// range is written by the warp as a whole: lane l stores the aligned 16-byte vectors l, l + 32, ... of the
+// range (a store instruction covers 512 contiguous bytes = 4 lines, where one thread per task at a 258-byte
+// stride touched 32 lines: the LSU, not HBM, bounded the round-1 kernel — profiles/r1_final_identity_main_summary.txt).
+// A vector starts inside exactly one copied task t (entries are >= 16 bytes, so it ends in t or t + 1):
+//   t(v) = #{r >= 1 : first byte of r <= 16 v}  =  prefix-popcount of a bitmap with bit ceil(ex_r / 16) set,
+// one bitmap word per block of 32 vectors, word prefixes by one warp scan. The 16 source bytes come from two
+// aligned 16-byte shared loads + a byte shift. Vectors that cross into the next task are left to one extra
+// pass (lane r: the vector around the end of task r).
+__device__ __forceinline__ uint4 lds128(const uint8_t* p) { return *(const uint4*)p; }
+// 16 bytes at byte offset `at` (any alignment) of the stage buffer
+__device__ __forceinline__ uint4 ld_unaligned16(const uint8_t* __restrict__ sbuf, uint32_t at) {
+    const uint32_t s = at & 15u, q = s >> 2, bits = (s & 3u) * 8u;
+    const uint4 a = lds128(sbuf + (at - s)), b = lds128(sbuf + (at - s) + 16);
+    uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+    if (q & 2u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7; }
+    if (q & 1u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+    uint4 o;
+    o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
+    o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
+    return o;
+}
+constexpr uint32_t D3_COPY_MAX_BYTES = 16384;      // 32 bitmap words x 32 vectors x 16 bytes
+
+// All 32 lanes. c_len = bytes my task contributes (0: none), ex = their offset in the tile's range, src = their
+// offset in the stage buffer; tb = bytes of the range; out = its (16-byte aligned) address. Preconditions,
+// checked by the caller: every non-zero c_len >= 16, tb <= D3_COPY_MAX_BYTES, the range is padded to 16 bytes.
+__device__ __forceinline__ void d3_copy_tile(D3CopyTab& C, const uint8_t* __restrict__ sbuf, uint8_t* __restrict__ out,
+                                             uint32_t c_len, uint32_t ex, uint32_t src, uint32_t tb, int lane) {
+    const uint32_t nz = __ballot_sync(0xffffffffu, c_len != 0u);
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t r = __popc(nz & lt), cnt = __popc(nz);
+    const uint32_t nblk = (tb + 511u) >> 9;
+    const uint32_t delta = src - ex;
+    const uint32_t above = nz & ~lt & ~(1u << lane);
+    const uint32_t delta_next = __shfl_sync(0xffffffffu, delta, above ? (__ffs(above) - 1) : lane);
+    if ((uint32_t)lane < nblk) C.bp[lane] = make_uint2(0u, 0u);
+    __syncwarp();
+    if (c_len) {
+        C.ent[r] = make_uint4(ex, above ? ex + c_len : 0xFFFFFFFFu, delta, delta_next);   // (the last task owns the padding)
+        if (r) { const uint32_t fv = (ex + 15u) >> 4; atomicOr(&C.bp[fv >> 5].x, 1u << (fv & 31u)); }
+    }
+    __syncwarp();
+    {
+        const uint32_t mine = (uint32_t)lane < nblk ? (uint32_t)__popc(C.bp[lane].x) : 0u;
+        const uint32_t before = warp_excl_scan(mine, lane);
+        if ((uint32_t)lane < nblk) C.bp[lane].y = before;
+    }
+    __syncwarp();
+    const uint32_t le = lt | (1u << lane);
+    #pragma unroll 2
+    for (uint32_t i = 0; i < nblk; ++i) {
+        const uint32_t o = (i << 9) + ((uint32_t)lane << 4);
+        if (o < tb) {
+            const uint2 bp = C.bp[i];
+            const uint4 e = C.ent[bp.y + __popc(bp.x & le)];
+            if (e.y - o >= 16u) *(uint4*)(out + o) = ld_unaligned16(sbuf, o + e.z);
+        }
+    }
+    if ((uint32_t)lane + 1u < cnt) {                                       // the vector around the end of task `lane` (by rank)
+        const uint4 e = C.ent[lane];
+        const uint32_t keep = e.y & 15u;                                   // its first `keep` bytes are this task's, the rest the next one's
+        if (keep) {
+            const uint32_t o = e.y - keep;
+            const uint4 a = ld_unaligned16(sbuf, o + e.z), b = ld_unaligned16(sbuf, o + e.w);
+            uint4 v; uint32_t m;
+            m = byte_range_mask(0, 0, keep); v.x = (a.x & m) | (b.x & ~m);
+            m = byte_range_mask(1, 0, keep); v.y = (a.y & m) | (b.y & ~m);
+            m = byte_range_mask(2, 0, keep); v.z = (a.z & m) | (b.z & ~m);
+            m = byte_range_mask(3, 0, keep); v.w = (a.w & m) | (b.w & ~m);
+            *(uint4*)(out + o) = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ identity: escaped strings, settled in the main loop
+// configs[1]'s 1 % "adversarial" share are strings json.dumps had to escape. Whatever json.dumps wrote comes back
+// from identity as the very same text (Go decodes, Python re-encodes), with ONE exception: a lone surrogate escape
+// becomes � (Go's decoder, oracle/pyoracle/gojson.py:212-264). So the warp does not transcode such a body, it
+// VERIFIES that every escape is one json.dumps writes — and then the task is a plain copy like its clean neighbours:
+//   * lane r owns bytes [16r, 16r+16) of a 512-byte pass; backslash and quote positions as 16-bit masks
+//     (exact SWAR equality + a multiply that gathers the four byte flags of a word into a nibble);
+//   * which backslashes START an escape: the odd-backslash-run rule (simdjson's find_escaped) per lane, the carry
+//     ("my first byte is escaped") resolved across lanes with two ballots — a lane's carry-out is constant or its
+//     carry-in XOR a constant, so the carry into lane r is a parity over the lanes above the last constant one;
+//   * one step per escape start: the two-character escapes json.dumps writes, or \uXXXX with lower-case hex and a
+//     value json.dumps would write that way (control characters without a short form, DEL, >= 0x80); surrogate
+//     escapes are paired by looking 6 bytes ahead / behind, lone ones are rewritten to � in the stage buffer.
+// Anything else (raw non-ASCII, "\/", upper-case hex, malformed text) is NOT decided here: the task goes to
+// drain_slow_kernel as before. The rule set has a Python model fuzzed against the oracle on the CPU
+// (tests/esc_verify_model.py, tests/test_esc_verify_model.py).
+__device__ __forceinline__ uint32_t eq_mask32(uint32_t w, uint32_t k4) {           // 0x80 in every byte of w equal to the byte of k4 (exact)
+    const uint32_t z = w ^ k4;
+    return ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t gather4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }   // byte flags (bit 7) -> 4 bits
+__device__ __forceinline__ uint32_t eq_bits16(const uint4& v, uint32_t k4) {
+    return gather4(eq_mask32(v.x, k4)) | (gather4(eq_mask32(v.y, k4)) << 4) | (gather4(eq_mask32(v.z, k4)) << 8) | (gather4(eq_mask32(v.w, k4)) << 12);
+}
+// 16 positions, the first cnt of them real bytes: the escaped ones (they follow an escape-start backslash); *cout = the real
+// bytes end on an unmatched escape start
+__device__ __forceinline__ uint32_t esc16(uint32_t bs, uint32_t cin, uint32_t cnt, uint32_t* cout) {
+    bs &= ~cin;
+    const uint32_t follows = ((bs << 1) | cin) & 0xFFFFu;
+    const uint32_t odd_starts = bs & 0xAAAAu & ~follows;
+    const uint32_t seq_even = odd_starts + bs;                             // 17 bits
+    const uint32_t escaped = (0x5555u ^ (seq_even << 1)) & follows;
+    *cout = cnt < 16u ? (escaped >> cnt) & 1u : (seq_even >> 16) & 1u;
+    return escaped;
+}
+// four hex digits given as a little-endian word -> their value, or -1 (SWAR, no loads)
+__device__ __forceinline__ int hex4w(uint32_t w) {
+    const uint32_t H = 0x80808080u;
+    const uint32_t x = w & 0x7F7F7F7Fu, y = x | 0x20202020u;
+    const uint32_t isd = ((x + 0x50505050u) & ~(x + 0x46464646u)) & H;    // '0' <= x <= '9'
+    const uint32_t isl = ((y + 0x1F1F1F1Fu) & ~(y + 0x19191919u)) & H;    // 'a' <= (x | 0x20) <= 'f'
+    const uint32_t nib = (x & 0x0F0F0F0Fu) + (isl >> 7) * 9u;
+    const int v = (int)(((nib & 0xFu) << 12) | (((nib >> 8) & 0xFu) << 8) | (((nib >> 16) & 0xFu) << 4) | (nib >> 24));
+    return ((isd | isl) != H || (w & H)) ? -1 : v;
+}
+
+// All 32 lanes; the body is sbuf[at, at + n) (stage buffer), `list` is scratch for 256 16-bit positions. true:
+// json.dumps(identity(body)) is the body text as it now stands in the stage buffer (lone surrogates rewritten). false:
+// not decided. The escape starts of a pass are first compacted into `list` (prefix sum over the lanes' counts), then
+// lane l classifies escapes l, l + 32, ... with straight-line code: the work is balanced over the warp however the
+// escapes cluster, and no lane walks a chain of dependent byte loads.
+__device__ __noinline__ bool esc_verify_canonical(uint8_t* __restrict__ sbuf, uint32_t at, uint32_t n, int lane, uint16_t* __restrict__ list) {
+    uint8_t* const body = sbuf + at;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t carry = 0;
+    for (uint32_t base0 = 0; base0 < n; base0 += 512u) {
+        const uint32_t base = base0 + 16u * (uint32_t)lane;
+        const uint32_t cnt = base < n ? min(16u, n - base) : 0u;
+        const uint32_t A = 0x61616161u;
+        uint4 v = make_uint4(A, A, A, A);
+        if (cnt) {
+            v = ld_unaligned16(sbuf, at + base);
+            if (cnt < 16u) {
+                uint32_t m;
+                m = byte_range_mask(0, 0, cnt); v.x = (v.x & m) | (A & ~m);
+                m = byte_range_mask(1, 0, cnt); v.y = (v.y & m) | (A & ~m);
+                m = byte_range_mask(2, 0, cnt); v.z = (v.z & m) | (A & ~m);
+                m = byte_range_mask(3, 0, cnt); v.w = (v.w & m) | (A & ~m);
+            }
+        }
+        // raw control bytes are not JSON; DEL and non-ASCII are escaped by json.dumps: neither is settled here
+        const uint32_t K1 = 0x01010101u, K60 = 0x60606060u;
+        const uint32_t hi = (v.x | v.y | v.z | v.w) | ((v.x + K1) | (v.y + K1) | (v.z + K1) | (v.w + K1));
+        const uint32_t lo = (v.x + K60) & (v.y + K60) & (v.z + K60) & (v.w + K60);
+        bool ok = ((hi | ~lo) & 0x80808080u) == 0u;
+        const uint32_t bs = eq_bits16(v, 0x5C5C5C5Cu), qt = eq_bits16(v, 0x22222222u);
+        uint32_t o0, o1;
+        esc16(bs, 0u, cnt, &o0); esc16(bs, 1u, cnt, &o1);
+        const uint32_t Kd = __ballot_sync(0xffffffffu, o0 != o1);           // lanes whose carry-out depends on their carry-in
+        const uint32_t V0 = __ballot_sync(0xffffffffu, o0 != 0u);
+        const uint32_t below = ~Kd & lt;
+        const uint32_t cin = below ? (uint32_t)__popc(V0 & lt & ~((1u << (31 - __clz(below))) - 1u)) & 1u : ((uint32_t)__popc(V0 & lt) & 1u) ^ carry;
+        const uint32_t fixed = ~Kd;
+        const uint32_t next_carry = fixed ? (uint32_t)__popc(V0 & ~((1u << (31 - __clz(fixed))) - 1u)) & 1u : ((uint32_t)__popc(V0) & 1u) ^ carry;
+        uint32_t co;
+        const uint32_t escaped = esc16(bs, cin, cnt, &co);
+        if (qt & ~escaped) ok = false;                                       // a raw quote inside the body
+        uint32_t starts = bs & ~cin & ~escaped;
+        // ---- compact the escape starts of the pass
+        const uint32_t mine_n = (uint32_t)__popc(starts);
+        uint32_t slot = warp_excl_scan(mine_n, lane);
+        const uint32_t total = __shfl_sync(0xffffffffu, slot + mine_n, 31);
+        while (starts) { list[slot++] = (uint16_t)(base - base0 + (uint32_t)(__ffs(starts) - 1)); starts &= starts - 1u; }
+        __syncwarp();
+        // ---- one escape per lane and round
+        uint32_t patch_rounds = 0;
+        for (uint32_t e0 = 0, round = 0; e0 < total; e0 += 32u, ++round) {
+            const uint32_t e = e0 + (uint32_t)lane;
+            if (e < total) {
+                const uint32_t i = base0 + list[e];
+                // bytes [i-8, i) and [i, i+12): the frame's 11-byte prefix precedes the body and its 17-byte suffix follows it
+                const uint32_t sa = at + i - 8u, mis = sa & 3u;
+                const uint32_t* wp = (const uint32_t*)(sbuf + (sa - mis));
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4], w5 = wp[5];
+                const uint32_t sh = mis * 8u;
+                const uint32_t P0 = __funnelshift_r(w0, w1, sh), P1 = __funnelshift_r(w1, w2, sh);           // i-8 .. i-1
+                const uint32_t F0 = __funnelshift_r(w2, w3, sh), F1 = __funnelshift_r(w3, w4, sh), F2 = __funnelshift_r(w4, w5, sh);   // i .. i+11
+                const uint32_t t = (F0 >> 8) & 0xFFu;
+                const uint32_t d = t - 0x5Cu;
+                const bool simple = t == '"' || (d < 32u && ((0x01440441u >> d) & 1u));   // \\ b f n r t
+                const uint32_t hw = (F0 >> 16) | (F1 << 16);                                // i+2 .. i+5
+                const int h = hex4w(hw);
+                bool good;
+                bool lone = false;
+                if (t != 'u') good = simple;
+                else {
+                    good = i + 6u <= n && h >= 0 && !hex_has_upper(hw)
+                           && !(h < 0x20 && ((0x3700u >> h) & 1u))                          // \b \t \n \f \r have short forms
+                           && !(h >= 0x20 && h < 0x7F);                                     // json.dumps writes the character itself
+                    if (h >= 0xD800 && h < 0xDC00) {                                        // high surrogate: paired with a low-surrogate escape right behind it?
+                        const int l2 = hex4w(F2);                                           // i+8 .. i+11
+                        lone = !(i + 12u <= n && (F1 >> 16) == 0x755Cu && l2 >= 0xDC00 && l2 <= 0xDFFF);
+                    } else if (h >= 0xDC00 && h < 0xE000) {                                 // low surrogate: consumed by a high-surrogate escape 6 bytes before?
+                        const int h2 = hex4w(P1);                                           // i-4 .. i-1
+                        lone = true;
+                        if (i >= 6u && (P0 >> 16) == 0x755Cu && h2 >= 0xD800 && h2 <= 0xDBFF) {
+                            // ... if the backslash at i-6 starts an escape: an even run of backslashes before it
+                            uint32_t run = 0;
+                            if (i >= 7u && ((P0 >> 8) & 0xFFu) == '\\') run = bs_run_before(body, i - 6u);
+                            lone = (run & 1u) != 0u;
+                        }
+                    }
+                }
+                if (!good) ok = false;
+                if (lone) patch_rounds |= 1u << round;
+            }
+        }
+        if (!__all_sync(0xffffffffu, ok)) return false;
+        carry = next_carry;
+        while (patch_rounds) {
+            const uint32_t round = (uint32_t)(__ffs(patch_rounds) - 1);
+            patch_rounds &= patch_rounds - 1u;
+            uint8_t* o = body + base0 + list[round * 32u + (uint32_t)lane] + 2u;
+            o[0] = 'f'; o[1] = 'f'; o[2] = 'f'; o[3] = 'd';
+        }
+        __syncwarp();
+    }
+    return carry == 0u;
 }
 
 template <int HANDLER>
@@ -914,6 +1164,13 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
     }
     if (lane == 0) { mbar_init(&W.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
+#ifndef B9_PDL_EARLY
+#define B9_PDL_EARLY 1
+#endif
+    // identity's second kernel is launched with programmatic stream serialization: let its CTAs take the places of this
+    // grid's CTAs as they retire (they block in griddepcontrol.wait until this grid has completed), instead of
+    // being launched only then
+    if (HANDLER == 0 && B9_PDL_EARLY) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // two tickets ahead: the slot words of the next tile are in registers when its turn comes, and
     // the ticket after that is in flight; nothing global sits between the end of a tile and the bulk
@@ -990,7 +1247,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             // json.dumps); everything else is handed to drain_slow_kernel through the work list, so that
             // this loop stays small enough for the instruction cache and no worker stalls on a 1 % case
             uint32_t q;
-            if (staged) q = quick_clean_framed<G>(sbuf + my_soff, my_len, sub, mine);
+            if (staged) q = quick_clean_framed<G>(sbuf + my_soff, my_len, sub, mine, a.one);
             else        q = quick_clean_framed_generic<G>(a.payload + my_goff, my_len, sub, mine);
             if (mine) {
                 if (q == 3u) {
@@ -998,6 +1255,20 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                     if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
                 } else { rec.mode = OM_DEFER; rec.value = (long long)(q & 1u); }
                 if (my_http) { rec.has = 0; rec.out_len = 0; rec.mode = OM_DEFER; rec.value = 0; }   // an HTTP body: the map rules decide (second kernel)
+            }
+            if constexpr (HANDLER == 0 && T == 32) {
+                // framed, but the body holds escapes: the warp checks that they are json.dumps's own (then the task is a copy after all)
+                uint32_t dirty = staged ? __ballot_sync(0xffffffffu, mine && rec.mode == OM_DEFER && rec.value == 1) : 0u;
+                while (dirty) {
+                    const int kt = __ffs(dirty) - 1;
+                    dirty &= dirty - 1u;
+                    const uint32_t ln = W.len[kt];
+                    const bool canon = esc_verify_canonical(sbuf, W.soff[kt] + FRAME_PRE_LEN, ln - FRAME_PRE_LEN - FRAME_SUF_LEN, lane, (uint16_t*)W.ct.ent);
+                    if (canon && lane == kt) {
+                        const uint32_t tok = ln - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
+                        rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; rec.value = 0;
+                    }
+                }
             }
         } else if (HANDLER == 1) {
             // crc32: the whole warp works on one task at a time (tasks are long and of very different lengths)
@@ -1046,11 +1317,22 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         const uint32_t tb = __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
         const uint32_t ex_bytes = __shfl_sync(0xffffffffu, ex_bytes0, k * G);      // every lane of a task sees the task's offset
         const uint32_t ex_cnt = __popc(ready_mask_t & ((1u << k) - 1u));
+        // thread-per-task handlers reserve whole 16-byte units, so that every tile's range starts on a vector
+        // boundary (the coalesced copy below); the <= 15 bytes of padding per tile are never referenced by a record
+        constexpr bool COAL = (T == 32 && G == 1);
+        const uint32_t tb_alloc = COAL ? ((tb + 15u) & ~15u) : tb;
         unsigned long long base = 0;
-        if (lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb);
+        if (lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb_alloc);
         base = __shfl_sync(0xffffffffu, base, 0);
-        const bool fits = base + tb <= a.out_cap;
+        const bool fits = base + tb_alloc <= a.out_cap;
         if (!fits && lane == 0) a.ctl->overflow = 1u;
+        bool coal = false;
+        if constexpr (COAL) {
+            const uint32_t c_len = (mine && rec.has && rec.mode == OM_COPY) ? rec.src_len : 0u;
+            const bool ok_me = rec.out_len == c_len && (c_len == 0u || c_len >= 16u);
+            coal = staged && fits && tb != 0u && tb <= D3_COPY_MAX_BYTES && __all_sync(0xffffffffu, ok_me);
+            if (coal) d3_copy_tile(W.ct, sbuf, a.out_payload + base, c_len, ex_bytes0, my_soff + rec.src_off, tb, lane);
+        }
 
         // ---------------- phase B: G lanes per task ----------------------------------------------------
         if (mine) {
@@ -1066,8 +1348,9 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             }
             if (rec.has && fits) {
                 if (rec.mode == OM_COPY) {
-                    if (staged) group_copy<G>(a.out_payload + ob, sbuf + my_soff + rec.src_off, rec.src_len, sub);
-                    else        group_copy_generic<G>(a.out_payload + ob, a.payload + my_goff + rec.src_off, rec.src_len, sub);
+                    if (coal) {}                                            // written by d3_copy_tile
+                    else if (staged) group_copy_staged<G>(a.out_payload + ob, sbuf + my_soff + rec.src_off, rec.src_len, sub);
+                    else             group_copy_generic<G>(a.out_payload + ob, a.payload + my_goff + rec.src_off, rec.src_len, sub);
                 } else if (sub == 0 && rec.mode != OM_STR_PAR) {
                     const uint8_t* p = (staged && !clobbered) ? (const uint8_t*)(sbuf + my_soff) : a.payload + my_goff;
                     d2_phase_b_task<HANDLER>(p, rec, a.out_payload + ob);
@@ -1128,9 +1411,10 @@ __global__ void __launch_bounds__(DS_WARPS * 32) drain_slow_kernel(DrainArgs a) 
             rec.status = (uint8_t)w; rec.has = (uint8_t)(w >> 8); rec.mode = (uint8_t)(w >> 16);
         }
         unsigned long long base = 0;
-        if (lane == 0 && rec.out_len) base = atomicAdd(&a.ctl->bytes, (unsigned long long)rec.out_len);
+        const uint32_t alloc = (rec.out_len + 15u) & ~15u;                 // the cursor moves in 16-byte units (the main kernel's tile ranges stay vector-aligned)
+        if (lane == 0 && rec.out_len) base = atomicAdd(&a.ctl->bytes, (unsigned long long)alloc);
         base = __shfl_sync(0xffffffffu, base, 0);
-        const bool fits = base + rec.out_len <= a.out_cap;
+        const bool fits = base + alloc <= a.out_cap;
         if (!fits && lane == 0) a.ctl->overflow = 1u;
         if (rec.has && fits) {
             uint8_t* o = a.out_payload + base;

@@ -85,6 +85,31 @@ def test_identity_adversarial_heavy(dq):
     assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "identity", nthreads=8))
 
 
+def test_identity_escaped_bodies_cooperative_check(dq):
+    """The warp-cooperative canonical-escape check of the identity main loop (esc_verify_canonical): what json.dumps wrote,
+    and mutations of it (raw quotes, "\\/", upper-case hex, lone / paired surrogates, odd backslash runs, raw non-ASCII,
+    truncated escapes), at body lengths around the 16-byte lane chunks and the 512-byte passes."""
+    import json
+    import random
+    from tests.test_esc_verify_model import MUT, rand_string
+    rng = random.Random(77)
+    payloads = []
+    for k in range(24_000):
+        n = rng.choice([1, 2, 7, 15, 16, 17, 31, 40, 100, 256, 300, 511, 512, 513, 700, 1500])
+        body = bytearray(json.dumps(rand_string(rng, n, rng.random() < 0.4)).encode()[1:-1])
+        if k % 3:
+            for _ in range(rng.randint(1, 3)):
+                pos = rng.randint(0, len(body))
+                if rng.random() < 0.3 and len(body):
+                    del body[pos:pos + rng.randint(1, 3)]
+                else:
+                    body[pos:pos] = rng.choice(MUT)
+        payloads.append(b'{"args": ["' + bytes(body) + b'"], "kwargs": {}}')
+    b = synth.from_payloads(payloads)
+    r = run_gpu(dq, b, "identity")
+    assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "identity", nthreads=8))
+
+
 def test_identity_1m_x_256_full_size(dq):
     b = synth.strings_batch(1_000_000, 256)       # BASELINE configs[1]
     r = run_gpu(dq, b, "identity")

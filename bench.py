@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — tasks/sec of the task fan-out hot path on N B200s (contract: see DESIGN.md §Measurement).
+"""bench.py — tasks/sec of the task fan-out hot path on N B200s (contract: DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 1|2|3|4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch: every pending task of the batch is popped,
 deserialised, run through the handler and serialised (one persistent drain kernel per GPU).
-Workload = BASELINE.json configs[1]: 1M x 256-character identity tasks per GPU (weak scaling:
-every rank owns its own shard of the pending ring; no data-path collective).
+Default workload = BASELINE.json configs[1]: 1M x 256-character identity tasks per GPU (weak scaling:
+every rank owns its own shard of the pending ring; no data-path collective in the drain).
 
-  value      whole-job tasks/s with the batch already resident in HBM (kernel-resident number)
-  e2e        the same through the C ABI with HOST buffers: b9_batch_push (H2D) + b9_drain (D2H)
-  roofline   drain kernel: SURVEY.md §8(d) algorithmic bytes (578 B/task) / CUDA-event kernel time
-  cpu_baseline  the oracle's C port of the reference loop on this box's host cores (rank 0, N=1)
+  value        whole-job tasks/s, batch resident in HBM: the MEDIAN of B bursts of exactly K steps each (B is chosen
+               so that the timed bursts add up to >= --sustain-seconds); every burst is bracketed by a barrier and a
+               synchronise on both sides and timed with CUDA events on the drain stream, max over ranks
+  e2e          the same through the C ABI with HOST buffers: b9_batch_push_async (H2D from pinned memory) + b9_drain (D2H)
+  e2e_packed   the same starting from payloads scattered over PAGEABLE memory: b9_batch_push_v (the pack step) + b9_drain
+  link         what the host<->device link gives on this box for the e2e byte counts (all ranks at once): e2e's roofline
+  roofline     drain kernel: SURVEY.md §8(d) algorithmic bytes / CUDA-event kernel time vs the measured HBM peak
+  rebalance    N > 1: skewed ingest (rank 0 holds 2x its share), ONE b9_rebalance (NCCL all-to-all), then the drain
+  cpu_baseline the oracle's C port of the reference loop on this box's host cores (rank 0, N = 1), plus the 1-thread rate
+               and BASELINE.md's C1 (the Python loop, one process, configs[0])
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import statistics
@@ -31,8 +38,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALGO_BYTES_PER_TASK = {"identity": 578.0}   # 256 in + 258 out + 2 x 32 B of index/id/header
 L2_BYTES = 126e6
+CONFIGS = {   # BASELINE.json configs[i] -> (handler, total tasks quoted, the GPU count it is quoted on)
+    1: ("identity", 1_000_000, 1),
+    2: ("crc32", 1_000_000, 1),
+    3: ("vadd_f32", 10_000_000, 8),
+    4: ("json_sum", 100_000, 4),
+}
 
 
 def parse_args():
@@ -41,15 +53,23 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tasks", type=int, default=1_000_000, help="tasks per GPU per step")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configs[i]; 1 = the metric's configuration")
+    ap.add_argument("--tasks", type=int, default=0, help="tasks per GPU per step (default: the config's total / its GPU count)")
     ap.add_argument("--chars", type=int, default=256)
-    ap.add_argument("--handler", default="identity")
+    ap.add_argument("--handler", default="", help="override the config's handler")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--sustain-seconds", type=float, default=1.0, help="bursts of K steps are repeated until their timed regions add up to this")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cancelled", type=float, default=0.0, help="fraction of the resident tasks pushed with B9_TF_CANCELLED (the drain compacts them away: look-back path)")
-    ap.add_argument("--skew", type=float, default=0.0, help="N>1: rank 0 pushes (1+skew)x the tasks and every step starts with the NCCL rebalance")
+    ap.add_argument("--cancelled", type=float, default=0.0, help="fraction of the resident tasks pushed with B9_TF_CANCELLED")
+    ap.add_argument("--skew", type=float, default=1.0, help="N>1 rebalance leg: rank 0 ingests (1+skew)x its fair share; 0 = no rebalance leg")
     ap.add_argument("--adversarial", type=float, default=0.01, help="share of tasks whose string needs escaping (SURVEY.md §8d: 1 %%)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    h, total, g = CONFIGS[a.config]
+    if not a.handler:
+        a.handler = h
+    if not a.tasks:
+        a.tasks = total // g
+    return a
 
 
 class ClockSampler:
@@ -105,6 +125,28 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def usable_cores() -> int:
+    """Threads this process can really run at once: the scheduler affinity, capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine; a container with a quota of 8 CPUs on a 128-core host loses throughput
+    when 128 threads are started)."""
+    n = len(os.sched_getaffinity(0))
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def bind_to_gpu_numa_node(local_rank: int) -> str:
     """Run this rank on the CPUs next to its GPU (NVML's ideal affinity), BEFORE any pinned buffer is
     allocated: page-locked memory lands on the allocating thread's NUMA node, and a host<->device copy
@@ -124,24 +166,39 @@ def bind_to_gpu_numa_node(local_rank: int) -> str:
     return "unchanged"
 
 
+def kernel_source_hash() -> str:
+    """sha256 over the CUDA sources the drain kernels are built from: stamps profiles/ncu_traffic.json entries."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "beta9_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def workload_key(args, n_tasks) -> str:
+    return f"{args.handler}:{n_tasks}:{args.chars}:{args.adversarial}" if args.handler == "identity" else f"{args.handler}:{n_tasks}"
+
+
 def ncu_traffic(args, n_tasks):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this workload's drain kernel(s), from the
-    committed ncu capture of the same command (profiles/ncu_traffic.json, written from
-    scripts/gpu_profile_final.sh's reports). null when no capture of exactly this workload is committed."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this workload's drain kernel, from the committed ncu
+    capture of the same command (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py on a GPU box). An entry is
+    used only if it was captured from the kernel sources of THIS build (src_hash); otherwise (traffic: null, why)."""
     try:
-        table = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except (OSError, ValueError):
-        return None
-    key = f"{args.handler}:{n_tasks}:{args.chars}:{args.adversarial}" if args.handler == "identity" else f"{args.handler}:{n_tasks}"
-    e = table.get(key)
-    return None if e is None else e.get("dram_bytes")
+        return None, "no profiles/ncu_traffic.json"
+    e = table.get(workload_key(args, n_tasks))
+    if e is None:
+        return None, "no capture of this workload"
+    if e.get("src_hash") != kernel_source_hash():
+        return None, f"stale capture (kernel sources {e.get('src_hash')} != {kernel_source_hash()})"
+    return e.get("dram_bytes"), f"ncu --set full, {e.get('captured', '?')}, kernel sources {e.get('src_hash')}"
 
 
-def workload(args, rank):
+def workload(args, rank, n=None):
     from beta9_b200 import synth
-    n = args.tasks
-    if args.skew > 0 and rank == 0 and int(os.environ.get("WORLD_SIZE", 1)) > 1:
-        n = int(n * (1 + args.skew))
+    n = args.tasks if n is None else n
     if args.handler == "identity":
         return synth.strings_batch(n, args.chars, adversarial_frac=args.adversarial, seed=synth.SEED + 1000 * rank)
     if args.handler == "crc32":          # configs[2]: zipf 32..4096-char strings
@@ -153,17 +210,23 @@ def workload(args, rank):
     raise SystemExit(f"bench: unknown handler {args.handler}")
 
 
+def workload_name(args, n) -> str:
+    if args.handler == "identity":
+        return f"configs[{args.config}]: {n} x {args.chars}-char identity tasks per GPU ({100 * args.adversarial:g}% adversarial escapes)"
+    return f"configs[{args.config}]: {args.handler}, {n} tasks per GPU"
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU task loop on this box's host cores. The Go gateway and
     the Python runner cannot be built/imported here (no Go toolchain, SDK deps missing), so this is
-    the oracle's C port of that loop (oracle/c/b9_oracle.c), multi-threaded over all cores; Redis,
-    Postgres, gRPC and the object store are left out, which flatters the reference."""
+    the oracle's C port of that loop (oracle/c/b9_oracle.c), multi-threaded over the cores this process may
+    use; Redis, Postgres, gRPC and the object store are left out, which flatters the reference."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     from oracle import coracle
     batch = workload(args, 0)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     times = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -174,14 +237,20 @@ def run_reference(args):
             times.append(dt)
     total = sum(times)
     v = batch.n * len(times) / total
+    # the same loop on ONE thread (a bounded sample): what the port does per core, and how it scales
+    sample = batch.slice(0, min(batch.n, 100_000))
+    t0 = time.perf_counter()
+    coracle.run_batch(sample.task_ids, sample.payload, sample.offsets, args.handler, nthreads=1, out_cap=int(sample.payload.size) + 64)
+    v1 = sample.n / (time.perf_counter() - t0)
     line = {
         "impl": "reference", "metric": "tasks_per_sec", "value": v, "unit": "tasks/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"configs[1]: {batch.n} x {args.chars}-char identity tasks, reference CPU loop (C port), "
-                               f"one bounded sample of {batch.n} tasks per step", "handler": args.handler},
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8" if args.handler != "vadd_f32" else "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, batch.n) + ", resident in HBM", "handler": args.handler, "tasks_per_gpu": batch.n,
+                   "arm": "reference CPU loop (C port of the Go + Python path), one bounded sample of the per-GPU batch per step"},
         "cpu_baseline": {"value": v, "unit": "tasks/s", "cores": cores, "kind": "port",
-                         "sample": f"{batch.n} tasks x {len(times)} steps, {cores} threads"},
+                         "sample": f"{batch.n} tasks x {len(times)} steps, {cores} threads (sched affinity capped by the cgroup quota; os.cpu_count() = {os.cpu_count()})",
+                         "one_thread": v1, "scaling_vs_one_thread": v / v1},
         "e2e": {"value": v, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -204,6 +273,31 @@ def emit(line: dict) -> None:
     out = _REAL_STDOUT or sys.stdout
     out.write(json.dumps(line) + "\n")
     out.flush()
+
+
+def link_ceiling(torch, h2d_bytes: int, d2h_bytes: int, barrier, reduce_max, reps: int = 5):
+    """What the host<->device link gives for one e2e step's byte counts: both directions at once from / to pinned memory on
+    two streams, every rank at the same time (they share the host's memory and PCIe root complexes). Plain cudaMemcpyAsync
+    through torch — no library code: this is e2e's roofline, not a product path."""
+    hin = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8).pin_memory()
+    hout = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
+    din = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device="cuda")
+    dout = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for r in range(reps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+        s1.synchronize(); s2.synchronize()
+        dt = reduce_max(time.perf_counter() - t0)
+        if r:
+            best = dt if best is None else min(best, dt)
+    del hin, hout, din, dout
+    return best
 
 
 def main():
@@ -229,15 +323,7 @@ def main():
     n = batch.n
     in_bytes = int(batch.payload.size)
     dq = DeviceQueue(device=local_rank, ring_bytes=max(1 << 30, 4 * in_bytes), ring_tasks=max(1 << 21, 4 * n),
-                     max_drain_tasks=max(1 << 21, n), max_result_bytes=max(1 << 30, 2 * in_bytes))
-
-    rebalance = world > 1 and args.skew > 0
-    if rebalance:
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(DeviceQueue.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        dq.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+                     max_drain_tasks=max(1 << 21, 2 * n), max_result_bytes=max(1 << 30, 3 * in_bytes))
 
     def barrier():
         if dist is not None:
@@ -266,63 +352,56 @@ def main():
         dq.push_batch(batch.task_ids, batch.payload, batch.offsets, flags=fl)
     else:
         dq.push_batch(batch.task_ids, batch.payload, batch.offsets)
-    rebalance_info = None
-    n_pushed = n
-    if rebalance:
-        # skewed ingest (rank 0 holds (1+skew)x): ONE NCCL all-to-all evens the pending bytes out before the drain
-        barrier()
-        r0 = time.perf_counter()
-        info = dq.rebalance()
-        barrier()
-        r_ms = reduce_max(1e3 * (time.perf_counter() - r0))
-        rebalance_info = {"ms": r_ms, "tasks_before_rank0": int(info.tasks_before) if rank == 0 else None,
-                          "bytes_moved_total": reduce_sum(float(info.bytes_sent)), "skew": args.skew}
-        n = dq.depth()                                   # my share after the exchange
     n_total = int(round(reduce_sum(float(n))))
-    kernel_ms = []
     for _ in range(args.warmup):
         dq.drain_launch(args.handler, n, peek=True)
     sampler = ClockSampler(local_rank)
     launches0 = dq.stats().kernel_launches
     barrier()
     sampler.start()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        # B9_DRAIN_ASYNC: the K steps are enqueued back to back, as a host that pipelines its drains would;
-        # the barrier below (stream sync on every rank) closes the timed region
-        got = dq.drain_launch(args.handler, n, peek=True, wait=False)
-    dq.sync()
-    burst_ms = float(dq.stats().last_drain_kernel_ms)        # CUDA events on the drain stream: first step's start -> last step's end
-    barrier()
-    t1 = time.perf_counter()
+    # bursts of EXACTLY K steps: the K launches are enqueued back to back (B9_DRAIN_ASYNC), as a host that pipelines its
+    # drains would; a barrier + synchronise brackets every burst; the device time of a burst comes from CUDA events on
+    # the drain stream (first step's start -> last step's end), the max over ranks is the burst's time
+    burst_dev, burst_wall = [], []
+    timed_total = 0.0
+    launches_per_burst = None
+    while True:
+        k0 = dq.stats().kernel_launches
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            got = dq.drain_launch(args.handler, n, peek=True, wait=False)
+        dq.sync()
+        dev_s = float(dq.stats().last_drain_kernel_ms) * 1e-3
+        barrier()
+        wall_s = time.perf_counter() - t0
+        assert got == n, (got, n)
+        launches_per_burst = dq.stats().kernel_launches - k0
+        d = reduce_max(dev_s)
+        burst_dev.append(d); burst_wall.append(reduce_max(wall_s))
+        timed_total += d
+        if timed_total >= args.sustain_seconds or len(burst_dev) >= 2000:
+            break
     clocks = sampler.stop()
     launches = dq.stats().kernel_launches - launches0
-    assert got == n, (got, n)
-    for _ in range(min(args.steps, 5)):             # per-step kernel time (CUDA events around one step's kernels), outside the timed region
+    elapsed = statistics.median(burst_dev)
+    wall_elapsed = statistics.median(burst_wall)
+    value = n_total * args.steps / elapsed
+    kernel_ms = []
+    for _ in range(5):                               # per-step kernel time (CUDA events around one step's kernel), outside the bursts
         dq.drain_launch(args.handler, n, peek=True)
         kernel_ms.append(dq.stats().last_drain_kernel_ms)
-    out_bytes = int(dq.stats().last_drain_out_bytes)
-    # timed on the device (CUDA events around the K steps), max over ranks; the host's wall clock over the same region,
-    # barriers included, is reported beside it (a 4 ms region is at the mercy of one scheduling hiccup)
-    wall_elapsed = reduce_max(t1 - t0)
-    elapsed = reduce_max(burst_ms * 1e-3)
-    value = n_total * args.steps / elapsed
     k_ms = reduce_max(statistics.mean(kernel_ms))
-    # drop the resident batch
+    # drop the resident batch; its records are the reference records of the legs below
     dq.drain_launch(args.handler, n, peek=False)
     res = dq.fetch()
-    assert res.n == n - (n_cancelled if not rebalance else 0) or rebalance, (res.n, n, n_cancelled)
+    assert res.n == n - n_cancelled, (res.n, n, n_cancelled)
     assert dq.depth() == 0
-    if rebalance or n_cancelled:
-        # the end-to-end leg below runs the un-skewed shard shape with every task live (the exchange / the
-        # compaction of cancelled slots is timed above): take its reference records from one more drain
-        res_n_after = n
-        n = min(n_pushed, args.tasks)
-        batch = batch.slice(0, n)
-        in_bytes = int(batch.payload.size)
+    if n_cancelled:
         dq.push_batch(batch.task_ids, batch.payload, batch.offsets)
         res = dq.drain(args.handler, n)
-        out_bytes = int(res.payload.size)
+    out_bytes = int(res.lengths.astype(np.int64).sum())      # result bytes proper (the blob also holds <= 15 B of padding per tile)
+    blob_bytes = int(res.payload.size)
 
     # ------------------------------------------------------------------ end to end through the C ABI, host buffers
     # Every step copies that step's inputs host->device from pinned memory and reads that step's result
@@ -335,9 +414,9 @@ def main():
         pi.array[:] = batch.task_ids.reshape(-1); pp.array[:] = batch.payload
         po.view(np.uint64, n + 1)[:] = batch.offsets
         pins.append((pi, pp, po))
-    cap_bytes = out_bytes + 4096
+    cap_bytes = blob_bytes + 4096
     o_ids = dq.pinned(n * 16); o_st = dq.pinned(n); o_has = dq.pinned(n); o_off = dq.pinned(n * 8); o_len = dq.pinned(n * 4); o_pl = dq.pinned(cap_bytes)
-    resbuf = L.Results(o_ids.ptr, o_st.ptr, o_has.ptr, o_off.ptr, o_len.ptr, o_pl.ptr, n, cap_bytes, 0, 0, 0, 0)
+    resbuf = L.Results(o_ids.ptr, o_st.ptr, o_has.ptr, o_off.ptr, o_len.ptr, o_pl.ptr, n, cap_bytes, 0, 0, 0, 0, 0.0, 0)
     lib = L.load()
     hid = {"identity": 0, "crc32": 1, "vadd_f32": 2, "json_sum": 3}[args.handler]
 
@@ -352,35 +431,111 @@ def main():
         if r != n:
             raise SystemExit(f"drain returned {r}: " + L.last_error())
 
-    def e2e_run(steps):
-        e2e_push(0)
+    def e2e_run(steps, push):
+        push(0)
         for k in range(steps):
             if k + 1 < steps:
-                e2e_push(k + 1)
+                push(k + 1)
             e2e_drain()
 
-    e2e_run(3)
+    def check_records():            # the records that came back are the real ones
+        e_off = o_off.view(np.uint64, n); e_len = o_len.view(np.uint32, n)
+        for i in (0, n // 2, n - 1):
+            assert bytes(o_pl.array[int(e_off[i]):int(e_off[i]) + int(e_len[i])]) == res.result(i)
+
+    e2e_run(3, e2e_push)
     s0 = dq.stats()
     barrier()
     t0 = time.perf_counter()
-    e2e_run(args.e2e_steps)
+    e2e_run(args.e2e_steps, e2e_push)
     barrier()
     t1 = time.perf_counter()
     s1 = dq.stats()
     e2e_elapsed = reduce_max(t1 - t0)
-    e2e_value = int(round(reduce_sum(float(n)))) * args.e2e_steps / e2e_elapsed
+    e2e_value = n_total * args.e2e_steps / e2e_elapsed
     h2d = (s1.bytes_h2d - s0.bytes_h2d) // args.e2e_steps
     d2h = (s1.bytes_d2h - s0.bytes_d2h) // args.e2e_steps
-    # the records that came back are the real ones
-    e_off = o_off.view(np.uint64, n); e_len = o_len.view(np.uint32, n)
-    for i in (0, n // 2, n - 1):
-        assert bytes(o_pl.array[int(e_off[i]):int(e_off[i]) + int(e_len[i])]) == res.result(i)
+    check_records()
+
+    # ------------------------------------------------------------------ ... and from scattered pageable payloads: the pack step
+    # What a Go gateway holds is [][]byte: n separate payloads somewhere in pageable memory. Here they sit in one pageable
+    # blob in a random order (so the gather is a gather); b9_batch_push_v packs them into the context's pinned arenas with
+    # its own threads and pushes the arena; the pack of step k+1 runs while step k's DMA, kernel and read-back are in flight.
+    lens32 = np.diff(batch.offsets).astype(np.uint32)
+    perm = np.random.default_rng(17 + rank).permutation(n)
+    where = np.zeros(n, np.uint64)
+    where[perm] = np.concatenate([[0], np.cumsum(lens32[perm].astype(np.uint64))[:-1]])
+    src_rec = np.repeat(np.arange(n, dtype=np.int64), lens32.astype(np.int64))
+    starts = np.asarray(batch.offsets[:-1], dtype=np.int64)
+    within = np.arange(in_bytes, dtype=np.int64) - starts[src_rec]
+    blob = np.empty(in_bytes + 1, np.uint8)
+    blob[where.astype(np.int64)[src_rec] + within] = batch.payload
+    del src_rec, within
+    ptrs = (np.uint64(blob.ctypes.data) + where).astype(np.uint64)
+    ids_pageable = np.ascontiguousarray(batch.task_ids).copy()
+
+    def packed_push(k):
+        rc = lib.b9_batch_push_v(dq._ctx, ids_pageable.ctypes.data, ptrs.ctypes.data, lens32.ctypes.data, n, None)
+        if rc != 0:
+            raise SystemExit("push_v failed: " + L.last_error())
+
+    e2e_run(3, packed_push)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.e2e_steps, packed_push)
+    barrier()
+    packed_elapsed = reduce_max(time.perf_counter() - t0)
+    packed_value = n_total * args.e2e_steps / packed_elapsed
+    check_records()
+    pack_threads = int(os.environ.get("B9_PACK_THREADS", min(16, os.cpu_count() or 1)))
+
+    # ------------------------------------------------------------------ the link's own ceiling for these byte counts
+    link_s = link_ceiling(torch, int(h2d), int(d2h), barrier, reduce_max)
+    link = {"seconds_per_step": link_s, "h2d_GBps_per_gpu": h2d / link_s / 1e9, "d2h_GBps_per_gpu": d2h / link_s / 1e9,
+            "tasks_per_sec": n_total / link_s, "how": "cudaMemcpyAsync H2D + D2H of one step's bytes at once, pinned memory, two streams, all ranks together, best of 5"}
+
+    # ------------------------------------------------------------------ N > 1: skewed ingest -> ONE NCCL rebalance -> drain
+    rebalance_info = None
+    if world > 1 and args.skew > 0:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(DeviceQueue.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        dq.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        # the job's total stays N x n; rank 0 ingests (1 + skew) x n, the other ranks share the rest evenly
+        n0 = int(n * (1 + args.skew))
+        n_mine = n0 if rank == 0 else (n * world - n0) // (world - 1)
+        sk = workload(args, rank, n_mine) if n_mine != n else batch
+        total_in = int(round(reduce_sum(float(sk.n))))
+        ms, moved, after = [], 0.0, 0
+        for rep in range(4):
+            dq.push_batch(sk.task_ids, sk.payload, sk.offsets)
+            barrier()
+            r0 = time.perf_counter()
+            info = dq.rebalance()
+            torch.cuda.synchronize()
+            r_local = time.perf_counter() - r0
+            barrier()
+            if rep:                                       # the first exchange also sizes the arenas
+                ms.append(1e3 * reduce_max(r_local))
+            moved = reduce_sum(float(info.bytes_sent))
+            after = dq.depth()
+            dq.drain_launch(args.handler, after, peek=False)             # the drain after the exchange: every task exactly once
+            r = dq.fetch()
+            total_after = int(round(reduce_sum(float(r.n_popped))))
+            assert total_after == total_in, (total_after, total_in)
+        r_ms = statistics.median(ms)
+        share = reduce_max(float(after)) / (total_in / world)
+        rebalance_info = {"ms": r_ms, "ms_all": ms, "skew": args.skew, "tasks_rank0_before": n0, "tasks_per_rank_fair": total_in // world,
+                          "max_share_after": share, "bytes_moved_total": moved, "GBps_total": moved / (r_ms * 1e-3) / 1e9,
+                          "how": "wall clock of b9_rebalance (all-gather of counts, plan, grouped ncclSend/ncclRecv, ring append) "
+                                 "between barriers, max over ranks, median of 3 after one warm-up exchange"}
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import coracle
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         best = None
         for _ in range(3):
             c0 = time.perf_counter()
@@ -389,40 +544,62 @@ def main():
             best = dt if best is None else min(best, dt)
         # while we are here: the device answers are the oracle's answers
         assert np.array_equal(o.payload, res.fifo_payload()) and np.array_equal(o.status, res.status)
+        sample = batch.slice(0, min(n, 100_000))
+        c0 = time.perf_counter()
+        coracle.run_batch(sample.task_ids, sample.payload, sample.offsets, args.handler, nthreads=1, out_cap=int(sample.payload.size) + 64)
+        v1 = sample.n / (time.perf_counter() - c0)
+        # configs[0] (10k x 64-char echo) through the Python loop, one process (= reference workers=1)
+        from beta9_b200 import synth
+        from oracle.pyoracle.loop import run_task_loop
+        echo = synth.strings_batch(10_000, 64)
+        c0 = time.perf_counter()
+        run_task_loop(echo.tasks(), [bytes(t) for t in echo.task_ids], "identity")
+        c1 = echo.n / (time.perf_counter() - c0)
         cpu = {"value": n / best, "unit": "tasks/s", "cores": cores, "kind": "port",
-               "sample": f"all {n} tasks of the step, best of 3 passes, {cores} threads (oracle/c/b9_oracle.c)"}
+               "sample": f"all {n} tasks of the step, best of 3 passes, {cores} threads (oracle/c/b9_oracle.c; os.cpu_count() = {os.cpu_count()})",
+               "one_thread": v1, "scaling_vs_one_thread": (n / best) / v1,
+               "c1_python_one_process_configs0": c1}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         if os.path.exists(peaks_path):
             peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
-        if args.handler in ALGO_BYTES_PER_TASK:
-            algo = ALGO_BYTES_PER_TASK[args.handler] * n
+        if args.handler == "identity" and args.chars == 256 and args.adversarial <= 0.01:
+            algo = 578.0 * n        # 256 in + 258 out + 2 x 32 B of index/id/header
         else:   # argument bytes as carried + result bytes + 2 x 32 B of index/id/header per task
             algo = float(in_bytes - 28 * n + out_bytes + 64 * n)
         achieved = algo / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(args, n)
         line = {
             "metric": "tasks_per_sec", "value": value, "unit": "tasks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "wall_ms_per_step": 1e3 * wall_elapsed / args.steps,
-            "timing": "CUDA events on the drain stream around the K steps (enqueued back to back, B9_DRAIN_ASYNC), max over ranks; "
-                      "wall_ms_per_step = host clock over the same region, barrier + stream sync on both sides",
+            "timing": {"bursts": len(burst_dev), "steps_per_burst": args.steps, "timed_seconds": timed_total,
+                       "burst_ms_min_median_max": [1e3 * min(burst_dev), 1e3 * elapsed, 1e3 * max(burst_dev)],
+                       "how": "every burst = exactly K steps enqueued back to back (B9_DRAIN_ASYNC), CUDA events on the drain stream, "
+                              "barrier + synchronise on both sides, max over ranks; value uses the median burst; wall_ms_per_step = "
+                              "host clock over the median burst, barriers included"},
             "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": (f"configs[1]: {n} x {args.chars}-char identity tasks per GPU ({100 * args.adversarial:g}% adversarial escapes), resident in HBM"
-                                    if args.handler == "identity" else f"{args.handler}: {n} tasks per GPU, {in_bytes / n:.0f} payload bytes per task on average, resident in HBM"),
+            "vs_baseline": None, "dtype": "u8" if args.handler != "vadd_f32" else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, n) + ", resident in HBM",
                        "handler": args.handler, "tasks_per_gpu": n,
-                       "parallelism": (f"shard{world}" + ("+nccl_rebalance" if rebalance else "")) if world > 1 else "single",
+                       "parallelism": f"shard{world}" if world > 1 else "single",
                        "cpu_affinity": affinity, "cancelled_tasks_per_gpu": n_cancelled,
                        "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args, n), "kernel": f"b9::drain3_kernel<{args.handler}>" + (" + drain_slow_kernel" if args.handler == "identity" else ""),
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": f"b9::drain3_kernel<{args.handler}>",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_task": algo / n, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "tasks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / args.e2e_steps,
+                    "frac_of_link": e2e_value / link["tasks_per_sec"],
                     "api": "b9_batch_push_async + b9_drain, pinned host buffers, push of step k+1 overlapped with drain of step k"},
+            "e2e_packed": {"value": packed_value, "unit": "tasks/s", "ms_per_step": 1e3 * packed_elapsed / args.e2e_steps,
+                           "pack_threads": pack_threads, "frac_of_link": packed_value / link["tasks_per_sec"],
+                           "api": "b9_batch_push_v (payloads scattered over pageable memory, gathered into pinned arenas by the library) + b9_drain"},
+            "link": link,
             "gpu_launches": int(launches),
+            "gpu_launches_per_burst": int(launches_per_burst),
             "rebalance": rebalance_info,
             "clocks": clocks,
         }

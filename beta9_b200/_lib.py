@@ -29,7 +29,7 @@ class Results(C.Structure):
     _fields_ = [("task_ids", C.c_void_p), ("status", C.c_void_p), ("has_result", C.c_void_p),
                 ("offsets", C.c_void_p), ("lengths", C.c_void_p), ("payload", C.c_void_p), ("cap_tasks", C.c_uint32),
                 ("cap_bytes", C.c_uint64), ("n_results", C.c_uint32), ("n_popped", C.c_uint32),
-                ("n_bytes", C.c_uint64), ("need_bytes", C.c_uint64)]
+                ("n_bytes", C.c_uint64), ("need_bytes", C.c_uint64), ("task_duration", C.c_float), ("reserved_", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -64,7 +64,9 @@ SYMBOLS = {
     "b9_host_free": (None, [C.c_void_p, C.c_void_p]),
     "b9_batch_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PushMeta)]),
     "b9_batch_push_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PushMeta)]),
+    "b9_batch_push_v": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PushMeta)]),
     "b9_depth": (C.c_uint64, [C.c_void_p]),
+    "b9_running": (C.c_uint64, [C.c_void_p]),
     "b9_depth_bytes": (C.c_uint64, [C.c_void_p]),
     "b9_expire": (C.c_int64, [C.c_void_p, C.c_int64]),
     "b9_drain": (C.c_int64, [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(Results)]),
@@ -101,7 +103,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)      # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.b9_abi_version() != 1:
+    if lib.b9_abi_version() != 2:
         raise B9Error(B9_EINVAL, "ABI version mismatch")
     _lib = lib
     return lib

@@ -15,7 +15,11 @@
 #include <cstring>
 #include <chrono>
 #include <deque>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -58,6 +62,40 @@ struct Segment {             // one push = one contiguous byte range of the payl
 constexpr uint64_t RING_SLACK = 256;   // readable bytes past the ring end (vector loads may over-read)
 constexpr uint64_t SEG_ALIGN  = B9_SEG_ALIGN;
 
+// A few persistent threads for the host-side pack (b9_batch_push_v): the calling thread is worker 0.
+struct PackPool {
+    std::vector<std::thread> th;
+    std::mutex m; std::condition_variable cv, cv_done;
+    std::function<void(int)> job;
+    int nthreads = 1, generation = 0, pending = 0; bool stop = false;
+    explicit PackPool(int n) : nthreads(n < 1 ? 1 : n) {
+        for (int i = 1; i < nthreads; ++i) th.emplace_back([this, i] {
+            int seen = 0;
+            for (;;) {
+                std::function<void(int)> f;
+                { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return stop || generation != seen; }); if (stop) return; seen = generation; f = job; }
+                f(i);
+                { std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv_done.notify_one(); }
+            }
+        });
+    }
+    void run(const std::function<void(int)>& f) {
+        { std::lock_guard<std::mutex> lk(m); job = f; pending = nthreads - 1; ++generation; }
+        cv.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m); cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~PackPool() { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); for (auto& t : th) t.join(); }
+};
+
+// page-locked staging of one packed batch (b9_batch_push_v): two of them alternate, so that batch k+1 is gathered
+// while batch k is still on the wire
+struct PackArena {
+    uint8_t* payload = nullptr; uint64_t cap_bytes = 0;
+    uint64_t* offsets = nullptr; uint8_t* ids = nullptr; uint32_t cap_tasks = 0;
+    cudaEvent_t free_ev = nullptr; bool in_flight = false;
+};
+
 }  // namespace
 
 struct b9_ctx {
@@ -67,8 +105,16 @@ struct b9_ctx {
     cudaStream_t stream = nullptr;             // drain kernels + D2H
     cudaStream_t stream_in = nullptr;          // H2D + ingest kernel (so that pushes overlap drains: PCIe is full duplex)
     std::vector<cudaEvent_t> event_pool;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
-    std::mutex mu;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;   // drain stream (under out_mu)
+    cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;                                    // ingest stream (under in_mu)
+    // Three locks, always taken in this order: in_mu (push submission: H2D + ingest kernel are enqueued in FIFO order),
+    // out_mu (drain-side submission and the waiting-results state: launch, fetch, expire, wire records, rebalance), mu
+    // (ring bookkeeping + stats; held for pointer arithmetic only, never across a CUDA synchronisation). Producers
+    // therefore never wait for a drain's kernels or its D2H copy, and the drainer never waits for a push's DMA
+    // (Dispatcher.Register's goroutine-safety contract, pkg/task/dispatch.go:71-73).
+    std::mutex in_mu, out_mu, mu;
+    std::mutex pack_mu; PackPool* pack_pool = nullptr; PackArena pack[2]; int pack_next = 0;
+    std::atomic<uint64_t> running{0};           // tasks a drain has claimed (launched, not peeking) and not yet committed by a fetch
 
     // ---- pending ring (device)
     uint64_t ring_bytes = 0; uint32_t ring_tasks = 0, slot_mask = 0, max_task_bytes = 0;
@@ -88,7 +134,8 @@ struct b9_ctx {
     uint32_t max_drain_tasks = 0; uint64_t max_result_bytes = 0;
     uint8_t* d_out_payload = nullptr; uint64_t* d_out_off = nullptr; uint4* d_out_ids = nullptr;
     uint8_t* d_out_status = nullptr; uint8_t* d_out_has = nullptr; uint32_t* d_out_len = nullptr;
-    SlowItem* d_slow = nullptr;                 // identity: work list of the second kernel
+    SlowItem* d_slow = nullptr;                 // identity: work list of deferred tasks (kernel tail)
+    uint32_t drain_epoch = 0;                   // tag of the current launch's work-list items
     WireEnv* d_wire_env = nullptr;
     uint32_t* d_crc_shift = nullptr;            // crc32: zero-byte shift tables
     uint64_t cancelled_pending = 0;            // pending tasks carrying B9_TF_CANCELLED (pushed so, or expired)
@@ -102,7 +149,8 @@ struct b9_ctx {
     unsigned long long* d_count = nullptr; unsigned long long* h_count = nullptr;
     // results waiting on the device for b9_drain_fetch
     bool have_results = false, res_peek = false;
-    uint32_t res_n = 0, res_popped = 0; uint64_t res_bytes = 0, res_in_bytes = 0;
+    uint32_t res_n = 0, res_popped = 0; uint64_t res_bytes = 0, res_in_bytes = 0; float res_kernel_ms = 0.f;
+    bool expired_since_launch = false, recount_cancelled = false;   // (b9_expire between a launch and its fetch: recount, see b9_drain_fetch)
 
     // ---- multi-GPU (NCCL, loaded with dlopen: the library has no link-time dependency on it)
     void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
@@ -186,6 +234,36 @@ template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes,
     return cudaGetLastError();
 }
 
+__global__ void count_cancelled_kernel(const uint64_t* __restrict__ hdr, uint32_t slot_mask, uint64_t first_task, uint32_t n, unsigned long long* __restrict__ count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = i < n && (hdr_flags(hdr[(uint32_t)((first_task + i) & slot_mask)]) & 1u);
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31u) == 0u && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
+// cancelled_pending := the cancelled slots among the pending tasks, counted on the device. Caller holds c->out_mu (not c->mu).
+int recount_cancelled_locked_out(b9_ctx* c) {
+    uint64_t head = 0, depth = 0;
+    cudaStream_t s = c->stream;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        head = c->head_task; depth = c->tail_task - c->head_task;
+        for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(s, sg.ready, 0));
+    }
+    CU(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned long long), s));
+    if (depth) { count_cancelled_kernel<<<(uint32_t)((depth + 255) / 256), 256, 0, s>>>(c->d_hdr, c->slot_mask, head, (uint32_t)depth, c->d_count); CU(cudaGetLastError()); }
+    CU(cudaMemcpyAsync(c->h_count, c->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    std::lock_guard<std::mutex> lk(c->mu);
+    // tasks pushed (with B9_TF_CANCELLED) after the snapshot are in cancelled_pending already but not in the count: keep them
+    const uint64_t depth_now = c->tail_task - c->head_task;
+    if (depth_now == depth) c->cancelled_pending = *c->h_count;
+    else c->cancelled_pending = std::max<uint64_t>(c->cancelled_pending, *c->h_count);   // (an over-count only costs the count pre-pass)
+    c->recount_cancelled = false;
+    if (depth) c->stats.kernel_launches++;
+    return B9_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -244,6 +322,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     CUC(cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&c->ev_burst));
     CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b)); CUC(cudaEventCreate(&c->ev_c)); CUC(cudaEventCreate(&c->ev_d));
+    CUC(cudaEventCreate(&c->ev_pa)); CUC(cudaEventCreate(&c->ev_pb));
     const uint32_t rt = c->ring_tasks, md = c->max_drain_tasks;
     CUC(cudaMalloc(&c->d_payload, c->ring_bytes + RING_SLACK));
     CUC(cudaMemset(c->d_payload + c->ring_bytes, 0, RING_SLACK));
@@ -264,6 +343,7 @@ int b9_ctx_create(const b9_opts* opts, b9_ctx** out) {
     CUC(cudaMalloc(&c->d_out_has, md));
     CUC(cudaMalloc(&c->d_out_len, (size_t)md * sizeof(uint32_t)));
     CUC(cudaMalloc(&c->d_slow, (size_t)md * sizeof(SlowItem)));
+    CUC(cudaMemset(c->d_slow, 0, (size_t)md * sizeof(SlowItem)));
     CUC(cudaMalloc(&c->d_wire_env, sizeof(WireEnv)));
     {
         // Z_k = advance the reflected CRC-32 register over 2^k zero bytes, as 4 byte-indexed tables per k
@@ -312,6 +392,15 @@ void b9_ctx_destroy(b9_ctx* c) {
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->ev_c) cudaEventDestroy(c->ev_c);
     if (c->ev_d) cudaEventDestroy(c->ev_d);
+    if (c->ev_pa) cudaEventDestroy(c->ev_pa);
+    if (c->ev_pb) cudaEventDestroy(c->ev_pb);
+    delete c->pack_pool;
+    for (PackArena& A : c->pack) {
+        if (A.payload) cudaFreeHost(A.payload);
+        if (A.offsets) cudaFreeHost(A.offsets);
+        if (A.ids) cudaFreeHost(A.ids);
+        if (A.free_ev) cudaEventDestroy(A.free_ev);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream_in) cudaStreamDestroy(c->stream_in);
     delete c;
@@ -332,28 +421,38 @@ void b9_host_free(b9_ctx* c, void* p) {
     cudaFreeHost(p);
 }
 
-static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, const uint64_t* offsets, uint32_t n, const b9_push_meta* meta, bool wait) {
+// One push. Reservation and commit of the ring space are two short critical sections under c->mu; the DMA and the
+// ingest kernel are enqueued between them under c->in_mu only, so a drain can run (and be synchronised) meanwhile.
+// The batch becomes visible to drains (tail_task) only at the commit, after its `ready` event has been recorded.
+// `after`: optional event recorded once the copies are enqueued (b9_batch_push_v's arena reuse).
+static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, const uint64_t* offsets, uint32_t n, const b9_push_meta* meta, bool wait,
+                     cudaEvent_t after = nullptr) {
     if (!c) return fail(B9_EINVAL, "b9_batch_push: ctx is NULL");
     if (n == 0) return B9_OK;
     if (!task_ids || !payload || !offsets) return fail(B9_EINVAL, "b9_batch_push: NULL buffer");
     if (offsets[n] < offsets[0]) return fail(B9_EINVAL, "b9_batch_push: offsets not monotonic");
     const uint64_t bytes = offsets[n] - offsets[0];
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::mutex> in_lk(c->in_mu);
     CU(cudaSetDevice(c->device));
-    free_segments(c);
-    if ((uint64_t)n > (uint64_t)c->ring_tasks - (c->tail_task - c->head_task))
-        return fail(B9_ENOSPC, "b9_batch_push: %u tasks do not fit (%llu of %u slots pending)", n,
-                    (unsigned long long)(c->tail_task - c->head_task), c->ring_tasks);
-    uint64_t start = 0;
-    if (!place_segment(c, bytes, &start))
-        return fail(B9_ENOSPC, "b9_batch_push: %llu payload bytes do not fit the ring (%llu pending of %llu)",
-                    (unsigned long long)bytes, (unsigned long long)c->pending_bytes, (unsigned long long)c->ring_bytes);
+    uint64_t start = 0, tail = 0;
+    cudaEvent_t ready = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        free_segments(c);
+        if ((uint64_t)n > (uint64_t)c->ring_tasks - (c->tail_task - c->head_task))
+            return fail(B9_ENOSPC, "b9_batch_push: %u tasks do not fit (%llu of %u slots pending)", n,
+                        (unsigned long long)(c->tail_task - c->head_task), c->ring_tasks);
+        if (!place_segment(c, bytes, &start))
+            return fail(B9_ENOSPC, "b9_batch_push: %llu payload bytes do not fit the ring (%llu pending of %llu)",
+                        (unsigned long long)bytes, (unsigned long long)c->pending_bytes, (unsigned long long)c->ring_bytes);
+        if (!c->event_pool.empty()) { ready = c->event_pool.back(); c->event_pool.pop_back(); }
+        tail = c->tail_task;
+    }
+    if (!ready) CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    auto give_back = [&]() { std::lock_guard<std::mutex> lk(c->mu); c->event_pool.push_back(ready); };
     cudaStream_t s = c->stream_in;
-    cudaEvent_t ready;
-    if (!c->event_pool.empty()) { ready = c->event_pool.back(); c->event_pool.pop_back(); }
-    else CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    CU(cudaEventRecord(c->ev_a, s));
-    // the payload DMA goes first (into ring space that is free until this push is committed), so that
+    CU(cudaEventRecord(c->ev_pa, s));
+    // the payload DMA goes first (into ring space that stays free until this push is committed), so that
     // the O(n) host-side validation of the index below runs while the bytes are already on the wire
     if (bytes) CU(cudaMemcpyAsync(c->d_payload + start, payload + offsets[0], bytes, cudaMemcpyHostToDevice, s));
     uint64_t n_cancelled = 0;
@@ -367,7 +466,7 @@ static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload,
             prev = cur;
         }
         if (bad != ~0ull || big != ~0ull) {
-            c->event_pool.push_back(ready);
+            give_back();
             cudaStreamSynchronize(s);            // the stray DMA must not outlive the caller's buffer
             if (bad != ~0ull) return fail(B9_EINVAL, "b9_batch_push: offsets not monotonic at task %llu", (unsigned long long)bad);
             return fail(B9_E2BIG, "b9_batch_push: task %llu is %llu bytes, max_task_bytes is %u", (unsigned long long)big,
@@ -377,7 +476,7 @@ static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload,
     }
     CU(cudaMemcpyAsync(c->d_in_off, offsets, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     // ids go straight into their ring slots (two pieces when the slot ring wraps)
-    const uint32_t slot0 = (uint32_t)(c->tail_task & c->slot_mask);
+    const uint32_t slot0 = (uint32_t)(tail & c->slot_mask);
     const uint32_t first = std::min<uint32_t>(n, c->ring_tasks - slot0);
     CU(cudaMemcpyAsync(c->d_ids + slot0, task_ids, (size_t)first * 16, cudaMemcpyHostToDevice, s));
     if (first < n) CU(cudaMemcpyAsync(c->d_ids, task_ids + (size_t)first * 16, (size_t)(n - first) * 16, cudaMemcpyHostToDevice, s));
@@ -389,23 +488,28 @@ static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload,
         if (meta->retries)         { CU(cudaMemcpyAsync(c->d_in_retries, meta->retries, n, cudaMemcpyHostToDevice, s)); rt = c->d_in_retries; meta_bytes += n; }
         if (meta->flags)           { CU(cudaMemcpyAsync(c->d_in_flags, meta->flags, n, cudaMemcpyHostToDevice, s)); fl = c->d_in_flags; meta_bytes += n; }
     }
-    CU(cudaEventRecord(c->ev_b, s));
-    ingest_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->d_in_off, n, start, c->tail_task, c->slot_mask, ts, ex, rt, fl,
+    CU(cudaEventRecord(c->ev_pb, s));
+    if (after) CU(cudaEventRecord(after, s));
+    ingest_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->d_in_off, n, start, tail, c->slot_mask, ts, ex, rt, fl,
                                                   c->d_off, c->d_hdr, c->d_ts, c->d_exp);
     CU(cudaGetLastError());
-    c->stats.kernel_launches++;
     CU(cudaEventRecord(ready, s));
-    if (wait) {
-        CU(cudaStreamSynchronize(s));        // the caller may reuse its buffers as soon as we return
-        float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->stats.last_push_h2d_ms = ms;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->segs.push_back(Segment{tail, n, start, bytes, ready});
+        c->write_pos = start + b9_seg_span(bytes);
+        c->tail_task += n;
+        c->pending_bytes += bytes;
+        c->cancelled_pending += n_cancelled;
+        c->stats.kernel_launches++;
+        c->stats.tasks_pushed += n;
+        c->stats.bytes_h2d += bytes + ((uint64_t)n + 1) * 8 + (uint64_t)n * 16 + meta_bytes;
     }
-    c->segs.push_back(Segment{c->tail_task, n, start, bytes, ready});
-    c->write_pos = start + ((bytes + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
-    c->tail_task += n;
-    c->pending_bytes += bytes;
-    c->cancelled_pending += n_cancelled;
-    c->stats.tasks_pushed += n;
-    c->stats.bytes_h2d += bytes + ((uint64_t)n + 1) * 8 + (uint64_t)n * 16 + meta_bytes;
+    if (wait) {
+        CU(cudaStreamSynchronize(s));            // the caller may reuse its buffers as soon as we return
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev_pa, c->ev_pb);
+        std::lock_guard<std::mutex> lk(c->mu); c->stats.last_push_h2d_ms = ms;
+    }
     return B9_OK;
 }
 
@@ -415,6 +519,71 @@ int b9_batch_push(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, co
 
 int b9_batch_push_async(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload, const uint64_t* offsets, uint32_t n, const b9_push_meta* meta) {
     return push_impl(c, task_ids, payload, offsets, n, meta, false);
+}
+
+// The pack step of the north star ("packs the whole pending batch into pinned host buffers"): n payloads scattered over
+// the caller's (pageable) memory — Go's [][]byte — are gathered by a few threads into one of two page-locked arenas of
+// the context, the n + 1 offsets are built on the way, and the arena is pushed asynchronously. Everything the call
+// needs has been copied when it returns (cgo pointer rules); the arena is reused two pushes later, after its DMA.
+int b9_batch_push_v(b9_ctx* c, const uint8_t* task_ids, const uint8_t* const* payloads, const uint32_t* lengths, uint32_t n, const b9_push_meta* meta) {
+    if (!c) return fail(B9_EINVAL, "b9_batch_push_v: ctx is NULL");
+    if (n == 0) return B9_OK;
+    if (!task_ids || !payloads || !lengths) return fail(B9_EINVAL, "b9_batch_push_v: NULL buffer");
+    std::lock_guard<std::mutex> pk(c->pack_mu);
+    CU(cudaSetDevice(c->device));
+    if (!c->pack_pool) {
+        int nt = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("B9_PACK_THREADS")) nt = std::max(1, atoi(e));
+        c->pack_pool = new (std::nothrow) PackPool(nt);
+        if (!c->pack_pool) return fail(B9_ENOMEM, "b9_batch_push_v: thread pool");
+    }
+    const int T = c->pack_pool->nthreads;
+    // pass 1: bytes per thread range (ranges of equal task count)
+    std::vector<uint64_t> part((size_t)T + 1, 0);
+    auto lo_of = [&](int t) { return (uint32_t)((uint64_t)n * (uint64_t)t / (uint64_t)T); };
+    c->pack_pool->run([&](int t) {
+        uint64_t sum = 0; const uint32_t lo = lo_of(t), hi = lo_of(t + 1);
+        for (uint32_t i = lo; i < hi; ++i) sum += lengths[i];
+        part[(size_t)t + 1] = sum;
+    });
+    for (int t = 0; t < T; ++t) part[(size_t)t + 1] += part[(size_t)t];
+    const uint64_t total = part[(size_t)T];
+    PackArena& A = c->pack[c->pack_next];
+    c->pack_next ^= 1;
+    if (A.in_flight) { CU(cudaEventSynchronize(A.free_ev)); A.in_flight = false; }   // its previous batch is on the device
+    if (!A.free_ev) CU(cudaEventCreateWithFlags(&A.free_ev, cudaEventDisableTiming));
+    if (A.cap_bytes < total + 64) {
+        if (A.payload) cudaFreeHost(A.payload);
+        A.payload = nullptr; A.cap_bytes = 0;
+        const uint64_t want = (total + 64) + (total + 64) / 4;
+        if (cudaHostAlloc(&A.payload, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(B9_ENOMEM, "b9_batch_push_v: %llu bytes of page-locked memory", (unsigned long long)want); }
+        A.cap_bytes = want;
+    }
+    if (A.cap_tasks < n) {
+        if (A.offsets) cudaFreeHost(A.offsets);
+        if (A.ids) cudaFreeHost(A.ids);
+        A.offsets = nullptr; A.ids = nullptr; A.cap_tasks = 0;
+        const uint32_t want = n + n / 4 + 16;
+        if (cudaHostAlloc(&A.offsets, ((size_t)want + 1) * 8, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc(&A.ids, (size_t)want * 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(B9_ENOMEM, "b9_batch_push_v: page-locked index"); }
+        A.cap_tasks = want;
+    }
+    // pass 2: gather
+    c->pack_pool->run([&](int t) {
+        const uint32_t lo = lo_of(t), hi = lo_of(t + 1);
+        uint64_t o = part[(size_t)t];
+        for (uint32_t i = lo; i < hi; ++i) {
+            A.offsets[i] = o;
+            const uint32_t l = lengths[i];
+            if (l) memcpy(A.payload + o, payloads[i], l);
+            o += l;
+        }
+        memcpy(A.ids + (size_t)lo * 16, task_ids + (size_t)lo * 16, (size_t)(hi - lo) * 16);
+    });
+    A.offsets[n] = total;
+    const int rc = push_impl(c, A.ids, A.payload, A.offsets, n, meta, /*wait=*/false, A.free_ev);
+    if (rc == B9_OK) A.in_flight = true;
+    return rc;
 }
 
 uint64_t b9_depth(b9_ctx* c) {
@@ -429,24 +598,32 @@ uint64_t b9_depth_bytes(b9_ctx* c) {
     return c->pending_bytes;
 }
 
+uint64_t b9_running(b9_ctx* c) { return c ? c->running.load(std::memory_order_relaxed) : 0; }
+
 int64_t b9_expire(b9_ctx* c, int64_t now_unix_ns) {
     if (!c) return fail(B9_EINVAL, "b9_expire: ctx is NULL");
-    std::lock_guard<std::mutex> lk(c->mu);
-    const uint64_t depth = c->tail_task - c->head_task;
-    if (!depth) return 0;
+    std::lock_guard<std::mutex> out_lk(c->out_mu);
     CU(cudaSetDevice(c->device));
-    for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));
+    uint64_t head = 0, depth = 0;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        head = c->head_task; depth = c->tail_task - c->head_task;
+        if (!depth) return 0;
+        for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));
+    }
     CU(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned long long), c->stream));
-    expire_kernel<<<(uint32_t)((depth + 255) / 256), 256, 0, c->stream>>>(c->d_hdr, c->d_exp, c->slot_mask, c->head_task, (uint32_t)depth, now_unix_ns, c->d_count);
+    expire_kernel<<<(uint32_t)((depth + 255) / 256), 256, 0, c->stream>>>(c->d_hdr, c->d_exp, c->slot_mask, head, (uint32_t)depth, now_unix_ns, c->d_count);
     CU(cudaGetLastError());
-    c->stats.kernel_launches++;
     CU(cudaMemcpyAsync(c->h_count, c->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->stats.kernel_launches++;
     c->cancelled_pending += *c->h_count;
+    c->expired_since_launch = true;
     return (int64_t)*c->h_count;
 }
 
-// Waits for the last launch and publishes its outcome (records, bytes, overflow) to the ctx. Caller holds c->mu.
+// Waits for the last launch and publishes its outcome (records, bytes, overflow) to the ctx. Caller holds c->out_mu (not c->mu).
 static int finish_launch(b9_ctx* c) {
     if (!c->res_async) return B9_OK;
     c->res_async = false;
@@ -454,14 +631,18 @@ static int finish_launch(b9_ctx* c) {
     // one launch: the time around its kernels; a burst of B9_DRAIN_ASYNC launches: from the first one's start to the last one's end
     float ms = 0; cudaEventElapsedTime(&ms, c->burst_open ? c->ev_burst : c->ev_a, c->ev_b);
     c->burst_open = false;
-    c->stats.last_drain_kernel_ms = ms;
-    if (c->h_ctl->overflow)
+    c->res_kernel_ms = ms;
+    if (c->h_ctl->overflow) {
+        c->running.store(0, std::memory_order_relaxed);
         return fail(B9_ENOSPC, "b9_drain_launch: results exceed max_result_bytes (%llu); drain fewer tasks or enlarge the staging",
                     (unsigned long long)c->max_result_bytes);
+    }
     c->res_bytes = c->h_ctl->bytes; c->res_n = c->h_ctl->total_cnt;
     c->res_popped = c->res_async_n;
     c->res_in_bytes = c->res_async_in_bytes;
     c->have_results = true;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->stats.last_drain_kernel_ms = ms;
     c->stats.last_drain_in_bytes = c->res_async_in_bytes;
     c->stats.last_drain_out_bytes = c->res_bytes;
     return B9_OK;
@@ -470,40 +651,52 @@ static int finish_launch(b9_ctx* c) {
 int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     if (!c) return fail(B9_EINVAL, "b9_drain_launch: ctx is NULL");
     if (handler < 0 || handler >= B9_H_COUNT_) return fail(B9_ENOSYS, "b9_drain_launch: unknown handler %d", handler);
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::mutex> out_lk(c->out_mu);
     CU(cudaSetDevice(c->device));
     // results of an earlier launch that were never fetched are dropped; their tasks are still
     // pending (a pop is committed by a successful fetch, never by a launch). (An open burst of async launches stays open.)
     c->have_results = false; c->res_async = false;
-    const uint64_t depth = c->tail_task - c->head_task;
-    const uint32_t n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
+    c->running.store(0, std::memory_order_relaxed);
     c->res_n = 0; c->res_popped = 0; c->res_bytes = 0; c->res_in_bytes = 0; c->res_peek = (peek & B9_DRAIN_PEEK) != 0;
-    c->res_async = false;
-    if (n == 0) { c->have_results = true; return 0; }
-    // payload bytes of the window
-    uint64_t in_bytes = 0;
+    cudaStream_t s = c->stream;
+    // the window: a snapshot of the ring's head under the bookkeeping lock. Only drain-side calls (all under out_mu)
+    // move the head or free segments, so the snapshot stays valid while the launch is prepared without c->mu.
+    struct Piece { Segment sg; uint64_t a, b; };
+    std::vector<Piece> pieces;
+    uint64_t head = 0; uint32_t n = 0; uint32_t count_mode = 0;
     {
-        uint64_t lo = c->head_task, hi = c->head_task + n;
+        std::lock_guard<std::mutex> lk(c->mu);
+        head = c->head_task;
+        const uint64_t depth = c->tail_task - c->head_task;
+        n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
+        count_mode = c->cancelled_pending ? 1u : 0u;
+        c->expired_since_launch = false;
+        const uint64_t lo = head, hi = head + n;
         for (const Segment& sg : c->segs) {
-            uint64_t a = std::max<uint64_t>(lo, sg.first_task), b = std::min<uint64_t>(hi, sg.first_task + sg.n);
-            if (a < b) {
-                CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));     // this batch's H2D + ingest must have landed
-                uint64_t o0 = 0, o1 = 0;
-                int rc = task_phys_off(c, sg, a, &o0); if (rc) return rc;
-                rc = task_phys_off(c, sg, b, &o1); if (rc) return rc;
-                in_bytes += o1 - o0;
-            }
+            const uint64_t a = std::max<uint64_t>(lo, sg.first_task), b = std::min<uint64_t>(hi, sg.first_task + sg.n);
+            if (a < b) pieces.push_back(Piece{sg, a, b});
         }
+    }
+    if (n == 0) { c->have_results = true; return 0; }
+    uint64_t in_bytes = 0;                                                  // payload bytes of the window
+    for (const Piece& pc : pieces) {
+        CU(cudaStreamWaitEvent(s, pc.sg.ready, 0));                         // this batch's H2D + ingest must have landed
+        uint64_t o0 = 0, o1 = 0;
+        int rc = task_phys_off(c, pc.sg, pc.a, &o0); if (rc) return rc;
+        rc = task_phys_off(c, pc.sg, pc.b, &o1); if (rc) return rc;
+        in_bytes += o1 - o0;
     }
     DrainArgs a{};
     a.payload = c->d_payload; a.off = c->d_off; a.hdr = c->d_hdr; a.ids = c->d_ids; a.slot_mask = c->slot_mask;
-    a.first_task = c->head_task; a.n_tasks = n; a.n_tiles = 0;             // (set per handler by launch_drain3)
+    a.first_task = head; a.n_tasks = n; a.n_tiles = 0;                     // (set per handler by launch_drain3)
     a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_ids = c->d_out_ids;
     a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_base = (const uint32_t*)c->d_tile_state; a.block_base = (const uint32_t*)c->d_tile_state + ((size_t)c->max_drain_tasks / D2_THREADS + 2); a.handler = handler;
-    a.count_mode = c->cancelled_pending ? 1u : 0u;
+    a.count_mode = count_mode;
     a.slow = c->d_slow; a.crc_shift_tabs = c->d_crc_shift;
     a.static_rounds = 0; a.one = 1u;
-    cudaStream_t s = c->stream;
+    c->drain_epoch = (c->drain_epoch + 1u) & 0xFFFFFFu;
+    if (c->drain_epoch == 0u) { c->drain_epoch = 1u; CU(cudaMemsetAsync(c->d_slow, 0, (size_t)c->max_drain_tasks * sizeof(SlowItem), s)); }   // the 24-bit tag wrapped: forget old tags
+    a.epoch = c->drain_epoch;
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
     int grid = 0;
     if (!c->burst_open) CU(cudaEventRecord(c->ev_burst, s));
@@ -516,27 +709,16 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     default:            le = launch_drain3<3>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
     }
     if (le != cudaSuccess) return fail(B9_EIO, "drain kernel launch failed: %s", cudaGetErrorString(le));
-    c->stats.kernel_launches += a.count_mode ? 3 : 1;                      // (+ tile_count_kernel and tile_scan_kernel)
-    static const bool dbg_skip_slow = getenv("B9_DEBUG_SKIP_SLOW") != nullptr;   // timing experiments only: deferred tasks get no record
-    if (handler == B9_H_IDENTITY && !dbg_skip_slow) {
-        // second kernel: the tasks the main identity kernel deferred (escaped strings, foreign framing, ...)
-        static int slow_per_sm = 0;
-        if (!slow_per_sm) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slow_per_sm, drain_slow_kernel, DS_WARPS * 32, 0) != cudaSuccess || slow_per_sm < 1) slow_per_sm = 4; }
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(c->sm_count * slow_per_sm)); cfg.blockDim = dim3(DS_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        le = cudaLaunchKernelEx(&cfg, drain_slow_kernel, a);
-        if (le == cudaSuccess) le = cudaGetLastError();
-        if (le != cudaSuccess) return fail(B9_EIO, "drain_slow_kernel launch failed: %s", cudaGetErrorString(le));
-        c->stats.kernel_launches++;
-    }
     CU(cudaEventRecord(c->ev_b, s));
     CU(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(DrainCtl), cudaMemcpyDeviceToHost, s));
-    c->stats.last_drain_tiles = (n + 127) / 128;   // (reported in units of 128 tasks)
-    c->stats.drains++;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->stats.kernel_launches += a.count_mode ? 3 : 1;                  // (+ tile_count_kernel and tile_scan_kernel)
+        c->stats.last_drain_tiles = (n + 127) / 128;                       // (reported in units of 128 tasks)
+        c->stats.drains++;
+    }
     c->res_async = true; c->res_async_n = n; c->res_async_in_bytes = in_bytes;
+    if (!c->res_peek) c->running.store(n, std::memory_order_relaxed);
     if (peek & B9_DRAIN_ASYNC) { c->burst_open = true; return (int64_t)n; }   // records = n minus the cancelled slots: known after b9_sync / b9_drain_fetch
     int rc = finish_launch(c);
     return rc ? rc : (int64_t)c->res_n;
@@ -544,15 +726,15 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
 
 int64_t b9_drain_fetch(b9_ctx* c, b9_results* out) {
     if (!c || !out) return fail(B9_EINVAL, "b9_drain_fetch: NULL argument");
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::mutex> out_lk(c->out_mu);
     CU(cudaSetDevice(c->device));
     { int rc = finish_launch(c); if (rc) return rc; }
     if (!c->have_results) return fail(B9_EINVAL, "b9_drain_fetch: no drain results are waiting");
     out->n_results = c->res_n; out->n_popped = c->res_popped; out->n_bytes = c->res_bytes; out->need_bytes = c->res_bytes;
+    out->task_duration = 0.f;
     if (c->res_n > out->cap_tasks || c->res_bytes > out->cap_bytes)
         return fail(B9_ENOSPC, "b9_drain_fetch: need %u records / %llu bytes, caller gave %u / %llu", c->res_n,
                     (unsigned long long)c->res_bytes, out->cap_tasks, (unsigned long long)out->cap_bytes);
-    CU(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const size_t n = c->res_n;
     CU(cudaEventRecord(c->ev_c, s));
@@ -570,13 +752,24 @@ int64_t b9_drain_fetch(b9_ctx* c, b9_results* out) {
     }
     CU(cudaEventRecord(c->ev_d, s));
     CU(cudaStreamSynchronize(s));
-    float ms = 0; cudaEventElapsedTime(&ms, c->ev_c, c->ev_d); c->stats.last_drain_d2h_ms = ms;
-    c->stats.bytes_d2h += c->res_bytes + n * (16 + 1 + 1 + 8 + 4);
-    if (!c->res_peek) {
-        c->head_task += c->res_popped; c->pending_bytes -= c->res_in_bytes; c->stats.tasks_drained += c->res_popped;
-        c->cancelled_pending -= std::min<uint64_t>(c->cancelled_pending, (uint64_t)(c->res_popped - c->res_n));
-        free_segments(c);
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_c, c->ev_d);
+    // TaskQueueCompleteRequest.task_duration (taskqueue.proto:50): the runner reports the seconds it spent on a task; a
+    // drain spends kernel + read-back time on res_popped tasks at once, so every task of the batch is charged its share
+    if (c->res_popped) out->task_duration = (c->res_kernel_ms + ms) * 1e-3f / (float)c->res_popped;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->stats.last_drain_d2h_ms = ms;
+        c->stats.bytes_d2h += c->res_bytes + n * (16 + 1 + 1 + 8 + 4);
+        if (!c->res_peek) {
+            c->head_task += c->res_popped; c->pending_bytes -= c->res_in_bytes; c->stats.tasks_drained += c->res_popped;
+            c->cancelled_pending -= std::min<uint64_t>(c->cancelled_pending, (uint64_t)(c->res_popped - c->res_n));
+            c->recount_cancelled = c->expired_since_launch;              // an expire ran between this drain's launch and its commit: its
+                                                                          // count included tasks of the window that are gone now
+            free_segments(c);
+        }
     }
+    if (!c->res_peek && c->recount_cancelled) { int rc = recount_cancelled_locked_out(c); if (rc) return rc; }
+    c->running.store(0, std::memory_order_relaxed);
     c->have_results = false; c->res_async = false; c->burst_open = false;
     return (int64_t)n;
 }
@@ -618,11 +811,19 @@ static size_t host_go_quote(const char* s, uint8_t* o, size_t cap) {
 
 int64_t b9_wire_encode(b9_ctx* c, const b9_wire_env* env, uint32_t max_tasks) {
     if (!c || !env || !env->workspace_name || !env->stub_id) return fail(B9_EINVAL, "b9_wire_encode: NULL argument");
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::mutex> out_lk(c->out_mu);
     CU(cudaSetDevice(c->device));
     c->have_results = false; c->res_async = false; c->burst_open = false;
-    const uint64_t depth = c->tail_task - c->head_task;
-    const uint32_t n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
+    c->running.store(0, std::memory_order_relaxed);
+    uint64_t head = 0; uint32_t n = 0;
+    cudaStream_t s = c->stream;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        head = c->head_task;
+        const uint64_t depth = c->tail_task - c->head_task;
+        n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(depth, max_tasks), c->max_drain_tasks);
+        for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(s, sg.ready, 0));
+    }
     c->res_n = 0; c->res_popped = 0; c->res_bytes = 0; c->res_in_bytes = 0; c->res_peek = true;
     if (n == 0) { c->have_results = true; return 0; }
     WireEnv we; memset(&we, 0, sizeof we);
@@ -637,26 +838,26 @@ int64_t b9_wire_encode(b9_ctx* c, const b9_wire_env* env, uint32_t max_tasks) {
         we.mid_len = (uint32_t)k;
     }
     we.max_retries = env->max_retries; we.timeout = env->timeout; we.ttl = env->ttl;
-    cudaStream_t s = c->stream;
-    for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(s, sg.ready, 0));
     CU(cudaMemcpyAsync(c->d_wire_env, &we, sizeof we, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(DrainCtl), s));
     WireArgs a{};
     a.payload = c->d_payload; a.off = c->d_off; a.hdr = c->d_hdr; a.ids = c->d_ids; a.ts = c->d_ts; a.exp = c->d_exp;
-    a.slot_mask = c->slot_mask; a.first_task = c->head_task; a.n_tasks = n;
+    a.slot_mask = c->slot_mask; a.first_task = head; a.n_tasks = n;
     a.out_payload = c->d_out_payload; a.out_cap = c->max_result_bytes; a.out_off = c->d_out_off; a.out_len = c->d_out_len;
     a.out_ids = c->d_out_ids; a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.ctl = c->d_ctl;
     CU(cudaEventRecord(c->ev_a, s));
     wire_encode_kernel<<<(n + 127) / 128, 128, 0, s>>>(a, c->d_wire_env);
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev_b, s));
-    c->stats.kernel_launches++;
     CU(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(DrainCtl), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));     // (the stack copy of `we` is consumed by now as well)
     if (c->h_ctl->overflow) return fail(B9_ENOSPC, "b9_wire_encode: records exceed max_result_bytes (%llu)", (unsigned long long)c->max_result_bytes);
     c->res_bytes = c->h_ctl->bytes; c->res_n = n; c->res_popped = 0; c->have_results = true;
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->res_kernel_ms = ms;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->stats.kernel_launches++;
     c->stats.last_drain_out_bytes = c->res_bytes;
-    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->stats.last_drain_kernel_ms = ms;
+    c->stats.last_drain_kernel_ms = ms;
     return (int64_t)n;
 }
 
@@ -718,11 +919,6 @@ __global__ void gather_tasks_kernel(const uint8_t* __restrict__ payload, const u
     if (lane == 0) { o_ts[w] = ts[slot]; o_exp[w] = exp[slot]; o_ids[w] = ids[slot]; o_flags[w] = (uint8_t)hdr_flags(h); o_retries[w] = (uint8_t)(h >> 40); }
 }
 
-__global__ void count_cancelled_kernel(const uint64_t* __restrict__ hdr, uint32_t slot_mask, uint64_t first_task, uint32_t n, unsigned long long* __restrict__ count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && (hdr_flags(hdr[(uint32_t)((first_task + i) & slot_mask)]) & 1u)) atomicAdd(count, 1ull);
-}
-
 // layout of one peer's meta message for n tasks (every section 16-byte aligned)
 struct MetaLayout { size_t rel, ts, exp, ids, flags, retries, total; };
 MetaLayout meta_layout(uint64_t n) {
@@ -782,7 +978,8 @@ int b9_comm_unique_id(uint8_t* out128) {
 int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
     if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(B9_EINVAL, "b9_comm_init: bad argument");
     int rc = load_nccl(); if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::mutex> in_lk(c->in_mu);
+    std::lock_guard<std::mutex> out_lk(c->out_mu);
     CU(cudaSetDevice(c->device));
     B9NcclId id; memcpy(id.internal, id128, 128);
     if (c->nccl_comm) { nccl_comm_destroy(c->nccl_comm); c->nccl_comm = nullptr; }   // re-init: the old communicator is not leaked
@@ -836,6 +1033,8 @@ int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
 int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     if (!c) return fail(B9_EINVAL, "b9_rebalance: ctx is NULL");
     if (!c->nccl_comm) return fail(B9_EINVAL, "b9_rebalance: b9_comm_init was not called");
+    std::lock_guard<std::mutex> in_lk(c->in_mu);       // the exchange rewrites both ends of the ring: no push, no drain meanwhile
+    std::lock_guard<std::mutex> out_lk(c->out_mu);
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     const int W = c->comm_world, R = c->comm_rank;
@@ -1044,7 +1243,7 @@ int b9_sync(b9_ctx* c) {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream_in));
     CU(cudaStreamSynchronize(c->stream));
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::mutex> out_lk(c->out_mu);
     return finish_launch(c);
 }
 

@@ -26,15 +26,16 @@ struct DrainCtl {
     unsigned long long bytes;       // result-byte cursor (one atomicAdd per tile); final value = total bytes
     unsigned int overflow;          // result staging too small
     unsigned int total_cnt;         // result records of the whole window
-    unsigned int n_slow;            // identity: tasks deferred to the second kernel (escapes, foreign framing)
+    unsigned int n_slow;            // identity: tasks deferred to the tail of the kernel (non-canonical escapes, foreign framing), reserved so far
     unsigned int slow_head;         // identity: next deferred task to take
+    unsigned int workers_done;      // identity: workers that are through with their tiles (everything they defer is published before)
 };
 
-// a task the main identity kernel could not settle with its quick look
+// A task the identity main loop could not settle. Published without a lock: w1 first, then (after a fence) w0, whose upper
+// 24 bits carry the launch's epoch — a consumer that claimed the slot polls w0 until the epoch is this launch's.
 struct SlowItem {
-    uint64_t goff;                  // physical ring offset of the payload
-    uint32_t len;                   // payload length; bit 31 = the SDK's canonical frame is present
-    uint32_t j;                     // index of the task's result record
+    unsigned long long w0;          // payload ring offset (40 bits) | epoch << 40
+    unsigned long long w1;          // len (30 bits) | bit 30 = HTTP body, bit 31 = the SDK's canonical frame is present | record index << 32
 };
 
 struct DrainArgs {
@@ -60,7 +61,8 @@ struct DrainArgs {
     const uint32_t* block_base;     // count_mode: [n / 256 + 1] ready tasks before each 256-slot block (tile_scan_kernel); last = window total
     int handler;
     uint32_t count_mode;            // 0 = no pending task is cancelled (record index = task index), 1 = record index from tile_base
-    SlowItem* slow;                 // identity: [n_tasks] work list for the second kernel
+    SlowItem* slow;                 // identity: [n_tasks] work list of deferred tasks
+    uint32_t epoch;                 // identity: this launch's tag in SlowItem.w0 (1 .. 2^24 - 1)
     const uint32_t* crc_shift_tabs; // crc32: [levels][4][256] "advance the CRC register over 2^k zero bytes" tables
     uint32_t one;                   // the integer 1 (a run-time value the compiler cannot fold: see swar_special16)
     uint32_t static_rounds;         // a worker's first static_rounds tiles are worker + q * workers, the rest come from the ticket counter

@@ -27,8 +27,9 @@ class DrainResult:
     has_result: np.ndarray   # uint8 [n]
     offsets: np.ndarray      # uint64 [n]   start of record i's bytes in `payload`
     lengths: np.ndarray      # uint32 [n]
-    payload: np.ndarray      # uint8 [n_bytes]  dense; byte order = tile completion order, use offsets
+    payload: np.ndarray      # uint8 [n_bytes]  byte order = tile completion order (16-byte padded ranges), use offsets
     n_popped: int
+    task_duration: float = 0.0   # seconds charged to every task of the drain (TaskQueueCompleteRequest.task_duration)
 
     @property
     def n(self) -> int:
@@ -129,8 +130,21 @@ class DeviceQueue:
         self._check(self._lib.b9_batch_push(self._ctx, ids.ctypes.data, pl.ctypes.data if pl.size else ids.ctypes.data,
                                             off.ctypes.data, n, C.byref(meta)))
 
+    def push_scattered(self, task_ids: np.ndarray, pointers: np.ndarray, lengths: np.ndarray) -> None:
+        """b9_batch_push_v: `pointers` uint64[n] host addresses of the payloads (anywhere in pageable memory),
+        `lengths` uint32[n]. The library gathers them into its page-locked arena (the pack step) and pushes that."""
+        ids = np.ascontiguousarray(task_ids, dtype=np.uint8)
+        ptrs = np.ascontiguousarray(pointers, dtype=np.uint64)
+        lens = np.ascontiguousarray(lengths, dtype=np.uint32)
+        n = lens.shape[0]
+        assert ids.size == n * 16 and ptrs.shape[0] == n
+        self._check(self._lib.b9_batch_push_v(self._ctx, ids.ctypes.data, ptrs.ctypes.data, lens.ctypes.data, n, None))
+
     def depth(self) -> int:                       # client.go:99-106 QueueLength / task_redis.go:112-119 TasksInFlight
         return int(self._lib.b9_depth(self._ctx))
+
+    def running(self) -> int:                     # task_redis.go:58 TasksClaimed / client.go:109 TasksRunning
+        return int(self._lib.b9_running(self._ctx))
 
     def depth_bytes(self) -> int:
         return int(self._lib.b9_depth_bytes(self._ctx))
@@ -166,9 +180,9 @@ class DeviceQueue:
         ln = np.zeros(max(n, 1), np.uint32)
         pl = np.empty(max(cap_bytes, 1), np.uint8)
         r = L.Results(ids.ctypes.data, status.ctypes.data, has.ctypes.data, off.ctypes.data, ln.ctypes.data, pl.ctypes.data,
-                      max(n, 1), max(cap_bytes, 1), 0, 0, 0, 0)
+                      max(n, 1), max(cap_bytes, 1), 0, 0, 0, 0, 0.0, 0)
         got = self._check(self._lib.b9_drain_fetch(self._ctx, C.byref(r)))
-        return DrainResult(ids[:got], status[:got], has[:got], off[:got], ln[:got], pl[:int(r.n_bytes)], int(r.n_popped))
+        return DrainResult(ids[:got], status[:got], has[:got], off[:got], ln[:got], pl[:int(r.n_bytes)], int(r.n_popped), float(r.task_duration))
 
     def drain_into(self, handler: str, max_tasks: int, res: "L.Results") -> int:
         """b9_drain straight into caller-owned (ideally pinned) buffers described by `res`."""

@@ -10,13 +10,18 @@
  *
  * Conventions
  *   - plain C, no exceptions across the boundary; `int` returns: 0 = ok, negative = -errno style
- *     code below; `b9_last_error()` gives text for the calling thread's last failure on a ctx.
+ *     code below; `b9_last_error()` gives text for the CALLING THREAD's last failure (thread-local,
+ *     whatever ctx is passed; a cgo caller must stay on its OS thread between the failing call and
+ *     this one: runtime.LockOSThread).
  *   - a `b9_ctx` owns all device and pinned memory of one GPU; callers own the buffers they pass.
  *     Every call copies what it needs before returning (cgo pointer rules), so Go may free or
  *     reuse its slices immediately. Buffers obtained from `b9_host_alloc` are page-locked: pass
  *     those for full PCIe bandwidth (pageable memory works, more slowly).
  *   - thread safety: all functions may be called concurrently from many OS threads (goroutine
- *     backed or not); calls on one ctx are serialised internally.
+ *     backed or not). Producers and the drainer of one ctx run CONCURRENTLY: pushes serialise among
+ *     themselves (FIFO order is the order in which they are enqueued), drain-side calls (launch,
+ *     fetch, expire, wire records) serialise among themselves, and neither side waits for the
+ *     other's DMA or kernels. b9_rebalance excludes both for its duration.
  *   - a batch is packed SoA: `task_ids` n x 16 raw UUID bytes, `payload` one blob, `offsets`
  *     n+1 byte offsets into it. A task's payload is the exact `TaskQueuePutRequest.payload`
  *     bytes (pkg/abstractions/taskqueue/taskqueue.proto:20-23), i.e. what the SDK's
@@ -32,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B9_ABI_VERSION 1u
+#define B9_ABI_VERSION 2u   /* 2: b9_results.task_duration, b9_batch_push_v, b9_running */
 
 /* ---- error codes ------------------------------------------------------------------------ */
 #define B9_OK          0
@@ -113,16 +118,22 @@ typedef struct b9_results {
     uint64_t *offsets;      /* [cap_tasks]    result i = payload[offsets[i] .. offsets[i]+lengths[i]) */
     uint32_t *lengths;      /* [cap_tasks]                                                       */
     uint8_t  *payload;      /* [cap_bytes]    TaskQueueCompleteRequest.result bytes
-                                              (taskqueue.proto:47-56). Dense (n_bytes in total),
-                                              records are FIFO-ordered but their bytes are laid out
-                                              in tile-completion order: always go through offsets */
+                                              (taskqueue.proto:47-56). Records are FIFO-ordered, their
+                                              bytes are laid out in tile-completion order, each tile's
+                                              range rounded up to 16 bytes: always go through offsets */
     uint32_t  cap_tasks;
     uint64_t  cap_bytes;
     /* filled by the library */
     uint32_t  n_results;    /* records written                                                   */
     uint32_t  n_popped;     /* tasks removed from the queue (n_results + compacted-away ones)    */
-    uint64_t  n_bytes;      /* total result bytes written to payload                             */
+    uint64_t  n_bytes;      /* bytes of payload in use (records + the <= 15 bytes of padding a tile's
+                               range is rounded up by): what a copy of the blob has to carry     */
     uint64_t  need_bytes;   /* on B9_ENOSPC: payload capacity that would have sufficed           */
+    float     task_duration;/* seconds charged to EVERY task of this drain: (kernel + read-back time) / n_popped.
+                               Feeds TaskQueueCompleteRequest.task_duration (taskqueue.proto:50), which the gateway
+                               RPUSHes (taskqueue.go:352) and taskQueueAutoscalerSampleFunc averages
+                               (taskqueue/autoscaler.go:18-51)                                    */
+    uint32_t  reserved_;
 } b9_results;
 
 typedef struct b9_stats {
@@ -169,11 +180,26 @@ int      b9_batch_push(b9_ctx *ctx, const uint8_t *task_ids, const uint8_t *payl
 int      b9_batch_push_async(b9_ctx *ctx, const uint8_t *task_ids, const uint8_t *payload,
                              const uint64_t *offsets, uint32_t n, const b9_push_meta *meta);
 
+/* The pack step: the n payloads sit anywhere in the caller's (pageable) memory — Go's `[][]byte`, one slice per
+ * TaskQueuePutRequest.payload — and are gathered by a few library threads (B9_PACK_THREADS, default min(16, cores))
+ * into one of two page-locked arenas owned by the context, together with the n + 1 offsets; the arena is then pushed
+ * like b9_batch_push_async. Everything is copied when the call returns (cgo pointer rules: `payloads[i]` may point into
+ * Go memory only if the array of pointers itself is C memory — INTEGRATION.md §1 shows the binding); while batch k is on
+ * the wire, batch k+1 is gathered into the other arena. */
+int      b9_batch_push_v(b9_ctx *ctx, const uint8_t *task_ids, const uint8_t *const *payloads,
+                         const uint32_t *lengths, uint32_t n, const b9_push_meta *meta);
+
 /* Pending tasks = what `TaskRepository.TasksInFlight` / `taskQueueClient.QueueLength` report for
  * this queue (pkg/repository/task_redis.go:112-119, taskqueue/client.go:99-106); feeds
  * `taskQueueAutoscalerSampleFunc` (taskqueue/autoscaler.go:18-51) unchanged. */
 uint64_t b9_depth(b9_ctx *ctx);
 uint64_t b9_depth_bytes(b9_ctx *ctx);
+
+/* Tasks a drain has claimed and not yet handed back: the window of the last b9_drain_launch (without B9_DRAIN_PEEK) until
+ * its b9_drain_fetch commits the pop. What `TaskRepository.TasksClaimed` (pkg/repository/task_redis.go:58) /
+ * `taskQueueClient.TasksRunning` (taskqueue/client.go:109) count for this queue: the first thing
+ * `taskQueueAutoscalerSampleFunc` reads (taskqueue/autoscaler.go:19). Lock-free. b9_depth() still includes these tasks. */
+uint64_t b9_running(b9_ctx *ctx);
 
 /* Marks every pending task whose expires_unix_ns is non-zero and <= now as cancelled — the
  * unclaimed-task branch of `Dispatcher.monitor` (pkg/task/dispatch.go:173-230). Returns count. */

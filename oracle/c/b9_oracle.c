@@ -727,10 +727,16 @@ static int run_one(scratch_t *sc, const env_t *env, const uint8_t *id, const uin
 }
 
 /* ------------------------------------------------------------------ batch API */
+/* Every thread owns a contiguous range of the batch and appends its results (and wire records) to its OWN growing
+ * buffer: the batch's result blob is then the threads' buffers back to back, moved by one memcpy per thread, in parallel.
+ * (Round 1 malloc'ed every result and gathered serially: 8 threads gave 1.2x of one.) */
 typedef struct {
     const uint8_t *ids, *payload; const uint64_t *offsets; uint32_t lo, hi; int handler; env_t env;
-    uint8_t *status, *has; uint32_t *out_len; uint8_t **out_ptr;   /* per-task malloc'd results */
-    int keep_wire; uint8_t **wire_ptr; uint32_t *wire_len;
+    uint8_t *status, *has; uint32_t *out_len;
+    buf_t out;                                  /* this thread's results, in task order */
+    int keep_wire; uint32_t *wire_len; buf_t wire;
+    /* second phase: where this thread's bytes go */
+    uint8_t *dst_out, *dst_wire; uint64_t base_out, base_wire; uint64_t *out_offsets, *wire_offsets; int over;
 } job_t;
 
 static void *worker(void *arg) {
@@ -741,13 +747,27 @@ static void *worker(void *arg) {
         int st = run_one(&sc, &j->env, j->ids + 16 * (size_t)i, j->payload + j->offsets[i], (size_t)(j->offsets[i + 1] - j->offsets[i]), j->handler, &has);
         j->status[i] = (uint8_t)st; j->has[i] = (uint8_t)has;
         j->out_len[i] = has ? (uint32_t)sc.res.len : 0;
-        if (has) { j->out_ptr[i] = (uint8_t *)malloc(sc.res.len ? sc.res.len : 1); memcpy(j->out_ptr[i], sc.res.p, sc.res.len); } else j->out_ptr[i] = NULL;
+        if (has && sc.res.len) buf_put(&j->out, sc.res.p, sc.res.len);
         if (j->keep_wire) {
-            if (st != B9O_REJECTED && sc.wire.len) { j->wire_ptr[i] = (uint8_t *)malloc(sc.wire.len); memcpy(j->wire_ptr[i], sc.wire.p, sc.wire.len); j->wire_len[i] = (uint32_t)sc.wire.len; }
-            else { j->wire_ptr[i] = NULL; j->wire_len[i] = 0; }
+            if (st != B9O_REJECTED && sc.wire.len) { buf_put(&j->wire, sc.wire.p, sc.wire.len); j->wire_len[i] = (uint32_t)sc.wire.len; }
+            else j->wire_len[i] = 0;
         }
     }
     arena_free_all(&sc.ar); free(sc.wire.p); free(sc.res.p);
+    return NULL;
+}
+
+static void *placer(void *arg) {
+    job_t *j = (job_t *)arg;
+    if (!j->over && j->out.len) memcpy(j->dst_out + j->base_out, j->out.p, j->out.len);
+    uint64_t o = j->base_out;
+    for (uint32_t i = j->lo; i < j->hi; i++) { o += j->out_len[i]; j->out_offsets[i + 1] = o; }
+    if (j->keep_wire) {
+        if (!j->over && j->wire.len) memcpy(j->dst_wire + j->base_wire, j->wire.p, j->wire.len);
+        uint64_t w = j->base_wire;
+        for (uint32_t i = j->lo; i < j->hi; i++) { w += j->wire_len[i]; j->wire_offsets[i + 1] = w; }
+    }
+    free(j->out.p); free(j->wire.p);
     return NULL;
 }
 
@@ -766,10 +786,8 @@ int64_t b9o_run_batch(const uint8_t *ids, const uint8_t *payload, const uint64_t
     if (!crc_ready) crc_init();
     if (nthreads < 1) nthreads = 1;
     if ((uint32_t)nthreads > n && n) nthreads = (int)n;
-    uint32_t *out_len = (uint32_t *)calloc(n + 1, sizeof(uint32_t));
-    uint8_t **out_ptr = (uint8_t **)calloc(n + 1, sizeof(uint8_t *));
-    uint8_t **wire_ptr = NULL; uint32_t *wire_len = NULL;
-    if (wire_offsets) { wire_ptr = (uint8_t **)calloc(n + 1, sizeof(uint8_t *)); wire_len = (uint32_t *)calloc(n + 1, sizeof(uint32_t)); }
+    uint32_t *out_len = (uint32_t *)calloc((size_t)n + 1, sizeof(uint32_t));
+    uint32_t *wire_len = wire_offsets ? (uint32_t *)calloc((size_t)n + 1, sizeof(uint32_t)) : NULL;
     job_t *jobs = (job_t *)calloc((size_t)nthreads, sizeof(job_t));
     pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
     for (int t = 0; t < nthreads; t++) {
@@ -778,30 +796,27 @@ int64_t b9o_run_batch(const uint8_t *ids, const uint8_t *payload, const uint64_t
         j->lo = (uint32_t)((uint64_t)n * (uint64_t)t / (uint64_t)nthreads); j->hi = (uint32_t)((uint64_t)n * (uint64_t)(t + 1) / (uint64_t)nthreads);
         j->env.workspace_name = workspace_name; j->env.stub_id = stub_id; j->env.executor = "taskqueue";
         j->env.max_retries = max_retries; j->env.timeout = timeout; j->env.ttl = ttl; j->env.now_unix_ns = now_unix_ns;
-        j->status = out_status; j->has = out_has; j->out_len = out_len; j->out_ptr = out_ptr;
-        j->keep_wire = wire_offsets != NULL; j->wire_ptr = wire_ptr; j->wire_len = wire_len;
+        j->status = out_status; j->has = out_has; j->out_len = out_len;
+        j->keep_wire = wire_offsets != NULL; j->wire_len = wire_len;
         if (nthreads == 1) worker(j); else pthread_create(&th[t], NULL, worker, j);
     }
     if (nthreads > 1) for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
-    int64_t total = 0; int over = 0;
+    uint64_t total = 0, wtotal = 0; int over = 0;
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t].base_out = total; jobs[t].base_wire = wtotal;
+        total += jobs[t].out.len; wtotal += jobs[t].wire.len;
+    }
+    if (total > out_cap || (wire_offsets && wtotal > wire_cap)) over = 1;
     out_offsets[0] = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        if ((uint64_t)total + out_len[i] > out_cap) over = 1;
-        if (!over && out_len[i]) memcpy(out_payload + total, out_ptr[i], out_len[i]);
-        total += out_len[i]; out_offsets[i + 1] = (uint64_t)total;
-        free(out_ptr[i]);
+    if (wire_offsets) wire_offsets[0] = 0;
+    for (int t = 0; t < nthreads; t++) {
+        job_t *j = &jobs[t];
+        j->dst_out = out_payload; j->dst_wire = wire_payload; j->out_offsets = out_offsets; j->wire_offsets = wire_offsets; j->over = over;
+        if (nthreads == 1) placer(j); else pthread_create(&th[t], NULL, placer, j);
     }
-    if (wire_offsets) {
-        uint64_t wt = 0; wire_offsets[0] = 0;
-        for (uint32_t i = 0; i < n; i++) {
-            if (wt + wire_len[i] > wire_cap) over = 1;
-            if (!over && wire_len[i]) memcpy(wire_payload + wt, wire_ptr[i], wire_len[i]);
-            wt += wire_len[i]; wire_offsets[i + 1] = wt; free(wire_ptr[i]);
-        }
-        free(wire_ptr); free(wire_len);
-    }
-    free(out_len); free(out_ptr); free(jobs); free(th);
-    return over ? -1 : total;
+    if (nthreads > 1) for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(out_len); free(wire_len); free(jobs); free(th);
+    return over ? -1 : (int64_t)total;
 }
 
 /* pkg/abstractions/taskqueue/autoscaler.go:53-79 — returns desired, *valid */

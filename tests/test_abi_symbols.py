@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol(so_path):
 
 def test_library_loads_and_reports_abi(so_path):
     lib = L.load()
-    assert lib.b9_abi_version() == 1
+    assert lib.b9_abi_version() == 2
     assert lib.b9_handler_name(0) == b"identity" and lib.b9_handler_name(3) == b"json_sum"
     assert lib.b9_handler_name(99) is None
     assert lib.b9_handler_id(b"crc32") == 1 and lib.b9_handler_id(b"echo") == 0

@@ -145,7 +145,8 @@ struct b9_ctx {
     uint32_t res_async_n = 0; uint64_t res_async_in_bytes = 0;
     DrainCtl* h_ctl = nullptr;                 // pinned
     uint8_t* d_xchg_send = nullptr; uint8_t* d_xchg_recv = nullptr; uint64_t xchg_send_cap = 0, xchg_recv_cap = 0;   // b9_rebalance staging, grow-only
-    uint64_t* h_scratch = nullptr; size_t h_scratch_words = 0;   // pinned, grown on demand (b9_rebalance's slot words + byte prefix)
+    uint64_t* d_prefix = nullptr; unsigned long long* d_scan_sums = nullptr;   // b9_rebalance: byte prefix of the pending tasks, on the device
+    uint64_t* d_rtab = nullptr; uint64_t* h_rtab = nullptr; size_t rtab_words = 0;   // b9_rebalance: all-gather tables + cut points (device / pinned), allocated once
     unsigned long long* d_count = nullptr; unsigned long long* h_count = nullptr;
     // results waiting on the device for b9_drain_fetch
     bool have_results = false, res_peek = false;
@@ -384,7 +385,8 @@ void b9_ctx_destroy(b9_ctx* c) {
     cudaFree(c->d_out_payload); cudaFree(c->d_out_off); cudaFree(c->d_out_ids); cudaFree(c->d_out_status); cudaFree(c->d_out_has); cudaFree(c->d_out_len); cudaFree(c->d_slow); cudaFree(c->d_wire_env); cudaFree(c->d_crc_shift);
     cudaFree(c->d_ctl); cudaFree(c->d_tile_state); cudaFree(c->d_count);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
-    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->h_rtab) cudaFreeHost(c->h_rtab);
+    cudaFree(c->d_rtab); cudaFree(c->d_prefix); cudaFree(c->d_scan_sums);
     cudaFree(c->d_xchg_send); cudaFree(c->d_xchg_recv);
     if (c->h_count) cudaFreeHost(c->h_count);
     if (c->ev_burst) cudaEventDestroy(c->ev_burst);
@@ -902,21 +904,129 @@ int load_nccl() {
 void nccl_comm_destroy(void* comm) { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm); }
 #define NC(call) do { int r_ = (call); if (r_ != 0) return fail(B9_EIO, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
 
-// one warp per task: payload bytes into the send buffer, slot words into the meta sections
+// ---- rebalance, device side ---------------------------------------------------------------------------------------
+// byte prefix of the pending tasks (prefix[0] = 0, prefix[i + 1] = bytes of tasks 0..i), from the slot ring's length words:
+// three small kernels (block sums, scan of the block sums, write-out) — only the W cut points ever cross PCIe
+constexpr uint32_t SCAN_BLOCK = 1024;        // tasks per block (256 threads x 4)
+__global__ void __launch_bounds__(256) scan_block_sums_kernel(const uint64_t* __restrict__ hdr, uint32_t slot_mask, uint64_t first_task, uint32_t n,
+                                                             unsigned long long* __restrict__ block_sum) {
+    __shared__ unsigned long long s_w[8];
+    const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * 4u;
+    unsigned long long v = 0;
+    #pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) if (base + k < n) v += hdr_len(hdr[(uint32_t)((first_task + base + k) & slot_mask)]);
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31u) == 0u) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long t = 0; for (int w = 0; w < 8; ++w) t += s_w[w]; block_sum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) scan_of_sums_kernel(unsigned long long* __restrict__ block_sum, uint32_t blocks) {   // in place, exclusive
+    __shared__ unsigned long long s_w[32];
+    const uint32_t per = (blocks + 1023u) / 1024u, lo = min(blocks, threadIdx.x * per), hi = min(blocks, lo + per);
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += block_sum[i];
+    unsigned long long inc = sum;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long x = s_w[lane], y = x;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, y, d); if ((int)lane >= d) y += t; }
+        s_w[lane] = y - x;
+    }
+    __syncthreads();
+    unsigned long long run = s_w[warp] + inc - sum;
+    for (uint32_t i = lo; i < hi; ++i) { const unsigned long long t = block_sum[i]; block_sum[i] = run; run += t; }
+}
+__global__ void __launch_bounds__(256) scan_write_kernel(const uint64_t* __restrict__ hdr, uint32_t slot_mask, uint64_t first_task, uint32_t n,
+                                                        const unsigned long long* __restrict__ block_base, uint64_t* __restrict__ prefix) {
+    __shared__ unsigned long long s_w[8];
+    const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * 4u;
+    unsigned long long l[4]; unsigned long long v = 0;
+    #pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) { l[k] = (base + k < n) ? hdr_len(hdr[(uint32_t)((first_task + base + k) & slot_mask)]) : 0ull; v += l[k]; }
+    unsigned long long inc = v;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    unsigned long long before = block_base[blockIdx.x];
+    for (uint32_t w = 0; w < warp; ++w) before += s_w[w];
+    unsigned long long run = before + inc - v;
+    if (blockIdx.x == 0 && threadIdx.x == 0) prefix[0] = 0;
+    #pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) { run += l[k]; if (base + k < n) prefix[base + k + 1] = run; }
+}
+
+// What one rank learns in the planning phase, written by the cut kernel and read back in ONE copy.
+struct RebalanceCuts {
+    uint64_t lo[16], hi[16];             // my FIFO range for every destination rank
+    uint64_t bytes[16];                  // payload bytes of that range
+    uint64_t phys[16];                   // physical ring offset of its first task
+    uint64_t contiguous[16];             // 1: the range is one contiguous byte range of the ring (send it from there)
+    uint64_t keep_end_phys;              // physical offset of the first task that leaves to a HIGHER rank (= end of what I keep)
+    uint64_t ok;                         // the plan succeeded
+};
+constexpr int REBALANCE_MAX_WORLD = 16;
+
+// ONE thread: the same plan function the host exports (rebalance_plan.h) over the device-resident prefix, plus the physical
+// facts the host needs to post the sends. tab = all-gathered (count, bytes, cancelled, 0) per rank; row_out = my row of the
+// send matrix (tasks, bytes per destination), all-gathered next.
+__global__ void rebalance_cut_kernel(const uint64_t* __restrict__ tab, uint32_t world, uint32_t rank, const uint64_t* __restrict__ prefix, uint64_t n,
+                                     const uint64_t* __restrict__ off, const uint64_t* __restrict__ hdr, uint32_t slot_mask, uint64_t first_task,
+                                     RebalanceCuts* __restrict__ cuts, uint64_t* __restrict__ row_out) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint64_t counts[REBALANCE_MAX_WORLD], bytes[REBALANCE_MAX_WORLD];
+    for (uint32_t r = 0; r < world; ++r) { counts[r] = tab[4 * r]; bytes[r] = tab[4 * r + 1]; }
+    RebalanceCuts c;
+    c.ok = b9_plan_ranges(world, rank, counts, bytes, prefix, n, c.lo, c.hi) == 0 ? 1ull : 0ull;
+    for (uint32_t d = 0; d < world; ++d) {
+        if (!c.ok) { c.lo[d] = c.hi[d] = 0; }
+        const uint64_t lo = c.lo[d], hi = c.hi[d];
+        c.bytes[d] = prefix[hi] - prefix[lo];
+        c.phys[d] = 0; c.contiguous[d] = 1;
+        if (hi > lo) {
+            const uint32_t s0 = (uint32_t)((first_task + lo) & slot_mask), s1 = (uint32_t)((first_task + hi - 1) & slot_mask);
+            c.phys[d] = off[s0];
+            c.contiguous[d] = (off[s1] + hdr_len(hdr[s1]) - off[s0] == c.bytes[d] && off[s1] >= off[s0]) ? 1ull : 0ull;
+        }
+        row_out[2 * d] = hi - lo; row_out[2 * d + 1] = c.bytes[d];
+    }
+    const uint64_t keep_hi = c.hi[rank];
+    c.keep_end_phys = keep_hi < n ? off[(uint32_t)((first_task + keep_hi) & slot_mask)] : 0;
+    *cuts = c;
+}
+
+// slot words of the tasks that leave (ids, lengths as relative offsets, flags, retries, timestamps, expiries) into one
+// meta message; with `out_payload` also their bytes (only for ranges that are not contiguous in the ring)
 __global__ void gather_tasks_kernel(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ off, const uint64_t* __restrict__ hdr,
                                     const uint4* __restrict__ ids, const int64_t* __restrict__ ts, const int64_t* __restrict__ exp,
-                                    uint32_t slot_mask, uint64_t first_task, uint32_t n, const uint64_t* __restrict__ rel /* n+1, device */,
-                                    uint8_t* __restrict__ out_payload, int64_t* __restrict__ o_ts, int64_t* __restrict__ o_exp,
+                                    uint32_t slot_mask, uint64_t first_task, uint32_t n, const uint64_t* __restrict__ prefix /* device prefix, at the range's first task */,
+                                    uint8_t* __restrict__ out_payload, uint64_t* __restrict__ o_rel, int64_t* __restrict__ o_ts, int64_t* __restrict__ o_exp,
                                     uint4* __restrict__ o_ids, uint8_t* __restrict__ o_flags, uint8_t* __restrict__ o_retries) {
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n) return;
-    const uint32_t slot = (uint32_t)((first_task + w) & slot_mask);
-    const uint64_t h = hdr[slot];
-    const uint32_t len = hdr_len(h);
-    const uint8_t* src = payload + off[slot];
-    uint8_t* dst = out_payload + (rel[w] - rel[0]);
-    for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
-    if (lane == 0) { o_ts[w] = ts[slot]; o_exp[w] = exp[slot]; o_ids[w] = ids[slot]; o_flags[w] = (uint8_t)hdr_flags(h); o_retries[w] = (uint8_t)(h >> 40); }
+    if (out_payload) {                                   // one warp per task
+        const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        if (w >= n) return;
+        const uint32_t slot = (uint32_t)((first_task + w) & slot_mask);
+        const uint64_t h = hdr[slot];
+        const uint32_t len = hdr_len(h);
+        const uint8_t* src = payload + off[slot];
+        uint8_t* dst = out_payload + (prefix[w] - prefix[0]);
+        for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+        if (lane == 0) { o_rel[w] = prefix[w]; if (w + 1 == n) o_rel[n] = prefix[n]; o_ts[w] = ts[slot]; o_exp[w] = exp[slot]; o_ids[w] = ids[slot]; o_flags[w] = (uint8_t)hdr_flags(h); o_retries[w] = (uint8_t)(h >> 40); }
+    } else {                                             // slot words only: one thread per task
+        const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+        if (w >= n) return;
+        const uint32_t slot = (uint32_t)((first_task + w) & slot_mask);
+        const uint64_t h = hdr[slot];
+        o_rel[w] = prefix[w]; if (w + 1 == n) o_rel[n] = prefix[n];
+        o_ts[w] = ts[slot]; o_exp[w] = exp[slot]; o_ids[w] = ids[slot]; o_flags[w] = (uint8_t)hdr_flags(h); o_retries[w] = (uint8_t)(h >> 40);
+    }
 }
 
 // layout of one peer's meta message for n tasks (every section 16-byte aligned)
@@ -933,8 +1043,8 @@ MetaLayout meta_layout(uint64_t n) {
     m.total = o; return m;
 }
 
-// drop k tasks from the tail of the ring (they were handed to another rank)
-int drop_back(b9_ctx* c, uint64_t k) {
+// drop k tasks from the tail of the ring (they were handed to another rank); cut_phys = physical offset of the first dropped task
+void drop_back(b9_ctx* c, uint64_t k, uint64_t cut_phys) {
     while (k && !c->segs.empty()) {
         Segment& sg = c->segs.back();
         if (sg.n <= k) {
@@ -942,17 +1052,14 @@ int drop_back(b9_ctx* c, uint64_t k) {
             c->event_pool.push_back(sg.ready); c->segs.pop_back();
         } else {
             const uint32_t keep = sg.n - (uint32_t)k;
-            uint64_t cut = 0;
-            int rc = task_phys_off(c, sg, sg.first_task + keep, &cut); if (rc) return rc;
-            const uint64_t nb = cut - sg.phys_start;
+            const uint64_t nb = cut_phys - sg.phys_start;               // (the cut lies inside this segment)
             c->pending_bytes -= sg.bytes - nb; c->tail_task -= k;
             sg.n = keep; sg.bytes = nb;
-            c->write_pos = sg.phys_start + ((nb + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
+            c->write_pos = sg.phys_start + b9_seg_span(nb);
             k = 0;
         }
     }
     if (c->segs.empty()) c->write_pos = 0;
-    return B9_OK;
 }
 
 }  // namespace
@@ -977,6 +1084,7 @@ int b9_comm_unique_id(uint8_t* out128) {
 
 int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
     if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(B9_EINVAL, "b9_comm_init: bad argument");
+    if (world > REBALANCE_MAX_WORLD) return fail(B9_EINVAL, "b9_comm_init: world %d > %d", world, REBALANCE_MAX_WORLD);
     int rc = load_nccl(); if (rc) return rc;
     std::lock_guard<std::mutex> in_lk(c->in_mu);
     std::lock_guard<std::mutex> out_lk(c->out_mu);
@@ -986,17 +1094,20 @@ int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
     void* comm = nullptr;
     NC(g_nccl.CommInitRank(&comm, world, id, rank));
     c->nccl_comm = comm; c->comm_rank = rank; c->comm_world = world;
-    // page-locked scratch for b9_rebalance's per-task bookkeeping, sized for a full slot ring, here and not on the first exchange
-    if (world > 1 && c->h_scratch_words < 2 * (size_t)c->ring_tasks + 2) {
-        if (c->h_scratch) cudaFreeHost(c->h_scratch);
-        c->h_scratch = nullptr; c->h_scratch_words = 0;
-        CU(cudaHostAlloc(&c->h_scratch, (2 * (size_t)c->ring_tasks + 2) * sizeof(uint64_t), cudaHostAllocDefault));
-        c->h_scratch_words = 2 * (size_t)c->ring_tasks + 2;
-    }
-    // ... and the two device arenas the exchange stages through (they grow on demand; a first size here keeps
-    // cudaMalloc, milliseconds for hundreds of MB, off the first exchange)
     if (world > 1) {
-        const uint64_t first = std::min<uint64_t>(c->ring_bytes / 4, 256ull << 20);
+        // everything the planning phase of b9_rebalance touches is allocated here, once: the byte prefix of a full slot ring,
+        // the block sums of its scan, the all-gather tables and the page-locked block the cut points come back in
+        if (!c->d_prefix) {
+            CU(cudaMalloc(&c->d_prefix, ((size_t)c->ring_tasks + 2) * sizeof(uint64_t)));
+            CU(cudaMalloc(&c->d_scan_sums, ((size_t)c->ring_tasks / SCAN_BLOCK + 2) * sizeof(unsigned long long)));
+        }
+        if (!c->d_rtab) {
+            c->rtab_words = 4 * (size_t)REBALANCE_MAX_WORLD * 2 + 2 * (size_t)REBALANCE_MAX_WORLD * (REBALANCE_MAX_WORLD + 1) + (size_t)REBALANCE_MAX_WORLD + sizeof(RebalanceCuts) / 8 + 16;
+            CU(cudaMalloc(&c->d_rtab, c->rtab_words * sizeof(uint64_t)));
+            CU(cudaHostAlloc(&c->h_rtab, c->rtab_words * sizeof(uint64_t), cudaHostAllocDefault));
+        }
+        // ... and a first size for the two arenas the slot words (and non-contiguous payload ranges) are staged in
+        const uint64_t first = std::max<uint64_t>((uint64_t)c->ring_tasks * 48 / 2, 16ull << 20);
         if (c->xchg_send_cap < first) { cudaFree(c->d_xchg_send); c->d_xchg_send = nullptr; c->xchg_send_cap = 0;
                                         if (cudaMalloc(&c->d_xchg_send, first) == cudaSuccess) c->xchg_send_cap = first; else cudaGetLastError(); }
         if (c->xchg_recv_cap < first) { cudaFree(c->d_xchg_recv); c->d_xchg_recv = nullptr; c->xchg_recv_cap = 0;
@@ -1026,10 +1137,20 @@ int b9_comm_init(b9_ctx* c, const uint8_t* id128, int rank, int world) {
     return B9_OK;
 }
 
-// Collective: every rank of the communicator must call it. Moves pending tasks between the ranks'
-// rings so that every rank holds ~1/W of the pending payload bytes: all-gather of
-// (count, bytes), the same byte-quantile plan on every rank, all-gather of the send matrix, then ONE
-// grouped ncclSend/ncclRecv exchange of slot words and payload bytes over NVLink.
+// Collective: every rank of the communicator must call it. Moves pending tasks between the ranks' rings so that every
+// rank holds ~1/W of the pending payload BYTES. Nothing per-task crosses PCIe:
+//   1. device: byte prefix of my pending tasks from the slot ring's length words (three small scan kernels);
+//   2. all-gather of (count, bytes, cancelled) per rank — on the device;
+//   3. device: ONE thread runs the byte-quantile plan (rebalance_plan.h, the function the CPU tests run) against the
+//      prefix and writes my cut points, the physical ring offsets at the cuts and my row of the send matrix;
+//   4. all-gather of the matrix rows; ONE copy brings table + cuts + matrix to the host (first synchronise);
+//   5. every rank decides whether what arrives fits its ring — slot count AND contiguous byte placement, with what leaves
+//      still in place — and the ranks vote (all-gather of one flag, second synchronise): if any rank cannot take its
+//      share, ALL return B9_ENOSPC with their rings untouched;
+//   6. the exchange, one grouped ncclSend/ncclRecv: payload ranges that are contiguous in the ring (a batch pushed in one
+//      piece is) leave straight from the ring, arriving payload lands straight in the ring space placed in 5; only the
+//      slot words (41 B per task) are staged through the two arenas;
+//   7. bookkeeping: what left is dropped from both ends, what arrived is appended source by source (ingest_kernel).
 int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     if (!c) return fail(B9_EINVAL, "b9_rebalance: ctx is NULL");
     if (!c->nccl_comm) return fail(B9_EINVAL, "b9_rebalance: b9_comm_init was not called");
@@ -1048,74 +1169,94 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         fprintf(stderr, "[b9_rebalance rank %d] %-28s %8.3f ms\n", R, what, std::chrono::duration<double, std::milli>(now - t_last).count());
         t_last = now;
     };
+    if (W == 1) {
+        if (info) { memset(info, 0, sizeof *info); info->world = 1; info->tasks_before = info->tasks_after = c->tail_task - c->head_task; info->bytes_before = info->bytes_after = c->pending_bytes; }
+        return B9_OK;
+    }
     for (const Segment& sg : c->segs) CU(cudaStreamWaitEvent(s, sg.ready, 0));
     c->have_results = false; c->res_async = false; c->burst_open = false;
+    c->running.store(0, std::memory_order_relaxed);
     free_segments(c);
     const uint64_t n = c->tail_task - c->head_task;
-    // byte prefix of my pending tasks (host bookkeeping holds every batch's offsets)
-    // (page-locked scratch: the 8 bytes per task travel at PCIe speed in both directions)
-    if (c->h_scratch_words < 2 * n + 2) {
-        if (c->h_scratch) cudaFreeHost(c->h_scratch);
-        c->h_scratch = nullptr; c->h_scratch_words = 0;
-        const size_t want = (size_t)(2 * n + 2) * 5 / 4;
-        CU(cudaHostAlloc(&c->h_scratch, want * sizeof(uint64_t), cudaHostAllocDefault));
-        c->h_scratch_words = want;
-    }
-    uint64_t* const hdrs = c->h_scratch;
-    uint64_t* const prefix = c->h_scratch + n;
-    prefix[0] = 0;
-    if (n) {   // lengths come back from the slot ring (the host keeps no per-task index)
-        const uint32_t slot0 = (uint32_t)(c->head_task & c->slot_mask);
-        const uint64_t first = std::min<uint64_t>(n, c->ring_tasks - slot0);
-        CU(cudaMemcpyAsync(hdrs, c->d_hdr + slot0, first * 8, cudaMemcpyDeviceToHost, s));
-        if (first < n) CU(cudaMemcpyAsync(hdrs + first, c->d_hdr, (n - first) * 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        for (uint64_t i = 0; i < n; ++i) prefix[i + 1] = prefix[i] + hdr_len(hdrs[i]);
-        if (prefix[n] != c->pending_bytes) return fail(B9_EIO, "b9_rebalance: ring bookkeeping inconsistent (%llu vs %llu bytes)",
-                                                       (unsigned long long)prefix[n], (unsigned long long)c->pending_bytes);
-    }
-    phase("slot words D2H + prefix");
-    // ---- 1. all-gather (count, bytes)
-    uint64_t* d_tab = nullptr; uint64_t* h_tab = nullptr;
-    const size_t tab_words = (size_t)W * 2 + (size_t)W * W * 2;
-    CU(cudaMalloc(&d_tab, (2 + tab_words) * sizeof(uint64_t)));
-    CU(cudaHostAlloc(&h_tab, (2 + tab_words) * sizeof(uint64_t), cudaHostAllocDefault));
-    struct Cleanup { uint64_t* d; uint64_t* h; std::vector<void*> bufs; ~Cleanup() { cudaFree(d); cudaFreeHost(h); for (void* b : bufs) cudaFree(b); } } cl{d_tab, h_tab, {}};
-    h_tab[0] = n; h_tab[1] = prefix[n];
-    CU(cudaMemcpyAsync(d_tab, h_tab, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    NC(g_nccl.AllGather(d_tab, d_tab + 2, 2, NCCL_U64, c->nccl_comm, s));
-    CU(cudaMemcpyAsync(h_tab + 2, d_tab + 2, (size_t)W * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    const uint64_t my_bytes = c->pending_bytes;
+    // ---- layout of the device / pinned table (64-bit words)
+    uint64_t* const d_me = c->d_rtab;                                   // [4] count, bytes, cancelled, 0
+    uint64_t* const d_tab = d_me + 4;                                   // [4 W] all-gathered
+    uint64_t* const d_row = d_tab + 4 * REBALANCE_MAX_WORLD;            // [2 W] my matrix row
+    uint64_t* const d_mat = d_row + 2 * REBALANCE_MAX_WORLD;            // [2 W W]
+    uint64_t* const d_vote = d_mat + 2 * REBALANCE_MAX_WORLD * REBALANCE_MAX_WORLD;   // [1 + W]
+    RebalanceCuts* const d_cuts = (RebalanceCuts*)(d_vote + 1 + REBALANCE_MAX_WORLD);
+    uint64_t* const h = c->h_rtab;
+    const size_t off_tab = 4, off_row = off_tab + 4 * REBALANCE_MAX_WORLD, off_mat = off_row + 2 * REBALANCE_MAX_WORLD,
+                 off_vote = off_mat + 2 * REBALANCE_MAX_WORLD * REBALANCE_MAX_WORLD, off_cuts = off_vote + 1 + REBALANCE_MAX_WORLD;
+    // ---- 1. byte prefix on the device
+    const uint32_t blocks = (uint32_t)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    if (n) {
+        scan_block_sums_kernel<<<blocks, 256, 0, s>>>(c->d_hdr, c->slot_mask, c->head_task, (uint32_t)n, c->d_scan_sums);
+        scan_of_sums_kernel<<<1, 1024, 0, s>>>(c->d_scan_sums, blocks);
+        scan_write_kernel<<<blocks, 256, 0, s>>>(c->d_hdr, c->slot_mask, c->head_task, (uint32_t)n, c->d_scan_sums, c->d_prefix);
+        CU(cudaGetLastError());
+        c->stats.kernel_launches += 3;
+    } else CU(cudaMemsetAsync(c->d_prefix, 0, sizeof(uint64_t), s));
+    // ---- 2. all-gather (count, bytes, cancelled)
+    h[0] = n; h[1] = my_bytes; h[2] = c->cancelled_pending; h[3] = 0;
+    CU(cudaMemcpyAsync(d_me, h, 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    NC(g_nccl.AllGather(d_me, d_tab, 4, NCCL_U64, c->nccl_comm, s));
+    // ---- 3. cuts, 4. matrix
+    rebalance_cut_kernel<<<1, 32, 0, s>>>(d_tab, (uint32_t)W, (uint32_t)R, c->d_prefix, n, c->d_off, c->d_hdr, c->slot_mask, c->head_task, d_cuts, d_row);
+    CU(cudaGetLastError());
+    c->stats.kernel_launches++;
+    NC(g_nccl.AllGather(d_row, d_mat, (size_t)2 * W, NCCL_U64, c->nccl_comm, s));
+    CU(cudaMemcpyAsync(h + off_tab, d_tab, (c->rtab_words - off_tab) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    std::vector<uint64_t> counts(W), bytes(W), lo(W), hi(W);
-    for (int r = 0; r < W; ++r) { counts[r] = h_tab[2 + 2 * r]; bytes[r] = h_tab[3 + 2 * r]; }
-    phase("all-gather counts");
-    // ---- 2. plan
-    if (b9_plan_ranges((uint32_t)W, (uint32_t)R, counts.data(), bytes.data(), prefix, n, lo.data(), hi.data()))
-        return fail(B9_EIO, "b9_rebalance: plan failed");
-    // ---- 3. all-gather of the send matrix rows (tasks, bytes per destination)
-    uint64_t* row = h_tab;   // reuse
-    for (int d = 0; d < W; ++d) { row[2 * d] = hi[d] - lo[d]; row[2 * d + 1] = prefix[hi[d]] - prefix[lo[d]]; }
-    uint64_t* d_row = d_tab; uint64_t* d_mat = d_tab + 2 + (size_t)W * 2;
-    CU(cudaMemcpyAsync(d_row, row, (size_t)W * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));   // d_tab has room: 2 + 2W >= 2W
-    NC(g_nccl.AllGather(d_row, d_mat, (size_t)W * 2, NCCL_U64, c->nccl_comm, s));
-    std::vector<uint64_t> mat((size_t)W * W * 2);
-    CU(cudaMemcpyAsync(mat.data(), d_mat, mat.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    phase("prefix + plan + matrix");
+    const RebalanceCuts& cuts = *(const RebalanceCuts*)(h + off_cuts);
+    const uint64_t* tab = h + off_tab;
+    const uint64_t* mat = h + off_mat;
     auto M_tasks = [&](int src, int dst) { return mat[((size_t)src * W + dst) * 2]; };
     auto M_bytes = [&](int src, int dst) { return mat[((size_t)src * W + dst) * 2 + 1]; };
-    phase("plan + all-gather matrix");
-    // ---- 4. pack what leaves, make room for what arrives (two grow-only device arenas kept in the ctx: a
-    // cudaMalloc per peer and call cost more than the exchange itself)
-    std::vector<uint8_t*> s_meta(W, nullptr), s_pay(W, nullptr), r_meta(W, nullptr), r_pay(W, nullptr);
+    if (!cuts.ok) return fail(B9_EIO, "b9_rebalance: ring bookkeeping inconsistent with the slot ring (%llu tasks, %llu bytes)", (unsigned long long)n, (unsigned long long)my_bytes);
+    bool any_cancelled = false;
+    for (int r = 0; r < W; ++r) any_cancelled |= tab[4 * r + 2] != 0;
+    // ---- 5. does what arrives fit? (placement with everything that leaves still in place: a receive never lands on bytes a send reads)
     uint64_t sent_tasks = 0, sent_bytes = 0, recv_tasks = 0, recv_bytes = 0;
+    for (int d = 0; d < W; ++d) if (d != R) { sent_tasks += cuts.hi[d] - cuts.lo[d]; sent_bytes += cuts.bytes[d]; recv_tasks += M_tasks(d, R); recv_bytes += M_bytes(d, R); }
+    std::vector<uint64_t> r_start(W, 0);
+    bool fits = n - sent_tasks + recv_tasks <= c->ring_tasks;
+    {
+        // a dry run of the appends on a copy of the placement state
+        uint64_t wp = c->write_pos, live = 0; bool have = !c->segs.empty();
+        const uint64_t oldest = have ? c->segs.front().phys_start : 0;
+        for (const Segment& sg : c->segs) live += sg.bytes;
+        for (int src = 0; src < W && fits; ++src) {
+            if (src == R || !M_tasks(src, R)) continue;
+            const uint64_t pb = M_bytes(src, R);
+            uint64_t st = 0;
+            if (!b9_ring_place(c->ring_bytes, have, have ? oldest : 0, wp, live, pb, &st)) { fits = false; break; }
+            r_start[src] = st;
+            have = true;                                               // (an empty ring's first arrival is placed at 0 and becomes the oldest segment: oldest = 0)
+            wp = st + b9_seg_span(pb); live += pb;
+        }
+    }
+    h[0] = fits ? 1 : 0;
+    CU(cudaMemcpyAsync(d_vote, h, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    NC(g_nccl.AllGather(d_vote, d_vote + 1, 1, NCCL_U64, c->nccl_comm, s));
+    CU(cudaMemcpyAsync(h + off_vote, d_vote, (size_t)(1 + W) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int r = 0; r < W; ++r)
+        if (!h[off_vote + 1 + r])
+            return fail(B9_ENOSPC, "b9_rebalance: rank %d cannot take its share (%llu tasks / %llu bytes arrive here); no rank changed its ring",
+                        r, (unsigned long long)recv_tasks, (unsigned long long)recv_bytes);
+    phase("feasibility vote");
+    // ---- 6. stage the slot words of what leaves (and the payload of ranges that are not one piece of the ring)
     auto al = [](uint64_t x) { return (x + 255ull) & ~255ull; };
     uint64_t need_s = 0, need_r = 0;
     for (int d = 0; d < W; ++d) {
         if (d == R) continue;
-        const uint64_t k = hi[d] - lo[d];
-        if (k) need_s += al(meta_layout(k).total) + al(prefix[hi[d]] - prefix[lo[d]] + 16);
+        const uint64_t k = cuts.hi[d] - cuts.lo[d];
+        if (k) need_s += al(meta_layout(k).total) + (cuts.contiguous[d] ? 0 : al(cuts.bytes[d] + 16));
         const uint64_t rk = M_tasks(d, R);
-        if (rk) need_r += al(meta_layout(rk).total) + al(M_bytes(d, R) + 16);
+        if (rk) need_r += al(meta_layout(rk).total);
     }
     auto ensure = [&](uint8_t*& buf, uint64_t& cap, uint64_t need) -> cudaError_t {
         if (need <= cap) return cudaSuccess;
@@ -1128,71 +1269,61 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
     };
     CU(ensure(c->d_xchg_send, c->xchg_send_cap, need_s));
     CU(ensure(c->d_xchg_recv, c->xchg_recv_cap, need_r));
+    std::vector<uint8_t*> s_meta(W, nullptr), r_meta(W, nullptr);
+    std::vector<const uint8_t*> s_pay(W, nullptr);
     uint64_t so = 0, ro = 0;
     for (int d = 0; d < W; ++d) {
         if (d == R) continue;
-        const uint64_t k = hi[d] - lo[d];
+        const uint64_t k = cuts.hi[d] - cuts.lo[d];
         if (k) {
             const MetaLayout ml = meta_layout(k);
-            const uint64_t pb = prefix[hi[d]] - prefix[lo[d]];
             s_meta[d] = c->d_xchg_send + so; so += al(ml.total);
-            s_pay[d] = c->d_xchg_send + so; so += al(pb + 16);
-            CU(cudaMemcpyAsync(s_meta[d] + ml.rel, prefix + lo[d], (k + 1) * 8, cudaMemcpyHostToDevice, s));
-            const uint32_t blocks = (uint32_t)((k * 32 + 255) / 256);
-            gather_tasks_kernel<<<blocks, 256, 0, s>>>(c->d_payload, c->d_off, c->d_hdr, c->d_ids, c->d_ts, c->d_exp, c->slot_mask,
-                                                       c->head_task + lo[d], (uint32_t)k, (const uint64_t*)(s_meta[d] + ml.rel), s_pay[d],
-                                                       (int64_t*)(s_meta[d] + ml.ts), (int64_t*)(s_meta[d] + ml.exp), (uint4*)(s_meta[d] + ml.ids),
-                                                       s_meta[d] + ml.flags, s_meta[d] + ml.retries);
+            uint8_t* staged = nullptr;
+            if (!cuts.contiguous[d]) { staged = c->d_xchg_send + so; so += al(cuts.bytes[d] + 16); }
+            s_pay[d] = staged ? staged : c->d_payload + cuts.phys[d];
+            const uint32_t threads = staged ? (uint32_t)k * 32u : (uint32_t)k;
+            gather_tasks_kernel<<<(threads + 255) / 256, 256, 0, s>>>(c->d_payload, c->d_off, c->d_hdr, c->d_ids, c->d_ts, c->d_exp, c->slot_mask,
+                                                                       c->head_task + cuts.lo[d], (uint32_t)k, c->d_prefix + cuts.lo[d], staged,
+                                                                       (uint64_t*)(s_meta[d] + ml.rel), (int64_t*)(s_meta[d] + ml.ts), (int64_t*)(s_meta[d] + ml.exp),
+                                                                       (uint4*)(s_meta[d] + ml.ids), s_meta[d] + ml.flags, s_meta[d] + ml.retries);
             CU(cudaGetLastError());
             c->stats.kernel_launches++;
-            sent_tasks += k; sent_bytes += pb;
         }
         const uint64_t rk = M_tasks(d, R);
-        if (rk) {
-            r_meta[d] = c->d_xchg_recv + ro; ro += al(meta_layout(rk).total);
-            r_pay[d] = c->d_xchg_recv + ro; ro += al(M_bytes(d, R) + 16);
-            recv_tasks += rk; recv_bytes += M_bytes(d, R);
-        }
+        if (rk) { r_meta[d] = c->d_xchg_recv + ro; ro += al(meta_layout(rk).total); }
     }
-    // capacity for what arrives (after what leaves is dropped)
-    if (n - sent_tasks + recv_tasks > c->ring_tasks)
-        return fail(B9_ENOSPC, "b9_rebalance: %llu incoming tasks do not fit the slot ring", (unsigned long long)recv_tasks);
-    phase("alloc + pack");
-    // ---- 5. the exchange: one grouped send/recv
+    // ---- the exchange: one grouped send/recv; arriving payload goes straight to its place in the ring
     NC(g_nccl.GroupStart());
     for (int d = 0; d < W; ++d) {
         if (d == R) continue;
-        const uint64_t k = hi[d] - lo[d];
+        const uint64_t k = cuts.hi[d] - cuts.lo[d];
         if (k) {
             NC(g_nccl.Send(s_meta[d], meta_layout(k).total, NCCL_U8, d, c->nccl_comm, s));
-            const uint64_t pb = prefix[hi[d]] - prefix[lo[d]];
-            if (pb) NC(g_nccl.Send(s_pay[d], pb, NCCL_U8, d, c->nccl_comm, s));
+            if (cuts.bytes[d]) NC(g_nccl.Send(s_pay[d], cuts.bytes[d], NCCL_U8, d, c->nccl_comm, s));
         }
         const uint64_t rk = M_tasks(d, R);
         if (rk) {
             NC(g_nccl.Recv(r_meta[d], meta_layout(rk).total, NCCL_U8, d, c->nccl_comm, s));
-            if (M_bytes(d, R)) NC(g_nccl.Recv(r_pay[d], M_bytes(d, R), NCCL_U8, d, c->nccl_comm, s));
+            if (M_bytes(d, R)) NC(g_nccl.Recv(c->d_payload + r_start[d], M_bytes(d, R), NCCL_U8, d, c->nccl_comm, s));
         }
     }
     NC(g_nccl.GroupEnd());
-    CU(cudaStreamSynchronize(s));
-    phase("grouped send/recv");
-    // ---- 6. what left: a prefix of my FIFO went to lower ranks, a suffix to higher ranks
+    phase("pack slot words + exchange");
+    // ---- 7. what left: a prefix of my FIFO went to lower ranks, a suffix to higher ranks
     {
-        const uint64_t front = lo[R], back = n - hi[R];
-        if (front) { c->pending_bytes -= prefix[front]; c->head_task += front; free_segments(c); }
-        if (back) { int rc = drop_back(c, back); if (rc) return rc; }
+        const uint64_t front = cuts.lo[R], back = n - cuts.hi[R];
+        uint64_t front_bytes = 0;
+        for (int d = 0; d < R; ++d) front_bytes += cuts.bytes[d];
+        if (back) drop_back(c, back, cuts.keep_end_phys);
+        if (front) { c->pending_bytes -= front_bytes; c->head_task += front; free_segments(c); }
     }
-    // ---- 7. what arrived is appended, source by source, as new segments of the ring
+    // what arrived is appended, source by source, as new segments at the places chosen in 5
     for (int src = 0; src < W; ++src) {
         const uint64_t rk = (src == R) ? 0 : M_tasks(src, R);
         if (!rk) continue;
         const MetaLayout ml = meta_layout(rk);
         const uint64_t pb = M_bytes(src, R);
-        uint64_t start = 0;
-        free_segments(c);
-        if (!place_segment(c, pb, &start)) return fail(B9_ENOSPC, "b9_rebalance: %llu incoming bytes do not fit the ring", (unsigned long long)pb);
-        if (pb) CU(cudaMemcpyAsync(c->d_payload + start, r_pay[src], pb, cudaMemcpyDeviceToDevice, s));
+        const uint64_t start = r_start[src];
         // slot words: ids may wrap in the slot ring
         const uint32_t slot0 = (uint32_t)(c->tail_task & c->slot_mask);
         const uint32_t first = (uint32_t)std::min<uint64_t>(rk, c->ring_tasks - slot0);
@@ -1208,23 +1339,25 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         else CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
         CU(cudaEventRecord(ready, s));
         c->segs.push_back(Segment{c->tail_task, (uint32_t)rk, start, pb, ready});
-        c->write_pos = start + ((pb + SEG_ALIGN - 1) & ~(SEG_ALIGN - 1));
+        c->write_pos = start + b9_seg_span(pb);
         c->tail_task += rk; c->pending_bytes += pb;
     }
-    phase("drop + append received");
-    // ---- 8. cancelled tasks may have moved either way: recount over the new window
-    {
+    // ---- cancelled tasks may have moved either way: recount over the new window (only if some rank held any)
+    if (any_cancelled) {
         const uint64_t depth = c->tail_task - c->head_task;
         CU(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned long long), s));
         if (depth) { count_cancelled_kernel<<<(uint32_t)((depth + 255) / 256), 256, 0, s>>>(c->d_hdr, c->slot_mask, c->head_task, (uint32_t)depth, c->d_count); CU(cudaGetLastError()); c->stats.kernel_launches++; }
         CU(cudaMemcpyAsync(c->h_count, c->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         c->cancelled_pending = *c->h_count;
+    } else {
+        CU(cudaStreamSynchronize(s));         // the caller's next call may be on any stream; the exchange is complete when we return
+        c->cancelled_pending = 0;
     }
-    phase("recount cancelled");
+    phase("drop + append + recount");
     if (info) {
         info->world = (uint32_t)W; info->rank = (uint32_t)R;
-        info->tasks_before = n; info->bytes_before = prefix[n];
+        info->tasks_before = n; info->bytes_before = my_bytes;
         info->tasks_sent = sent_tasks; info->bytes_sent = sent_bytes; info->tasks_received = recv_tasks; info->bytes_received = recv_bytes;
         info->tasks_after = c->tail_task - c->head_task; info->bytes_after = c->pending_bytes;
     }

@@ -1,7 +1,8 @@
 // Byte-quantile rebalance plan for the pending-task ring sharded over the GPUs of one box
 // (SURVEY.md §8e). Pure host arithmetic, identical on every rank given the same all-gathered
 // (count, bytes) table — exported through the C ABI so that the CPU (gloo) tests and the NCCL path
-// run the very same function.
+// run the very same function; on the GPU path ONE device thread runs it against the device-resident byte prefix
+// (rebalance_cut_kernel), so that only the 2 W cut points cross PCIe.
 //
 // Model: the pending tasks of all ranks form one global sequence ordered by (rank, local FIFO
 // index). Rank d is to end up with the tasks whose first byte's global position falls in
@@ -9,11 +10,16 @@
 // contiguous in that sequence, what it sends to every peer is a contiguous range of its local FIFO.
 #pragma once
 #include <stdint.h>
+#ifdef __CUDACC__
+#define B9_PLAN_HD __host__ __device__
+#else
+#define B9_PLAN_HD
+#endif
 
 // prefix[i] = payload bytes of the caller's pending tasks 0..i-1 (prefix[0] = 0, prefix[n] = bytes[rank]).
 // Fills send_lo/send_hi [world]: local task range [lo, hi) destined for each rank (empty ranges have lo == hi).
 // Returns 0, or -1 if the table is inconsistent with `prefix`.
-static inline int b9_plan_ranges(uint32_t world, uint32_t rank, const uint64_t* counts, const uint64_t* bytes,
+B9_PLAN_HD static inline int b9_plan_ranges(uint32_t world, uint32_t rank, const uint64_t* counts, const uint64_t* bytes,
                                  const uint64_t* prefix, uint64_t n, uint64_t* send_lo, uint64_t* send_hi) {
     if (world == 0 || rank >= world || counts[rank] != n || prefix[n] != bytes[rank]) return -1;
     uint64_t total = 0, base = 0;

@@ -8,7 +8,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 SO = os.environ.get("B9GPU_LIB") or os.path.join(PKG, "libb9gpu.so")     # B9GPU_LIB: an alternative build, for A/B timing
 
-B9_OK, B9_EINVAL, B9_ENOMEM, B9_ENOSPC, B9_E2BIG, B9_EIO, B9_ENODEV, B9_ENOSYS = 0, -22, -12, -28, -7, -5, -19, -38
+B9_OK, B9_EINVAL, B9_ENOMEM, B9_ENOSPC, B9_E2BIG, B9_EIO, B9_ENODEV, B9_ENOSYS, B9_ENOENT = 0, -22, -12, -28, -7, -5, -19, -38, -2
 H_IDENTITY, H_CRC32, H_VADD_F32, H_JSON_SUM = 0, 1, 2, 3
 ST_COMPLETE, ST_ERROR, ST_RETRY, ST_REJECTED, ST_UNSUPPORTED = 0, 1, 2, 3, 4
 TF_CANCELLED = 0x01
@@ -38,6 +38,11 @@ class Stats(C.Structure):
                 ("last_push_h2d_ms", C.c_float), ("last_drain_kernel_ms", C.c_float),
                 ("last_drain_d2h_ms", C.c_float), ("last_drain_tiles", C.c_uint32), ("sm_count", C.c_uint32),
                 ("last_drain_in_bytes", C.c_uint64), ("last_drain_out_bytes", C.c_uint64)]
+
+
+class SinkRecord(C.Structure):
+    _fields_ = [("task_id", C.c_void_p), ("data", C.c_void_p), ("length", C.c_uint32), ("index", C.c_uint32),
+                ("status", C.c_uint8), ("has_result", C.c_uint8)]
 
 
 class WireEnv(C.Structure):
@@ -77,6 +82,12 @@ SYMBOLS = {
     "b9_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "b9_rebalance": (C.c_int, [C.c_void_p, C.POINTER(RebalanceInfo)]),
     "b9_rebalance_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "b9_sink_object_bytes": (C.c_uint64, [C.c_uint32, C.c_uint64]),
+    "b9_sink_pack": (C.c_int64, [C.POINTER(Results), C.c_void_p, C.c_uint64]),
+    "b9_drain_fetch_object": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "b9_sink_get": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(SinkRecord)]),
+    "b9_sink_find": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(SinkRecord)]),
+    "b9_sink_result_json": (C.c_int64, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "b9_stats_get": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "b9_sync": (C.c_int, [C.c_void_p]),
     "b9_task_queue_scale": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int)]),

@@ -29,6 +29,7 @@
 #include "drain2.cuh"
 #include "rebalance_plan.h"
 #include "ring_place.h"
+#include "sink.h"
 #include "wire_encode.cuh"
 
 #include <dlfcn.h>
@@ -1362,6 +1363,93 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         info->tasks_after = c->tail_task - c->head_task; info->bytes_after = c->pending_bytes;
     }
     return B9_OK;
+}
+
+// =========================================================================== result sink
+uint64_t b9_sink_object_bytes(uint32_t n_records, uint64_t blob_bytes) { return b9sink::layout(n_records, blob_bytes).total; }
+
+int64_t b9_sink_pack(const b9_results* r, uint8_t* obj, uint64_t cap) {
+    if (!r || !obj) return fail(B9_EINVAL, "b9_sink_pack: NULL argument");
+    const uint32_t n = r->n_results;
+    const b9sink::Layout L = b9sink::layout(n, r->n_bytes);
+    if (cap < L.total) return fail(B9_ENOSPC, "b9_sink_pack: object needs %llu bytes, caller gave %llu", (unsigned long long)L.total, (unsigned long long)cap);
+    memset(obj, 0, L.blob);                                               // header + index, padding included: the object is deterministic
+    b9sink::write_header(obj, n, r->n_bytes, r->task_duration, r->n_popped);
+    if (n) {
+        memcpy(obj + L.ids, r->task_ids, (size_t)n * 16); memcpy(obj + L.offsets, r->offsets, (size_t)n * 8);
+        memcpy(obj + L.lengths, r->lengths, (size_t)n * 4); memcpy(obj + L.status, r->status, n); memcpy(obj + L.has, r->has_result, n);
+    }
+    if (r->n_bytes) memcpy(obj + L.blob, r->payload, r->n_bytes);
+    return (int64_t)L.total;
+}
+
+// b9_drain_fetch with the records landing as ONE sink object in the caller's buffer: the device-to-host copies write the
+// object's sections directly (pass page-locked memory for full PCIe bandwidth), the header is written last.
+int64_t b9_drain_fetch_object(b9_ctx* c, uint8_t* obj, uint64_t cap, uint64_t* object_bytes) {
+    if (!c || !obj) return fail(B9_EINVAL, "b9_drain_fetch_object: NULL argument");
+    uint32_t n = 0; uint64_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> out_lk(c->out_mu);
+        CU(cudaSetDevice(c->device));
+        { int rc = finish_launch(c); if (rc) return rc; }
+        if (!c->have_results) return fail(B9_EINVAL, "b9_drain_fetch_object: no drain results are waiting");
+        n = c->res_n; bytes = c->res_bytes;
+    }
+    const b9sink::Layout L = b9sink::layout(n, bytes);
+    if (object_bytes) *object_bytes = L.total;
+    if (cap < L.total) return fail(B9_ENOSPC, "b9_drain_fetch_object: object needs %llu bytes, caller gave %llu", (unsigned long long)L.total, (unsigned long long)cap);
+    memset(obj, 0, sizeof(b9sink::Header));
+    b9_results r; memset(&r, 0, sizeof r);
+    r.task_ids = obj + L.ids; r.offsets = (uint64_t*)(obj + L.offsets); r.lengths = (uint32_t*)(obj + L.lengths);
+    r.status = obj + L.status; r.has_result = obj + L.has; r.payload = obj + L.blob;
+    r.cap_tasks = n ? n : 1; r.cap_bytes = bytes ? bytes : 1;
+    const int64_t got = b9_drain_fetch(c, &r);
+    if (got < 0) return got;
+    // the gaps between the sections (alignment) are part of the object: make them deterministic
+    auto zero_gap = [&](uint64_t from, uint64_t to) { if (to > from) memset(obj + from, 0, to - from); };
+    zero_gap(L.ids + (uint64_t)n * 16, L.offsets); zero_gap(L.offsets + (uint64_t)n * 8, L.lengths); zero_gap(L.lengths + (uint64_t)n * 4, L.status);
+    zero_gap(L.status + n, L.has); zero_gap(L.has + n, L.blob);
+    b9sink::write_header(obj, n, bytes, r.task_duration, r.n_popped);
+    return got;
+}
+
+int b9_sink_get(const uint8_t* obj, uint64_t size, uint32_t index, b9_sink_record* rec) {
+    const b9sink::Header* h = b9sink::check(obj, size);
+    if (!h || !rec) return fail(B9_EINVAL, "b9_sink_get: not a sink object");
+    if (index >= h->n_records) return fail(B9_EINVAL, "b9_sink_get: record %u of %u", index, h->n_records);
+    const uint64_t off = ((const uint64_t*)(obj + h->off_offsets))[index];
+    const uint32_t len = ((const uint32_t*)(obj + h->off_lengths))[index];
+    if (off + len > h->blob_bytes) return fail(B9_EINVAL, "b9_sink_get: record %u points outside the blob", index);
+    rec->task_id = obj + h->off_ids + (uint64_t)index * 16;
+    rec->status = obj[h->off_status + index]; rec->has_result = obj[h->off_has + index];
+    rec->data = obj + h->off_blob + off; rec->length = len; rec->index = index;
+    return B9_OK;
+}
+
+int b9_sink_find(const uint8_t* obj, uint64_t size, const uint8_t* task_id, b9_sink_record* rec) {
+    const b9sink::Header* h = b9sink::check(obj, size);
+    if (!h || !task_id || !rec) return fail(B9_EINVAL, "b9_sink_find: not a sink object");
+    const uint8_t* ids = obj + h->off_ids;
+    for (uint32_t i = 0; i < h->n_records; ++i)
+        if (memcmp(ids + (uint64_t)i * 16, task_id, 16) == 0) return b9_sink_get(obj, size, i, rec);
+    return B9_ENOENT;
+}
+
+int64_t b9_sink_result_json(const uint8_t* data, uint64_t length, uint8_t* out, uint64_t cap) {
+    if (length == 0) return 0;                                             // `if len(result) > 0`: the field stays unset
+    if (!data || !out) return fail(B9_EINVAL, "b9_sink_result_json: NULL argument");
+    uint64_t vs = 0, ve = 0;
+    if (b9sink::raw_message(data, length, &vs, &ve)) {
+        if (ve - vs > cap) return fail(B9_ENOSPC, "b9_sink_result_json: %llu bytes needed", (unsigned long long)(ve - vs));
+        memcpy(out, data + vs, ve - vs);
+        return (int64_t)(ve - vs);
+    }
+    const uint64_t need = 11 + b9sink::base64_len(length) + 2;             // {"base64":"..."}
+    if (need > cap) return fail(B9_ENOSPC, "b9_sink_result_json: %llu bytes needed", (unsigned long long)need);
+    memcpy(out, "{\"base64\":\"", 11);
+    b9sink::base64_std(data, length, out + 11);
+    memcpy(out + 11 + b9sink::base64_len(length), "\"}", 2);
+    return (int64_t)need;
 }
 
 int b9_stats_get(b9_ctx* c, b9_stats* out) {

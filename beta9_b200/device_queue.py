@@ -184,6 +184,18 @@ class DeviceQueue:
         got = self._check(self._lib.b9_drain_fetch(self._ctx, C.byref(r)))
         return DrainResult(ids[:got], status[:got], has[:got], off[:got], ln[:got], pl[:int(r.n_bytes)], int(r.n_popped), float(r.task_duration))
 
+    def drain_object(self, handler: str, max_tasks: int = 1 << 22) -> np.ndarray:
+        """One drain whose records land as ONE result-sink object (b9_drain_fetch_object): header + index + blob."""
+        self._check(self._lib.b9_drain_launch(self._ctx, HANDLERS[handler], max_tasks, 0))
+        need = C.c_uint64(0)
+        probe = np.zeros(128, np.uint8)
+        rc = self._lib.b9_drain_fetch_object(self._ctx, probe.ctypes.data, 0, C.byref(need))      # B9_ENOSPC: tells the size, consumes nothing
+        if rc != L.B9_ENOSPC:
+            self._check(rc)
+        obj = np.empty(int(need.value), np.uint8)
+        self._check(self._lib.b9_drain_fetch_object(self._ctx, obj.ctypes.data, obj.size, C.byref(need)))
+        return obj
+
     def drain_into(self, handler: str, max_tasks: int, res: "L.Results") -> int:
         """b9_drain straight into caller-owned (ideally pinned) buffers described by `res`."""
         return self._check(self._lib.b9_drain(self._ctx, HANDLERS[handler], max_tasks, C.byref(res)))

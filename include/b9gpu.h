@@ -48,6 +48,7 @@ extern "C" {
 #define B9_EIO        (-5)   /* CUDA / NCCL runtime error (text in b9_last_error)               */
 #define B9_ENODEV    (-19)   /* no usable CUDA device                                           */
 #define B9_ENOSYS    (-38)   /* handler id unknown                                              */
+#define B9_ENOENT     (-2)   /* b9_sink_find: no record of that task in the object              */
 
 /* ---- GPU "kernel handlers": the user-function slot (sdk/src/beta9/runner/common.py:297-305)
  *      for which a device implementation exists. Semantics are those of the Python functions in
@@ -268,6 +269,33 @@ int      b9_rebalance(b9_ctx *ctx, b9_rebalance_info *info);   /* collective ove
  * [send_lo[d], send_hi[d]) destined for every rank d. Pure host arithmetic. */
 int      b9_rebalance_plan(uint32_t world, uint32_t rank, const uint64_t *counts, const uint64_t *bytes,
                            const uint64_t *prefix, uint64_t n, uint64_t *send_lo, uint64_t *send_hi);
+
+/* ---- result sink: one packed object per drain -------------------------------------------------------
+ * The reference stores every result with its own object-store PUT — `Dispatcher.StoreTaskResult`
+ * (pkg/task/dispatch.go:120-144), key "task/<id>/result" (dispatch.go:18-20), called from TaskQueueComplete when
+ * `in.Result != nil` (pkg/abstractions/taskqueue/taskqueue.go:394-399) — and the REST read-back applies
+ * `addResultToTask` (pkg/api/v1/task.go:295-325). Batched: the records of a drain form ONE self-describing object
+ * (128-byte header, SoA index: ids, offsets, lengths, status, has_result; then the result blob), uploaded once; the
+ * gateway keeps (object, record index) with the task. b9_drain_fetch_object is b9_drain_fetch with the device-to-host
+ * copies writing that object directly into `obj` (no per-task host work; *object_bytes = its size, also on B9_ENOSPC);
+ * b9_sink_pack builds the same object from records fetched the ordinary way. b9_sink_get / b9_sink_find give record i /
+ * the record of a task id (linear in the number of records) with pointers INTO the object; a record with has_result == 0
+ * is a task for which the reference uploads nothing. b9_sink_result_json is addResultToTask's rule for the bytes of one
+ * stored result: 0 = the field stays unset (empty object), else the number of bytes written to `out`: the JSON value
+ * itself when the bytes are valid JSON (json.Unmarshal into a json.RawMessage: syntax check only, white space around
+ * the value dropped), otherwise {"base64":"<std base64>"}. The sink functions are pure host code (no GPU needed). */
+typedef struct b9_sink_record {
+    const uint8_t *task_id;      /* 16 raw UUID bytes                                                     */
+    const uint8_t *data;         /* TaskQueueCompleteRequest.result bytes (meaningful when has_result)    */
+    uint32_t       length, index;
+    uint8_t        status, has_result;
+} b9_sink_record;
+uint64_t b9_sink_object_bytes(uint32_t n_records, uint64_t blob_bytes);
+int64_t  b9_sink_pack(const b9_results *results, uint8_t *obj, uint64_t cap);
+int64_t  b9_drain_fetch_object(b9_ctx *ctx, uint8_t *obj, uint64_t cap, uint64_t *object_bytes);
+int      b9_sink_get(const uint8_t *obj, uint64_t size, uint32_t index, b9_sink_record *rec);
+int      b9_sink_find(const uint8_t *obj, uint64_t size, const uint8_t *task_id, b9_sink_record *rec);
+int64_t  b9_sink_result_json(const uint8_t *data, uint64_t length, uint8_t *out, uint64_t cap);
 
 int      b9_stats_get(b9_ctx *ctx, b9_stats *out);
 int      b9_sync(b9_ctx *ctx);

@@ -48,7 +48,7 @@ class _Parser:
     decoding are fused here.
     """
 
-    MAX_DEPTH = 10000  # Go: "exceeded max depth" at 10000 nested values (scanner.go maxNestingDepth)
+    MAX_DEPTH = 10000  # Go: 10000 open containers are fine, the 10001st is "exceeded max depth" (scanner.go pushParseState)
 
     def __init__(self, data: bytes):
         self.d = data
@@ -79,15 +79,13 @@ class _Parser:
         return v
 
     def parse_value(self, depth: int) -> Any:
-        if depth > self.MAX_DEPTH:
-            raise self.err("exceeded max depth")
         if self.i >= self.n:
             raise self.err("unexpected end of JSON input")
         c = self.d[self.i]
-        if c == 0x7B:  # {
-            return self.parse_object(depth)
-        if c == 0x5B:  # [
-            return self.parse_array(depth)
+        if c == 0x7B or c == 0x5B:  # { [   (`depth` containers are open around this one)
+            if depth + 1 > self.MAX_DEPTH:
+                raise self.err("exceeded max depth")
+            return self.parse_object(depth) if c == 0x7B else self.parse_array(depth)
         if c == 0x22:
             return self.parse_string()
         if c == 0x2D or 0x30 <= c <= 0x39:

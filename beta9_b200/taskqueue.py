@@ -80,6 +80,7 @@ class _CallableWrapper:
     def __init__(self, func: Callable, parent: TaskQueue):
         self.func = func
         self.parent = parent
+        self._held: List[Task] = []       # drained on behalf of a map(): handed out by the next process_tasks()
 
     def __call__(self, *args: Any, **kwargs: Any) -> Any:
         # sdk taskqueue.py:218-224: callable only inside a container
@@ -149,7 +150,14 @@ class _CallableWrapper:
 
     # ---- consumer (what the runner loop + TaskQueueComplete hand back)
     def process_tasks(self, max_tasks: int = 1 << 22) -> List[Task]:
-        """Drain up to max_tasks pending tasks through the kernel handler; FIFO order."""
+        """Drain up to max_tasks pending tasks through the kernel handler; FIFO order. Tasks that a `map()` had to drain
+        on the way to its own (they were queued before it) are handed out first: nothing is dropped."""
+        out, self._held = self._held[:max_tasks], self._held[max_tasks:]
+        if len(out) < max_tasks:
+            out += self._drain(max_tasks - len(out))
+        return out
+
+    def _drain(self, max_tasks: int) -> List[Task]:
         res = self.parent.queue.drain(self.parent.gpu_handler, max_tasks=max_tasks)
         out = []
         for i in range(res.n):
@@ -159,14 +167,25 @@ class _CallableWrapper:
         return out
 
     def map(self, inputs: Sequence[Any]) -> Iterator[Any]:
-        """Fan out: one task per input, one push, one drain; yields each task's result (None for a task
-        that failed or produced no result, as function.py:266-268 does)."""
+        """Fan out: one task per input, one push, then drains until every one of ITS tasks has come back; yields each
+        task's result (None for a task that failed or produced no result, as function.py:266-268 does). The queue is
+        FIFO: tasks that earlier `put()`s left pending are drained on the way and kept for the next `process_tasks()`."""
         # Function.map spreads each input as positional arguments after `_format_args` (function.py:246-251):
         # a tuple or list IS the argument list, anything else is the single argument; never keyword arguments
         tasks = self.put_batch([(tuple(self._format_args(x)), {}) for x in inputs])
         if len(tasks) != len(inputs):
             raise RuntimeError("Failed to enqueue tasks")
-        done = {t.id: t for t in self.process_tasks(max_tasks=len(inputs))}
+        want = {t.id for t in tasks}
+        done = {}
+        while len(done) < len(want):
+            got = self._drain(1 << 22)
+            if not got:
+                break                                         # cancelled / expired tasks produce no record: their result is None
+            for t in got:
+                if t.id in want:
+                    done[t.id] = t
+                else:
+                    self._held.append(t)
         for t in tasks:
             yield done[t.id].result if t.id in done else None
 

@@ -120,3 +120,35 @@ def test_map_formats_inputs_like_function_format_args():
         {"args": [5], "kwargs": {}}, {"args": ["s"], "kwargs": {}}, {"args": [1, 2], "kwargs": {}}, {"args": [3, 4], "kwargs": {}},
         {"args": [[1], {"k": 2}], "kwargs": {}},            # two positional arguments, as the reference would pass them
         {"args": [{"d": 1}], "kwargs": {}}, {"args": [None], "kwargs": {}}, {"args": [], "kwargs": {}}, {"args": [], "kwargs": {}}]
+
+
+def test_map_keeps_the_results_of_tasks_queued_before_it():
+    """the queue is FIFO, so a map() behind pending put()s drains those first. Their results are kept for the
+    next process_tasks(), and map() goes on draining until its own tasks have come back."""
+    q = fake_queue()
+    fifo = []                                   # (id bytes) in push order
+
+    def push(ids, blob, offsets, **kw):
+        fifo.extend(bytes(r) for r in np.asarray(ids).reshape(-1, 16))
+    q.push_batch.side_effect = push
+
+    def drain(handler, max_tasks):
+        take = fifo[:2]                         # a small drain window: map() has to come back for more
+        del fifo[:2]
+        r = MagicMock()
+        r.n = len(take)
+        r.task_ids = np.frombuffer(b"".join(take), np.uint8).reshape(-1, 16) if take else np.zeros((0, 16), np.uint8)
+        r.status = np.zeros(r.n, np.uint8)
+        r.result = lambda i: json.dumps(take[i][:2].hex()).encode()
+        return r
+    q.drain.side_effect = drain
+
+    @task_queue(queue=q, max_pending_tasks=100)
+    def f(x):
+        return x
+    early = [f.put(i) for i in range(3)]
+    out = list(f.map([10, 11, 12]))
+    assert len(out) == 3 and all(o is not None for o in out)
+    held = f.process_tasks()
+    assert [t.id for t in held] == [t.id for t in early]           # nothing was dropped, FIFO order kept
+    assert all(t.status == "COMPLETE" for t in held)

@@ -1140,6 +1140,71 @@ __device__ __noinline__ bool esc_verify_canonical(uint8_t* __restrict__ sbuf, ui
     return carry == 0u;
 }
 
+// ------------------------------------------------------------------ cloudpickle-framed tasks (the function path)
+// `Function.map()` sends cloudpickle.dumps({"args": args, "kwargs": kwargs}) per input (sdk/src/beta9/abstractions/function.py:
+// 198-205,246-262); the gateway hands a blob that starts 80 05 95 to the runner as it is (pkg/abstractions/function/task.go:
+// 84,104-108), the runner unpickles, calls handler(*args, **kwargs) and cloudpickles the result (runner/function.py:236-283).
+// A GPU cannot unpickle objects; what it CAN do bit-exactly is the one shape the configurations' handlers take — a single
+// `str` argument, no keyword arguments — whose pickle is a fixed template around the UTF-8 bytes:
+//   80 05 | 95 <u64 len-11> | 7d 94 28 8c 04 "args" 94 | 8c <u8 n> or 58 <u32 n> | n bytes | 94 85 94 8c 06 "kwargs" 94 7d 94 75 2e
+// and identity's result is cloudpickle.dumps(s): 80 05 95 <u64 hdr+n+2> | the same string opcode + bytes | 94 2e. Anything
+// else (other argument types, memo references such as the interned "args", strings >= 64 KiB that the pickler writes outside
+// its frames, invalid UTF-8) is reported UNSUPPORTED — the host runs exactly those through the reference's CPU loop.
+struct PickleStr { uint32_t hdr, n; bool ok; };
+__device__ __forceinline__ PickleStr pickle_str_frame(const uint8_t* __restrict__ p, uint32_t len) {
+    PickleStr r; r.hdr = 0; r.n = 0; r.ok = false;
+    if (len < 39u) return r;
+    bool bad = (ld_u32_unaligned(p) & 0x00FFFFFFu) != 0x00950580u;                              // 80 05 95
+    bad |= ld_u32_unaligned(p + 3) != len - 11u || ld_u32_unaligned(p + 7) != 0u;          // FRAME length (u64)
+    bad |= ld_u32_unaligned(p + 11) != 0x8C28947Du;                                        // 7d 94 28 8c
+    bad |= ld_u32_unaligned(p + 15) != 0x67726104u;                                        // 04 'a' 'r' 'g'
+    bad |= (ld_u32_unaligned(p + 19) & 0x0000FFFFu) != 0x00009473u;                        // 's' 94
+    const uint32_t op = p[21];
+    if (op == 0x8Cu) { r.hdr = 2; r.n = p[22]; }
+    else if (op == 0x58u) { r.hdr = 5; r.n = ld_u32_unaligned(p + 22); bad |= r.n < 256u || r.n >= 65536u; }   // (the pickler's own choice of opcode)
+    else bad = true;
+    if (bad || len != 21u + r.hdr + r.n + 16u) return r;
+    const uint8_t* q = p + 21u + r.hdr + r.n;                                              // 94 85 94 8c | 06 6b 77 61 | 72 67 73 94 | 7d 94 75 2e
+    r.ok = ld_u32_unaligned(q) == 0x8C948594u && ld_u32_unaligned(q + 4) == 0x61776B06u && ld_u32_unaligned(q + 8) == 0x94736772u && ld_u32_unaligned(q + 12) == 0x2E75947Du;
+    return r;
+}
+// any byte >= 0x80 in p[lo, hi)? (4 bytes at a time; reads at most 3 bytes before lo / after hi, inside the payload's frame)
+__device__ __forceinline__ bool range_has_high_bit(const uint8_t* __restrict__ p, uint32_t lo, uint32_t hi) {
+    uint32_t acc = 0;
+    uint32_t i = lo;
+    for (; i + 4u <= hi; i += 4u) acc |= ld_u32_unaligned(p + i);
+    for (; i < hi; ++i) acc |= p[i];
+    return (acc & 0x80808080u) != 0u;
+}
+// UTF-8 as Python decodes a pickled str ("surrogatepass": the 3-byte encodings of U+D800..DFFF are accepted)
+__device__ __noinline__ bool utf8_valid_surrogatepass(const uint8_t* __restrict__ b, uint32_t n) {
+    uint32_t i = 0;
+    while (i < n) {
+        const uint8_t c = b[i];
+        if (c < 0x80) { ++i; continue; }
+        if (c >= 0xC2 && c <= 0xDF) { if (i + 2 > n || (b[i + 1] & 0xC0) != 0x80) return false; i += 2; continue; }
+        if (c >= 0xE0 && c <= 0xEF) {
+            if (i + 3 > n) return false;
+            const uint8_t lo = c == 0xE0 ? 0xA0 : 0x80;
+            if (b[i + 1] < lo || b[i + 1] > 0xBF || (b[i + 2] & 0xC0) != 0x80) return false;
+            i += 3; continue;
+        }
+        if (c >= 0xF0 && c <= 0xF4) {
+            if (i + 4 > n) return false;
+            const uint8_t lo = c == 0xF0 ? 0x90 : 0x80, hi = c == 0xF4 ? 0x8F : 0xBF;
+            if (b[i + 1] < lo || b[i + 1] > hi || (b[i + 2] & 0xC0) != 0x80 || (b[i + 3] & 0xC0) != 0x80) return false;
+            i += 4; continue;
+        }
+        return false;
+    }
+    return true;
+}
+__device__ __forceinline__ void pickle_result_header(uint8_t* __restrict__ o, uint32_t frame_len) {    // 80 05 95 <u64>
+    o[0] = 0x80; o[1] = 0x05; o[2] = 0x95;
+    o[3] = (uint8_t)frame_len; o[4] = (uint8_t)(frame_len >> 8); o[5] = (uint8_t)(frame_len >> 16); o[6] = (uint8_t)(frame_len >> 24);
+    o[7] = 0; o[8] = 0; o[9] = 0; o[10] = 0;
+}
+
 // ---------------------------------------------------------------- identity: deferred tasks, in the kernel's tail
 // What the main loop could not settle (escapes json.dumps would not have written, raw non-ASCII, foreign framing,
 // non-string arguments, HTTP bodies) is put on a work list and processed by the workers once they run out of tiles,
@@ -1147,7 +1212,7 @@ __device__ __noinline__ bool esc_verify_canonical(uint8_t* __restrict__ sbuf, ui
 // empty for SDK-made payloads, and a second launch cost ~6 us of every drain for nothing — profiles/r2_s4_*.)
 // No worker ever waits for another one: a worker takes what is claimable and leaves; every worker publishes its items
 // BEFORE it counts itself done, so the worker that counts last sees the final list and drains what is left.
-__device__ __noinline__ void slow_task(const DrainArgs& a, uint64_t goff, uint32_t lenw, uint32_t j, uint8_t* __restrict__ stage, uint32_t stage_cap, int lane) {
+__device__ __noinline__ void slow_task(const DrainArgs& a, uint64_t goff, uint32_t lenw, uint32_t j, bool pickle, uint8_t* __restrict__ stage, uint32_t stage_cap, int lane) {
     const uint32_t len = lenw & 0x3FFFFFFFu;
     const bool http = (lenw & 0x40000000u) != 0;
     const uint8_t* p = a.payload + goff;
@@ -1166,6 +1231,28 @@ __device__ __noinline__ void slow_task(const DrainArgs& a, uint64_t goff, uint32
     bool par = false, fast = false;
     EscLane L; L.start = 0; L.out_len = 0; L.npatch = 0; L.ok = true; L.len_change = false;
     L.patch_pos[0] = L.patch_pos[1] = 0; L.patch_cp[0] = L.patch_cp[1] = 0;
+    if (pickle) {
+        // cloudpickle-framed: lane 0 checks the template and the UTF-8 (anything else is not decided on the device)
+        uint32_t w = 0;
+        if (lane == 0) { const PickleStr ps = pickle_str_frame(p, len); if (ps.ok && utf8_valid_surrogatepass(p + 21u + ps.hdr, ps.n)) w = 0x80000000u | (ps.hdr << 24) | ps.n; }
+        w = __shfl_sync(0xffffffffu, w, 0);
+        const uint32_t hdr = (w >> 24) & 0x7Fu, n = w & 0xFFFFFFu;
+        const uint32_t out_len = w ? 11u + hdr + n + 2u : 0u;
+        unsigned long long base = 0;
+        const uint32_t alloc = (out_len + 15u) & ~15u;
+        if (lane == 0 && out_len) base = atomicAdd(&a.ctl->bytes, (unsigned long long)alloc);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const bool fits = base + alloc <= a.out_cap;
+        if (!fits && lane == 0) a.ctl->overflow = 1u;
+        if (w && fits) {
+            uint8_t* o = a.out_payload + base;
+            if (lane == 0) { pickle_result_header(o, hdr + n + 2u); o[11u + hdr + n + 1u] = 0x2E; }
+            warp_copy(o + 11, p + 21, hdr + n + 1u, lane);                 // string opcode + bytes + MEMOIZE
+        }
+        if (lane == 0) { a.out_off[j] = fits ? base : 0; a.out_len[j] = out_len; a.out_status[j] = w ? 0 : ST_UNSUPPORTED; a.out_has[j] = w ? 1 : 0; }
+        __syncwarp();
+        return;
+    }
     const uint32_t nbody = len - FRAME_PRE_LEN - FRAME_SUF_LEN;
     if (lenw & 0x80000000u) {                                              // canonical frame: the body needs transcoding
         uint32_t ol;
@@ -1232,7 +1319,7 @@ __device__ __noinline__ void d3_identity_tail(const DrainArgs& a, uint8_t* __res
             w1 = *(const volatile unsigned long long*)&a.slow[i].w1;
         }
         w0 = __shfl_sync(0xffffffffu, w0, 0); w1 = __shfl_sync(0xffffffffu, w1, 0);
-        slow_task(a, w0 & ((1ull << 40) - 1ull), (uint32_t)w1, (uint32_t)(w1 >> 32), stage, stage_cap, lane);
+        slow_task(a, w0 & ((1ull << 40) - 1ull), (uint32_t)w1, (uint32_t)(w1 >> 32) & 0xFFFFFFu, ((w1 >> 56) & 1ull) != 0ull, stage, stage_cap, lane);
     }
 }
 
@@ -1329,6 +1416,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         const uint32_t my_soff = (mine && staged) ? W.soff[k] : 0u;
         const uint64_t my_goff = mine ? W.goff[k] : 0ull;
         const bool my_http = mine && (W.flg[k] & B9_TF_HTTP_BODY_BIT) != 0;
+        const bool my_pickle = mine && (W.flg[k] & B9_TF_PICKLE_BIT) != 0;
         TaskRec rec; rec.ready = mine; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
         bool clobbered = false;
         if (HANDLER == 0) {
@@ -1343,7 +1431,22 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                     const uint32_t tok = my_len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2;
                     if (tok > 2) { rec.has = 1; rec.mode = OM_COPY; rec.src_off = FRAME_PRE_LEN - 1; rec.src_len = tok; rec.out_len = tok; }
                 } else { rec.mode = OM_DEFER; rec.value = (long long)(q & 1u); }
-                if (my_http) { rec.has = 0; rec.out_len = 0; rec.mode = OM_DEFER; rec.value = 0; }   // an HTTP body: the map rules decide (second kernel)
+                if (my_http) { rec.has = 0; rec.out_len = 0; rec.mode = OM_DEFER; rec.value = 0; }   // an HTTP body: the map rules decide (kernel tail)
+                if (my_pickle) {                                           // cloudpickle-framed (the function path): one str argument, settled here when it is ASCII
+                    rec.has = 0; rec.out_len = 0; rec.mode = OM_DEFER; rec.value = 2;
+                    if (staged) {
+                        uint8_t* p = sbuf + my_soff;
+                        const PickleStr ps = pickle_str_frame(p, my_len);
+                        if (ps.ok && !range_has_high_bit(p, 21u + ps.hdr, 21u + ps.hdr + ps.n)) {
+                            // the result is the string opcode run with a new frame header in front and STOP behind: patch the
+                            // 11 bytes before it and the byte after its MEMOIZE in the stage buffer; the task is then a copy
+                            pickle_result_header(p + 10, ps.hdr + ps.n + 2u);
+                            p[21u + ps.hdr + ps.n + 1u] = 0x2E;
+                            const uint32_t tok = 11u + ps.hdr + ps.n + 2u;
+                            rec.has = 1; rec.mode = OM_COPY; rec.src_off = 10; rec.src_len = tok; rec.out_len = tok; rec.value = 0;
+                        }
+                    }
+                }
             }
             if constexpr (HANDLER == 0 && T == 32) {
                 // framed, but the body holds escapes: the warp checks that they are json.dumps's own (then the task is a copy after all)
@@ -1363,6 +1466,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             // crc32: the whole warp works on one task at a time (tasks are long and of very different lengths)
             for (uint32_t kt = 0; kt < nt; ++kt) {
                 if (!((ready_mask_t >> kt) & 1u)) continue;
+                if (W.flg[kt] & B9_TF_PICKLE_BIT) { if (lane == (int)kt) rec.status = ST_UNSUPPORTED; continue; }   // function path: identity only
                 if (W.flg[kt] & B9_TF_HTTP_BODY_BIT) {                      // an HTTP body: the sequential parser with the map rules
                     if (lane == (int)kt) d2_parse_and_size<1>(staged ? (const uint8_t*)(sbuf + W.soff[kt]) : a.payload + W.goff[kt], W.len[kt], rec, s_crc_table, true);
                     continue;
@@ -1375,6 +1479,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             // json_sum: the whole warp parses one document at a time
             for (uint32_t kt = 0; kt < nt; ++kt) {
                 if (!((ready_mask_t >> kt) & 1u)) continue;
+                if (W.flg[kt] & B9_TF_PICKLE_BIT) { if (lane == (int)kt) rec.status = ST_UNSUPPORTED; continue; }
                 if (W.flg[kt] & B9_TF_HTTP_BODY_BIT) {
                     if (lane == (int)kt) d2_parse_and_size<3>(staged ? (const uint8_t*)(sbuf + W.soff[kt]) : a.payload + W.goff[kt], W.len[kt], rec, nullptr, true);
                     continue;
@@ -1390,6 +1495,8 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                     else d2_parse_and_size<3>(tp ? tp : a.payload + W.goff[kt], W.len[kt], rec, nullptr);
                 }
             }
+        } else if (my_pickle) {
+            rec.status = ST_UNSUPPORTED;                                   // function path: identity only
         } else if (mine) {
             int fr = 0;
             if (HANDLER == 2 && staged && !my_http) fr = vadd_fast(sbuf + my_soff, my_len, s_b64, rec);
@@ -1432,7 +1539,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
                 a.out_ids[j] = __ldg(a.ids + slot);
                 if (HANDLER == 0 && rec.mode == OM_DEFER) {                // the second kernel writes the rest of the record
                     SlowItem* it = a.slow + atomicAdd(&a.ctl->n_slow, 1u);
-                    it->w1 = (unsigned long long)(my_len | (rec.value ? 0x80000000u : 0u) | (my_http ? 0x40000000u : 0u)) | ((unsigned long long)j << 32);
+                    it->w1 = (unsigned long long)(my_len | (rec.value == 1 ? 0x80000000u : 0u) | (my_http ? 0x40000000u : 0u)) | ((unsigned long long)j << 32) | (rec.value == 2 ? (1ull << 56) : 0ull);
                     __threadfence();
                     *(volatile unsigned long long*)&it->w0 = my_goff | ((unsigned long long)a.epoch << 40);
                 } else { a.out_off[j] = fits ? ob : 0; a.out_len[j] = rec.out_len; a.out_status[j] = rec.status; a.out_has[j] = rec.has; }

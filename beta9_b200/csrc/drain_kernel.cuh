@@ -19,6 +19,7 @@ __host__ __device__ __forceinline__ uint64_t hdr_pack(uint32_t len, uint8_t flag
 __host__ __device__ __forceinline__ uint32_t hdr_len(uint64_t h) { return (uint32_t)h; }
 __host__ __device__ __forceinline__ uint32_t hdr_flags(uint64_t h) { return (uint32_t)(h >> 32) & 0xFFu; }
 constexpr uint32_t B9_TF_HTTP_BODY_BIT = 0x02u;      // == B9_TF_HTTP_BODY (include/b9gpu.h)
+constexpr uint32_t B9_TF_PICKLE_BIT    = 0x04u;      // == B9_TF_PICKLE
 
 struct DrainCtl {
     unsigned long long ticket;      // next tile to hand out
@@ -35,7 +36,7 @@ struct DrainCtl {
 // 24 bits carry the launch's epoch — a consumer that claimed the slot polls w0 until the epoch is this launch's.
 struct SlowItem {
     unsigned long long w0;          // payload ring offset (40 bits) | epoch << 40
-    unsigned long long w1;          // len (30 bits) | bit 30 = HTTP body, bit 31 = the SDK's canonical frame is present | record index << 32
+    unsigned long long w1;          // len (30 bits) | bit 30 = HTTP body, bit 31 = the SDK's canonical frame is present | record index (24 bits) << 32 | bit 56 = cloudpickle-framed
 };
 
 struct DrainArgs {

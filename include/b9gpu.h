@@ -89,6 +89,14 @@ enum b9_status {
                                   is an empty payload; B9_ST_REJECTED = HTTP 400 "invalid request payload".
                                   (Query-string arguments are the host's to merge before the push.)            */
 
+#define B9_TF_PICKLE    0x04u  /* the payload is the argument blob of the FUNCTION path: cloudpickle.dumps({"args": args,
+                                  "kwargs": kwargs}) as `.map()` / `.remote()` send it (sdk/src/beta9/abstractions/function.py:
+                                  198-205), which the gateway hands to the runner untouched when it starts 80 05 95
+                                  (pkg/abstractions/function/task.go:84,104-108); the result bytes are cloudpickle.dumps(result)
+                                  (sdk/src/beta9/runner/function.py:236-283). The device settles ONE shape bit-exactly — a single
+                                  `str` argument (< 64 KiB of UTF-8), no keyword arguments, handler identity — and reports every
+                                  other pickle B9_ST_UNSUPPORTED for the host's CPU loop.                                      */
+
 typedef struct b9_ctx b9_ctx;
 
 typedef struct b9_opts {

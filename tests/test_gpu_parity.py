@@ -423,3 +423,37 @@ def test_result_capacity_errors_do_not_consume():
         assert e.value.code in (L.B9_E2BIG, L.B9_EINVAL)
     finally:
         q.close()
+
+
+# ---- BASELINE.json configs at their stated per-GPU sizes (parity was run at reduced sizes for 3 of 4 configs)
+def test_crc32_1m_zipf_full_size():
+    """configs[2]: 1M zipf 32..4096-char strings through crc32, every record against the oracle."""
+    from beta9_b200.device_queue import DeviceQueue
+    b = synth.crc_batch(1_000_000)
+    with DeviceQueue(ring_bytes=2 << 30, ring_tasks=1 << 21, max_drain_tasks=1 << 21, max_result_bytes=1 << 28) as q:
+        r = run_gpu(q, b, "crc32")
+    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "crc32", nthreads=32, out_cap=16 * b.n + 64)
+    assert_matches_oracle(b, r, o)
+    assert int(r.status.sum()) == 0
+
+
+def test_json_sum_100k_full_size(dq):
+    """configs[4]: 100k x 1 KB JSON documents through json_sum."""
+    b = synth.json_batch(100_000)
+    r = run_gpu(dq, b, "json_sum")
+    assert_matches_oracle(b, r, coracle.run_batch(b.task_ids, b.payload, b.offsets, "json_sum", nthreads=32, out_cap=24 * b.n + 64))
+    assert int(r.status.sum()) == 0 and int(r.has_result.sum()) == b.n
+
+
+def test_vadd_f32_per_gpu_share_of_10m(dq):
+    """configs[3]: 10M x 256 B fp32 vector-add over 8 GPUs = 1.25M tasks per GPU; float results within 1e-6 rel
+    (north_star) — they are bit-equal to the oracle's (numpy's IEEE add), which is stricter."""
+    b = synth.vadd_batch(1_250_000)
+    r = run_gpu(dq, b, "vadd_f32")
+    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "vadd_f32", nthreads=32, out_cap=200 * b.n + 64)
+    assert_matches_oracle(b, r, o)
+    import base64
+    for i in range(0, b.n, 100_003):
+        got = np.frombuffer(base64.b64decode(r.result(i)[1:-1]), "<f4")
+        want = np.frombuffer(base64.b64decode(o.result(i)[1:-1]), "<f4")
+        assert np.allclose(got, want, rtol=1e-6, atol=0)

@@ -145,7 +145,7 @@ def test_pusher_and_drainer_threads_run_concurrently(dq):
     assert not tp.is_alive() and not tc.is_alive()
     assert dq.depth() == 0
     print(f"serial {serial * 1e3:.1f} ms, two threads {piped * 1e3:.1f} ms")
-    assert piped < 0.9 * serial, (piped, serial)   # H2D of batch k+1 ran beside the kernel + D2H of batch k
+    assert piped < 0.95 * serial, (piped, serial)  # H2D of batch k+1 ran beside the kernel + D2H of batch k (typically ~0.7)
     for t in pins:
         for p in t:
             p.free()

@@ -70,6 +70,9 @@ SYMBOLS = {
     "b9_batch_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PushMeta)]),
     "b9_batch_push_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PushMeta)]),
     "b9_batch_push_v": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PushMeta)]),
+    "b9_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8]),
+    "b9_flush": (C.c_int64, [C.c_void_p]),
+    "b9_buffered": (C.c_uint64, [C.c_void_p]),
     "b9_depth": (C.c_uint64, [C.c_void_p]),
     "b9_running": (C.c_uint64, [C.c_void_p]),
     "b9_depth_bytes": (C.c_uint64, [C.c_void_p]),

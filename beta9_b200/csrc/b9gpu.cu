@@ -30,6 +30,7 @@
 #include "rebalance_plan.h"
 #include "ring_place.h"
 #include "sink.h"
+#include "submit_buffer.h"
 #include "wire_encode.cuh"
 
 #include <dlfcn.h>
@@ -115,6 +116,9 @@ struct b9_ctx {
     // (Dispatcher.Register's goroutine-safety contract, pkg/task/dispatch.go:71-73).
     std::mutex in_mu, out_mu, mu;
     std::mutex pack_mu; PackPool* pack_pool = nullptr; PackArena pack[2]; int pack_next = 0;
+    // micro-batching of single-task submissions (b9_submit / b9_flush): two page-locked arenas, lock-free appends
+    std::mutex sb_mu; SubmitBuffer* sb = nullptr; cudaEvent_t sb_free[2] = {nullptr, nullptr}; bool sb_in_flight[2] = {false, false};
+    int sb_unpushed = -1; uint32_t sb_unpushed_n = 0;   // an arena whose push was refused (ring full): pushed again by the next flush
     std::atomic<uint64_t> running{0};           // tasks a drain has claimed (launched, not peeking) and not yet committed by a fetch
 
     // ---- pending ring (device)
@@ -398,6 +402,17 @@ void b9_ctx_destroy(b9_ctx* c) {
     if (c->ev_pa) cudaEventDestroy(c->ev_pa);
     if (c->ev_pb) cudaEventDestroy(c->ev_pb);
     delete c->pack_pool;
+    if (c->sb) {
+        for (int k = 0; k < 2; ++k) {
+            SubmitArena& A = c->sb->arena[k];
+            if (A.payload) cudaFreeHost(A.payload);
+            if (A.offsets) cudaFreeHost(A.offsets);
+            if (A.ids) cudaFreeHost(A.ids);
+            if (A.flags) cudaFreeHost(A.flags);
+            if (c->sb_free[k]) cudaEventDestroy(c->sb_free[k]);
+        }
+        delete c->sb;
+    }
     for (PackArena& A : c->pack) {
         if (A.payload) cudaFreeHost(A.payload);
         if (A.offsets) cudaFreeHost(A.offsets);
@@ -587,6 +602,86 @@ int b9_batch_push_v(b9_ctx* c, const uint8_t* task_ids, const uint8_t* const* pa
     const int rc = push_impl(c, A.ids, A.payload, A.offsets, n, meta, /*wait=*/false, A.free_ev);
     if (rc == B9_OK) A.in_flight = true;
     return rc;
+}
+
+// ---- single-task submissions from many threads, batched under the hood (submit_buffer.h) ------------------------------
+static int sb_ensure(b9_ctx* c) {
+    std::lock_guard<std::mutex> lk(c->sb_mu);
+    if (c->sb) return B9_OK;
+    CU(cudaSetDevice(c->device));
+    uint64_t bytes = 64ull << 20; uint32_t tasks = 256u << 10;
+    if (const char* e = getenv("B9_SUBMIT_BYTES")) bytes = (uint64_t)std::max<long long>(4096, atoll(e));
+    if (const char* e = getenv("B9_SUBMIT_TASKS")) tasks = (uint32_t)std::max<long long>(16, atoll(e));
+    tasks = std::min<uint32_t>(tasks, c->ring_tasks);
+    bytes = std::min<uint64_t>(bytes, c->ring_bytes / 2);
+    SubmitBuffer* sb = new (std::nothrow) SubmitBuffer();
+    if (!sb) return fail(B9_ENOMEM, "b9_submit: buffer");
+    for (int k = 0; k < 2; ++k) {
+        SubmitArena& A = sb->arena[k];
+        if (cudaHostAlloc(&A.payload, bytes, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc(&A.offsets, ((size_t)tasks + 1) * 8, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc(&A.ids, (size_t)tasks * 16, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc(&A.flags, tasks, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B9_ENOMEM, "b9_submit: %llu bytes of page-locked memory per arena", (unsigned long long)bytes);
+        }
+        A.cap_bytes = bytes; A.cap_tasks = tasks;
+        CU(cudaEventCreateWithFlags(&c->sb_free[k], cudaEventDisableTiming));
+    }
+    c->sb = sb;
+    return B9_OK;
+}
+
+static int sb_push(b9_ctx* c, int k, uint32_t n) {
+    SubmitArena& A = c->sb->arena[k];
+    b9_push_meta meta{}; meta.flags = A.any_flags.load(std::memory_order_relaxed) ? A.flags : nullptr;
+    const int rc = push_impl(c, A.ids, A.payload, A.offsets, n, meta.flags ? &meta : nullptr, /*wait=*/false, c->sb_free[k]);
+    if (rc == B9_OK) { c->sb_in_flight[k] = true; c->sb_unpushed = -1; }
+    else { c->sb_unpushed = k; c->sb_unpushed_n = n; }                       // nothing is lost: the next flush pushes it again
+    return rc;
+}
+
+int64_t b9_flush(b9_ctx* c) {
+    if (!c) return fail(B9_EINVAL, "b9_flush: ctx is NULL");
+    if (!c->sb) return 0;
+    SubmitBuffer* sb = c->sb;
+    std::lock_guard<std::mutex> lk(sb->flush_mu);
+    CU(cudaSetDevice(c->device));
+    int64_t pushed = 0;
+    if (c->sb_unpushed >= 0) {                                               // an earlier batch the ring refused
+        const uint32_t n = c->sb_unpushed_n;
+        const int rc = sb_push(c, c->sb_unpushed, n);
+        if (rc) return rc;
+        pushed += n;
+    }
+    const int cur = sb->active.load(std::memory_order_acquire), other = cur ^ 1;
+    if (sb->buffered() == 0) return pushed;
+    // the other arena takes the submissions from now on: its previous batch must be on the device
+    if (c->sb_in_flight[other]) { CU(cudaEventSynchronize(c->sb_free[other])); c->sb_in_flight[other] = false; }
+    SubmitBuffer::reset(sb->arena[other]);
+    uint32_t n = 0; uint64_t bytes = 0;
+    sb->seal(&n, &bytes);
+    if (n == 0) return pushed;
+    const int rc = sb_push(c, cur, n);
+    if (rc) return rc;
+    return pushed + n;
+}
+
+int b9_submit(b9_ctx* c, const uint8_t* task_id, const uint8_t* payload, uint32_t length, uint8_t flags) {
+    if (!c || !task_id || (!payload && length)) return fail(B9_EINVAL, "b9_submit: NULL argument");
+    if (length > c->max_task_bytes) return fail(B9_E2BIG, "b9_submit: task is %u bytes, max_task_bytes is %u", length, c->max_task_bytes);
+    if (!c->sb) { const int rc = sb_ensure(c); if (rc) return rc; }
+    for (int attempt = 0; attempt < 64; ++attempt) {
+        const int r = c->sb->submit(task_id, payload, length, flags);
+        if (r == SUBMIT_OK) return B9_OK;
+        if (r == SUBMIT_TOO_BIG) return fail(B9_E2BIG, "b9_submit: task is %u bytes, the submission arena holds %llu", length, (unsigned long long)c->sb->arena[0].cap_bytes);
+        const int64_t f = b9_flush(c);                                       // the arena is full: hand it to the device, go on in the other one
+        if (f < 0) return (int)f;
+    }
+    return fail(B9_ENOSPC, "b9_submit: the submission arenas stay full");
+}
+
+uint64_t b9_buffered(b9_ctx* c) {
+    if (!c || !c->sb) return 0;
+    return (uint64_t)c->sb->buffered() + (c->sb_unpushed >= 0 ? c->sb_unpushed_n : 0u);
 }
 
 uint64_t b9_depth(b9_ctx* c) {

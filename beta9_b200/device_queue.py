@@ -140,6 +140,16 @@ class DeviceQueue:
         assert ids.size == n * 16 and ptrs.shape[0] == n
         self._check(self._lib.b9_batch_push_v(self._ctx, ids.ctypes.data, ptrs.ctypes.data, lens.ctypes.data, n, None))
 
+    def submit(self, task_id: bytes, payload: bytes, flags: int = 0) -> None:
+        """b9_submit: one task (16 raw id bytes + payload) from any thread; batched under the hood, `flush()` pushes."""
+        self._check(self._lib.b9_submit(self._ctx, task_id, payload, len(payload), flags))
+
+    def flush(self) -> int:
+        return self._check(self._lib.b9_flush(self._ctx))
+
+    def buffered(self) -> int:
+        return int(self._lib.b9_buffered(self._ctx))
+
     def depth(self) -> int:                       # client.go:99-106 QueueLength / task_redis.go:112-119 TasksInFlight
         return int(self._lib.b9_depth(self._ctx))
 

@@ -198,6 +198,19 @@ int      b9_batch_push_async(b9_ctx *ctx, const uint8_t *task_ids, const uint8_t
 int      b9_batch_push_v(b9_ctx *ctx, const uint8_t *task_ids, const uint8_t *const *payloads,
                          const uint32_t *lengths, uint32_t n, const b9_push_meta *meta);
 
+/* ONE task per call, from any number of threads — the reference's own call pattern: `RedisTaskQueue.put` per gRPC / HTTP
+ * request goroutine (pkg/abstractions/taskqueue/taskqueue.go:176-226), the endpoint's `RequestBuffer.ForwardRequest`
+ * per request (pkg/abstractions/endpoint/buffer.go:139-168, a mutex-guarded RingBuffer drained one element at a time,
+ * buffer.go:170-195). b9_submit appends the payload straight into a page-locked arena of the context (a lock-free
+ * reservation + memcpy; the bytes are copied when it returns) and b9_flush hands everything submitted since the last flush
+ * to the device as ONE batch, in submission order; while that batch is on the wire, submissions go on into a second arena.
+ * A full arena flushes itself. b9_flush returns the number of tasks it pushed (a batch the ring refused — B9_ENOSPC — is
+ * kept and pushed again by the next flush). b9_buffered: tasks submitted and not yet pushed (admission: b9_depth +
+ * b9_buffered against max_pending_tasks). B9_SUBMIT_BYTES / B9_SUBMIT_TASKS size the arenas (64 MiB / 256 Ki). */
+int      b9_submit(b9_ctx *ctx, const uint8_t *task_id, const uint8_t *payload, uint32_t length, uint8_t flags);
+int64_t  b9_flush(b9_ctx *ctx);
+uint64_t b9_buffered(b9_ctx *ctx);
+
 /* Pending tasks = what `TaskRepository.TasksInFlight` / `taskQueueClient.QueueLength` report for
  * this queue (pkg/repository/task_redis.go:112-119, taskqueue/client.go:99-106); feeds
  * `taskQueueAutoscalerSampleFunc` (taskqueue/autoscaler.go:18-51) unchanged. */

@@ -149,3 +149,42 @@ def test_pusher_and_drainer_threads_run_concurrently(dq):
     for t in pins:
         for p in t:
             p.free()
+
+
+def test_submit_from_many_threads_then_flush(dq, monkeypatch):
+    """b9_submit: one task per call from 8 threads (the reference's call pattern: one goroutine per put / per endpoint
+    request), micro-batched into page-locked arenas; small arenas so that they fill, flush themselves and alternate."""
+    import os
+    os.environ["B9_SUBMIT_TASKS"] = "1000"; os.environ["B9_SUBMIT_BYTES"] = str(200_000)
+    b = synth.strings_batch(24_000, 64, adversarial_frac=0.1)
+    per = b.n // 8
+    errors = []
+
+    def producer(k):
+        try:
+            for i in range(k * per, (k + 1) * per):
+                dq.submit(b.task_ids[i].tobytes(), b.task(i))
+        except Exception as e:                 # noqa: BLE001
+            errors.append(e)
+    ths = [threading.Thread(target=producer, args=(k,)) for k in range(8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(120)
+    assert not errors, errors
+    dq.flush()
+    assert dq.buffered() == 0 and dq.depth() == b.n
+    r = dq.drain("identity")
+    o = coracle.run_batch(b.task_ids, b.payload, b.offsets, "identity", nthreads=4)
+    assert r.n == b.n
+    # arrival order is the order of the reservations: every producer's tasks in ITS order, every task exactly once, right bytes
+    index = {b.task_ids[i].tobytes(): i for i in range(b.n)}
+    got = [index[r.task_ids[j].tobytes()] for j in range(r.n)]
+    assert sorted(got) == list(range(b.n))
+    for k in range(8):
+        mine = [i for i in got if k * per <= i < (k + 1) * per]
+        assert mine == sorted(mine)
+    for j in range(0, r.n, 37):
+        i = got[j]
+        assert r.status[j] == o.status[i] and r.result(j) == o.result(i)
+    del os.environ["B9_SUBMIT_TASKS"], os.environ["B9_SUBMIT_BYTES"]

@@ -809,15 +809,16 @@ struct D3Warp {
     typename std::conditional<T == 32, D3CopyTab, D3NoTab>::type ct;
 };
 
-struct D3MetaRegs { uint64_t off, hdr; };
+struct D3MetaRegs { uint64_t off, hdr; uint4 id; };   // (the id rides along: it is only copied to the record, and loading it a tile ahead takes its latency off the record write)
 template <int T>
 __device__ __forceinline__ void d3_load_meta(const DrainArgs& a, unsigned long long tile, int lane, D3MetaRegs& r) {
     const uint32_t t0 = (uint32_t)tile * T;
-    r.off = 0; r.hdr = 0;
+    r.off = 0; r.hdr = 0; r.id = make_uint4(0u, 0u, 0u, 0u);
     if (lane < T && t0 + lane < a.n_tasks) {
         const uint32_t slot = (uint32_t)((a.first_task + t0 + lane) & a.slot_mask);
         r.hdr = __ldg(a.hdr + slot);
         r.off = __ldg(a.off + slot);
+        r.id = __ldg(a.ids + slot);
     }
 }
 
@@ -1368,7 +1369,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
     };
     unsigned long long t_cur = fetch(), t_raw = fetch();
     t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
-    D3MetaRegs mregs; mregs.off = 0; mregs.hdr = 0;
+    D3MetaRegs mregs; mregs.off = 0; mregs.hdr = 0; mregs.id = make_uint4(0u, 0u, 0u, 0u);
     if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
     uint32_t parity = 0;
 
@@ -1379,6 +1380,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         const uint32_t nt = min((uint32_t)T, a.n_tasks - t0);
         const bool valid = lane < (int)nt;
         const uint64_t m_off = mregs.off;
+        const uint4 m_id = mregs.id;                                       // (lane == task for G == 1)
         const uint32_t m_len = valid ? hdr_len(mregs.hdr) : 0u;
         const bool m_ready = valid && !(hdr_flags(mregs.hdr) & 1u);
         const uint64_t m_end = m_off + m_len;
@@ -1536,7 +1538,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
             if (sub == 0) {
                 const uint32_t slot = (uint32_t)((a.first_task + t0 + k) & a.slot_mask);
                 const uint32_t j = base_cnt + ex_cnt;
-                a.out_ids[j] = __ldg(a.ids + slot);
+                a.out_ids[j] = (G == 1) ? m_id : __ldg(a.ids + slot);
                 if (HANDLER == 0 && rec.mode == OM_DEFER) {                // the second kernel writes the rest of the record
                     SlowItem* it = a.slow + atomicAdd(&a.ctl->n_slow, 1u);
                     it->w1 = (unsigned long long)(my_len | (rec.value == 1 ? 0x80000000u : 0u) | (my_http ? 0x40000000u : 0u)) | ((unsigned long long)j << 32) | (rec.value == 2 ? (1ull << 56) : 0ull);

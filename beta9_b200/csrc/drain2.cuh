@@ -136,6 +136,21 @@ __device__ __forceinline__ uint32_t quick_clean_framed(const uint8_t* __restrict
     return (bits & 1u ? 0u : 1u) | (bits & 2u ? 0u : 2u);
 }
 
+// the frame part of quick_clean_framed alone (thread per task): is the payload {"args": ["...."], "kwargs": {}} ?
+__device__ __forceinline__ bool quick_frame_only(const uint8_t* __restrict__ p, uint32_t len) {
+    if (len < FRAME_PRE_LEN + FRAME_SUF_LEN) return false;
+    const uint8_t* q = p + len - FRAME_SUF_LEN;
+    bool bad = ld_u32_unaligned(p) != 0x7261227Bu;
+    bad |= ld_u32_unaligned(p + 4) != 0x3A227367u;
+    bad |= (ld_u32_unaligned(p + 8) & 0x00FFFFFFu) != 0x00225B20u;
+    bad |= ld_u32_unaligned(q) != 0x202C5D22u;
+    bad |= ld_u32_unaligned(q + 4) != 0x61776B22u;
+    bad |= ld_u32_unaligned(q + 8) != 0x22736772u;
+    bad |= ld_u32_unaligned(q + 12) != 0x7D7B203Au;
+    bad |= q[16] != '}';
+    return !bad;
+}
+
 // up to 15 bytes, destination alignment known to allow the 1/2/4/8-byte ladder used by the callers
 __device__ __forceinline__ void copy_small_up(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
     // dst + n is 16-byte aligned (head of a copy): ascending sizes keep every store naturally aligned
@@ -1421,6 +1436,25 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         const bool my_pickle = mine && (W.flg[k] & B9_TF_PICKLE_BIT) != 0;
         TaskRec rec; rec.ready = mine; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
         bool clobbered = false;
+#ifndef B9_SPEC_LAYOUT
+#define B9_SPEC_LAYOUT 0
+#endif
+        // identity, speculative layout (B9_SPEC_LAYOUT): a framed task's result, if the task turns out to be a copy, is as long
+        // as its token — known from the frame alone. So the tile's range is reserved BEFORE the body scan (the cursor add's
+        // round trip runs beside the scan instead of between scan and copy), every framed task gets its place, and a task
+        // that is deferred after all leaves a hole in the blob (its record is written by the tail with bytes of its own).
+        uint32_t spec_len = 0, spec_ex = 0, spec_tb = 0; unsigned long long spec_base = 0;
+        const bool spec = B9_SPEC_LAYOUT && HANDLER == 0 && T == 32 && G == 1 && staged;
+        if (spec) {
+            if (mine && !my_http) {
+                const uint8_t* p = sbuf + my_soff;
+                if (my_pickle) { const PickleStr ps = pickle_str_frame(p, my_len); if (ps.ok) spec_len = 11u + ps.hdr + ps.n + 2u; }
+                else if ((quick_frame_only(p, my_len)) && my_len - FRAME_PRE_LEN - FRAME_SUF_LEN > 0u) spec_len = my_len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2u;
+            }
+            spec_ex = warp_excl_scan(spec_len, lane);
+            spec_tb = __shfl_sync(0xffffffffu, spec_ex + spec_len, 31);
+            if (lane == 0 && spec_tb) spec_base = atomicAdd(&a.ctl->bytes, (unsigned long long)((spec_tb + 15u) & ~15u));
+        }
         if (HANDLER == 0) {
             // identity: settle the common case here (canonical frame, clean body -> the token is its own
             // json.dumps); everything else is put on the work list of the kernel's tail (d3_identity_tail), so that
@@ -1510,26 +1544,27 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         }
 
         // ---------------- compaction (ballot) + sizes (scan) + ONE cursor add per warp-tile -------------
-        const uint32_t my_bytes = (sub == 0) ? rec.out_len : 0u;
-        const uint32_t ex_bytes0 = warp_excl_scan(my_bytes, lane);
-        const uint32_t tb = __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
+        const uint32_t my_bytes = spec ? spec_len : ((sub == 0) ? rec.out_len : 0u);
+        const uint32_t ex_bytes0 = spec ? spec_ex : warp_excl_scan(my_bytes, lane);
+        const uint32_t tb = spec ? spec_tb : __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
         const uint32_t ex_bytes = __shfl_sync(0xffffffffu, ex_bytes0, k * G);      // every lane of a task sees the task's offset
         const uint32_t ex_cnt = __popc(ready_mask_t & ((1u << k) - 1u));
         // thread-per-task handlers reserve whole 16-byte units, so that every tile's range starts on a vector
         // boundary (the coalesced copy below); the <= 15 bytes of padding per tile are never referenced by a record
         constexpr bool COAL = (T == 32 && G == 1);
         const uint32_t tb_alloc = COAL ? ((tb + 15u) & ~15u) : tb;
-        unsigned long long base = 0;
-        if (lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb_alloc);
+        unsigned long long base = spec_base;
+        if (!spec && lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb_alloc);
         base = __shfl_sync(0xffffffffu, base, 0);
         const bool fits = base + tb_alloc <= a.out_cap;
         if (!fits && lane == 0) a.ctl->overflow = 1u;
         bool coal = false;
         if constexpr (COAL) {
-            const uint32_t c_len = (mine && rec.has && rec.mode == OM_COPY) ? rec.src_len : 0u;
-            const bool ok_me = rec.out_len == c_len && (c_len == 0u || c_len >= 16u);
+            // (speculative layout: every framed task's token is copied to its place, also those that were deferred after all)
+            const uint32_t c_len = spec ? spec_len : ((mine && rec.has && rec.mode == OM_COPY) ? rec.src_len : 0u);
+            const bool ok_me = (spec ? (rec.mode != OM_COPY || rec.out_len == c_len) : rec.out_len == c_len) && (c_len == 0u || c_len >= 16u);
             coal = staged && fits && tb != 0u && tb <= D3_COPY_MAX_BYTES && __all_sync(0xffffffffu, ok_me);
-            if (coal) d3_copy_tile(W.ct, sbuf, a.out_payload + base, c_len, ex_bytes0, my_soff + rec.src_off, tb, lane);
+            if (coal) d3_copy_tile(W.ct, sbuf, a.out_payload + base, c_len, ex_bytes0, my_soff + (spec ? 10u : rec.src_off), tb, lane);
         }
 
         // ---------------- phase B: G lanes per task ----------------------------------------------------

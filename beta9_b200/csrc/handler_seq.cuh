@@ -22,11 +22,34 @@ struct TaskRec {
     long long value;     // OM_U32_DEC / OM_I64_DEC
 };
 
+// decimal digits of v. (Round 1 divided by ten in 64 bits, one lane per task while 31 idle: 6-9 % of the crc32 and json_sum
+// kernels' instructions went into printing ~10 digits — profiles/r1_final_crc32_summary.txt. Now: compares against powers
+// of ten and 32-bit multiply-shift division by 10, in at most three 9-digit limbs.)
+__device__ __forceinline__ uint32_t dec_len_u32(uint32_t v) {
+    return 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) + (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+}
 __device__ __forceinline__ uint32_t dec_len_u64(unsigned long long v) {
-    uint32_t l = 1; while (v >= 10) { v /= 10; ++l; } return l;
+    if (v < 4294967296ull) return dec_len_u32((uint32_t)v);
+    const unsigned long long hi = v / 1000000000ull;                    // >= 4: v has more than 9 digits
+    if (hi < 4294967296ull) return 9u + dec_len_u32((uint32_t)hi);
+    return 18u + dec_len_u32((uint32_t)(hi / 1000000000ull));
+}
+// exactly n digits of x (x < 10^n), most significant first, zero-padded on the left
+__device__ __forceinline__ void write_dec_u32(uint8_t* o, uint32_t x, uint32_t n) {
+    for (uint32_t k = n; k-- > 0;) {
+        const uint32_t q = (uint32_t)(((unsigned long long)x * 0xCCCCCCCDull) >> 35);   // x / 10
+        o[k] = (uint8_t)('0' + (x - q * 10u));
+        x = q;
+    }
 }
 __device__ inline void write_dec(uint8_t* o, unsigned long long v, uint32_t len) {
-    for (uint32_t k = len; k-- > 0;) { o[k] = (uint8_t)('0' + v % 10); v /= 10; }
+    if (v < 4294967296ull) { write_dec_u32(o, (uint32_t)v, len); return; }
+    const unsigned long long hi = v / 1000000000ull;
+    write_dec_u32(o + (len - 9u), (uint32_t)(v - hi * 1000000000ull), 9u);
+    if (hi < 4294967296ull) { write_dec_u32(o, (uint32_t)hi, len - 9u); return; }
+    const unsigned long long top = hi / 1000000000ull;
+    write_dec_u32(o + (len - 18u), (uint32_t)(hi - top * 1000000000ull), 9u);
+    write_dec_u32(o, (uint32_t)top, len - 18u);
 }
 
 // String token p[s..e) (quotes included, validated): does the Python-escaped form equal a plain

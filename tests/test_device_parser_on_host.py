@@ -22,8 +22,9 @@ GXX = os.environ.get("CXX", "g++")
 
 @pytest.fixture(scope="module")
 def parser():
-    dep = os.path.join(os.path.dirname(HERE), "beta9_b200", "csrc", "json_device.cuh")
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(dep)):
+    csrc = os.path.join(os.path.dirname(HERE), "beta9_b200", "csrc")
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max([os.path.getmtime(SRC)] + [os.path.getmtime(d) for d in deps]):
         r = subprocess.run([GXX, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, SRC], capture_output=True, text=True)
         if r.returncode:
             pytest.skip("no host C++ compiler for the shim: " + r.stderr[-300:])

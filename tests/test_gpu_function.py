@@ -78,7 +78,7 @@ def test_identity_strings_at_size(dq):
 
 
 def test_foreign_pickles_are_never_answered_wrong(dq):
-    frames = [funcloop.frame_map_input(x) for x in [("a", "b"), 5, None, b"raw", ["l"], {"k": 1}, 1.5]]
+    frames = [funcloop.frame_map_input(x) for x in [("a", "b"), 5, None, b"raw", ["l", "m"], {"k": 1}, 1.5]]
     frames += [funcloop.frame_call("s", k=1), b"\x80\x05\x95", b"", b"\x80\x05\x95" + b"\x00" * 40,
                funcloop.frame_map_input("x" * 300)[:-1], funcloop.frame_map_input("ok")[:-1] + b"X",
                funcloop.frame_map_input("bad utf8").replace(b"bad", b"\xff\xfe\xfd")]

@@ -199,6 +199,8 @@ def ncu_traffic(args, n_tasks):
 def workload(args, rank, n=None):
     from beta9_b200 import synth
     n = args.tasks if n is None else n
+    if n <= 0:                                # (the skewed leg at N = 2 leaves rank 1 with nothing to ingest)
+        return synth.Batch(np.zeros((0, 16), np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.uint64), "empty")
     if args.handler == "identity":
         return synth.strings_batch(n, args.chars, adversarial_frac=args.adversarial, seed=synth.SEED + 1000 * rank)
     if args.handler == "crc32":          # configs[2]: zipf 32..4096-char strings
@@ -612,4 +614,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as e:      # a rank that fails must not leave its peers waiting in a collective until some outer timeout
+        if isinstance(e, SystemExit) and e.code in (0, None):
+            raise
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)

@@ -1551,7 +1551,9 @@ __global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, u
         const uint32_t ex_cnt = __popc(ready_mask_t & ((1u << k) - 1u));
         // thread-per-task handlers reserve whole 16-byte units, so that every tile's range starts on a vector
         // boundary (the coalesced copy below); the <= 15 bytes of padding per tile are never referenced by a record
-        constexpr bool COAL = (T == 32 && G == 1);
+        // (identity only: for vadd_f32, whose kernel is bound by the base64 arithmetic, the warp-wide copy's extra
+        // instructions cost more than its coalescing saves — 0.2038 -> 0.2215 ms per 1M tasks, profiles/r2_s1_*)
+        constexpr bool COAL = (T == 32 && G == 1 && HANDLER == 0);
         const uint32_t tb_alloc = COAL ? ((tb + 15u) & ~15u) : tb;
         unsigned long long base = spec_base;
         if (!spec && lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb_alloc);

@@ -1145,6 +1145,7 @@ __device__ __noinline__ bool esc_verify_canonical(uint8_t* __restrict__ sbuf, ui
         }
         if (!__all_sync(0xffffffffu, ok)) return false;
         carry = next_carry;
+        __syncwarp();                                                            // every window of the pass is read before a byte of it is rewritten
         while (patch_rounds) {
             const uint32_t round = (uint32_t)(__ffs(patch_rounds) - 1);
             patch_rounds &= patch_rounds - 1u;

@@ -5,7 +5,8 @@ mkdir -p gpurun_out
 TAG=${TAG:-ab}
 REPS=${REPS:-2}
 IFS=';' read -ra ARGSETS <<< "${ARGS:---adversarial 0.01;--adversarial 0}"
-if [ -n "$TESTS" ]; then timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/${TAG}_tests.log; fi
+# TESTS=1 runs the GPU suite first; TESTS_LIB=<name> runs it against ab_builds/<name>.so instead of the in-tree build
+if [ -n "$TESTS" ]; then ( [ -n "$TESTS_LIB" ] && export B9GPU_LIB=$PWD/ab_builds/$TESTS_LIB.so; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -12 | tee gpurun_out/${TAG}_tests.log ); fi
 for rep in $(seq 1 $REPS); do
   for v in ${VARIANTS:-cur}; do
     lib=${v%%@*}; envs=""; [ "$v" != "$lib" ] && envs=${v#*@}

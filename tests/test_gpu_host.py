@@ -104,47 +104,53 @@ def test_pusher_and_drainer_threads_run_concurrently(dq):
         assert r.n == b.n and np.array_equal(r.task_ids, b.task_ids) and np.array_equal(r.lengths, want_lens)
         return r
 
-    # serial reference time: push, drain, push, drain ...
+    def serial_run():
+        t0 = time.perf_counter()
+        for k in range(rounds):
+            push(k); drain_one()
+        return time.perf_counter() - t0
+
+    def piped_run():
+        errors = []
+        last = []
+        pushed = threading.Semaphore(0)
+        room = threading.Semaphore(2)              # at most two batches in the ring
+
+        def producer():
+            try:
+                for k in range(rounds):
+                    room.acquire()
+                    push(k)
+                    pushed.release()
+            except Exception as e:                 # noqa: BLE001
+                errors.append(e); pushed.release()
+
+        def consumer():
+            try:
+                for k in range(rounds):
+                    pushed.acquire()
+                    if errors:
+                        return
+                    last.append(drain_one())
+                    del last[:-1]
+                    room.release()
+            except Exception as e:                 # noqa: BLE001
+                errors.append(e); room.release()
+
+        t0 = time.perf_counter()
+        tp, tc = threading.Thread(target=producer), threading.Thread(target=consumer)
+        tp.start(); tc.start(); tp.join(120); tc.join(120)
+        piped = time.perf_counter() - t0
+        assert not errors, errors
+        assert not tp.is_alive() and not tc.is_alive()
+        assert dq.depth() == 0
+        assert np.array_equal(last[-1].fifo_payload(), o.payload)      # (outside the timed region: it costs more than the run)
+        return piped
+
     push(0); drain_one()
-    t0 = time.perf_counter()
-    for k in range(rounds):
-        push(k); drain_one()
-    serial = time.perf_counter() - t0
-
-    errors = []
-    last = []
-    pushed = threading.Semaphore(0)
-    room = threading.Semaphore(2)              # at most two batches in the ring
-
-    def producer():
-        try:
-            for k in range(rounds):
-                room.acquire()
-                push(k)
-                pushed.release()
-        except Exception as e:                 # noqa: BLE001
-            errors.append(e); pushed.release()
-
-    def consumer():
-        try:
-            for k in range(rounds):
-                pushed.acquire()
-                if errors:
-                    return
-                last.append(drain_one())
-                del last[:-1]
-                room.release()
-        except Exception as e:                 # noqa: BLE001
-            errors.append(e); room.release()
-
-    t0 = time.perf_counter()
-    tp, tc = threading.Thread(target=producer), threading.Thread(target=consumer)
-    tp.start(); tc.start(); tp.join(120); tc.join(120)
-    piped = time.perf_counter() - t0
-    assert not errors, errors
-    assert not tp.is_alive() and not tc.is_alive()
-    assert dq.depth() == 0
-    assert np.array_equal(last[-1].fifo_payload(), o.payload)          # (outside the timed region: it costs more than the run)
+    # a shared box's host threads are noisy: the best of three attempts each
+    serial = min(serial_run() for _ in range(3))
+    piped = min(piped_run() for _ in range(3))
     print(f"serial {serial * 1e3:.1f} ms, two threads {piped * 1e3:.1f} ms")
     assert piped < 0.95 * serial, (piped, serial)  # H2D of batch k+1 ran beside the kernel + D2H of batch k (typically ~0.7)
     for t in pins:

@@ -4,8 +4,8 @@ mkdir -p gpurun_out
 N=${N:-2}
 TAG=${TAG:-m$N}
 timeout 900 python -m pytest tests/test_gpu_multi.py -q -x 2>&1 | tail -15 | tee gpurun_out/${TAG}_tests.log
-B9_REBALANCE_TRACE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --config 3 --sustain-seconds 0.3 > gpurun_out/${TAG}_bench_config3.json 2> gpurun_out/${TAG}_bench_config3.err
+B9_REBALANCE_TRACE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --config 3 --sustain-seconds 0.3 > gpurun_out/${TAG}_bench_config3.json 2> gpurun_out/${TAG}_bench_config3.err
 grep "b9_rebalance rank 0" gpurun_out/${TAG}_bench.err | tail -12
 tail -4 gpurun_out/${TAG}_bench.err gpurun_out/${TAG}_bench_config3.err
 python - <<PY

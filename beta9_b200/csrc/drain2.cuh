@@ -1341,7 +1341,10 @@ __device__ __noinline__ void d3_identity_tail(const DrainArgs& a, uint8_t* __res
 }
 
 template <int HANDLER>
-__global__ void __launch_bounds__(D3_WARPS * 32, 9) drain3_kernel(DrainArgs a, uint32_t in_cap, uint32_t warp_stride) {
+#ifndef B9_CRC_MINB
+#define B9_CRC_MINB 9
+#endif
+__global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : 9)) drain3_kernel(DrainArgs a, uint32_t in_cap, uint32_t warp_stride) {
     constexpr int G = D3Cfg<HANDLER>::G, T = D3Cfg<HANDLER>::T;
     extern __shared__ __align__(128) uint8_t d3_smem[];
     __shared__ uint32_t s_crc_table[HANDLER == 1 ? 256 : 1];

@@ -1402,6 +1402,7 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : 9
         const uint4 m_id = mregs.id;                                       // (lane == task for G == 1)
         const uint32_t m_len = valid ? hdr_len(mregs.hdr) : 0u;
         const bool m_ready = valid && !(hdr_flags(mregs.hdr) & 1u);
+        const uint32_t m_flags = hdr_flags(mregs.hdr);
         const uint64_t m_end = m_off + m_len;
         uint64_t prev = __shfl_up_sync(0xffffffffu, m_end, 1);
         if (lane == 0) prev = m_off;
@@ -1428,6 +1429,24 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : 9
         t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
         if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
         t_raw = fetch();
+#ifndef B9_SPEC_TOP
+#define B9_SPEC_TOP 0
+#endif
+        // identity, B9_SPEC_TOP: the tile's result range is reserved from the slot words ALONE (a framed task's result is as
+        // long as its token: length - 26 for JSON, length - 24 for a cloudpickle record), so the cursor add's round trip runs
+        // beside the bulk copy's; tasks that are deferred after all leave holes in the blob.
+        uint32_t top_len = 0, top_ex = 0, top_tb = 0; unsigned long long top_base = 0;
+        if constexpr (B9_SPEC_TOP && HANDLER == 0 && T == 32 && G == 1) {
+            if (staged) {
+                if (m_ready && !(m_flags & B9_TF_HTTP_BODY_BIT)) {
+                    if (m_flags & B9_TF_PICKLE_BIT) top_len = m_len >= 39u ? m_len - 24u : 0u;
+                    else top_len = m_len > FRAME_PRE_LEN + FRAME_SUF_LEN ? m_len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2u : 0u;
+                }
+                top_ex = warp_excl_scan(top_len, lane);
+                top_tb = __shfl_sync(0xffffffffu, top_ex + top_len, 31);
+                if (lane == 0 && top_tb) top_base = atomicAdd(&a.ctl->bytes, (unsigned long long)((top_tb + 15u) & ~15u));
+            }
+        }
         __syncwarp();                                                      // W.* visible to all lanes
         if (staged) { mbar_wait(&W.mbar, parity); parity ^= 1u; }
 
@@ -1448,8 +1467,9 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : 9
         // round trip runs beside the scan instead of between scan and copy), every framed task gets its place, and a task
         // that is deferred after all leaves a hole in the blob (its record is written by the tail with bytes of its own).
         uint32_t spec_len = 0, spec_ex = 0, spec_tb = 0; unsigned long long spec_base = 0;
-        const bool spec = B9_SPEC_LAYOUT && HANDLER == 0 && T == 32 && G == 1 && staged;
-        if (spec) {
+        const bool spec = (B9_SPEC_LAYOUT || B9_SPEC_TOP) && HANDLER == 0 && T == 32 && G == 1 && staged;
+        if (B9_SPEC_TOP) { spec_len = top_len; spec_ex = top_ex; spec_tb = top_tb; spec_base = top_base; }
+        else if (spec) {
             if (mine && !my_http) {
                 const uint8_t* p = sbuf + my_soff;
                 if (my_pickle) { const PickleStr ps = pickle_str_frame(p, my_len); if (ps.ok) spec_len = 11u + ps.hdr + ps.n + 2u; }

@@ -203,8 +203,9 @@ template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes,
     constexpr int T = D3Cfg<H>::T;
     // stage buffer per warp sized for the window's average warp-tile: T tasks x 1.1 + 768 B, within [1 KiB, 48 KiB].
     // Tiles that do not fit are processed straight from global memory (same code, generic loads).
-    // (crc32's configuration has long-tailed sizes - zipf strings - and gets half a tile of headroom)
-    const uint64_t want = (H == B9_H_CRC32) ? avg_task_bytes * T * 3 / 2 + 1024 : avg_task_bytes * T * 11 / 10 + 768;
+    // (crc32's configuration has long-tailed sizes - zipf strings - and gets a third of a tile of headroom: more would
+    // cost resident warps, and its byte loop lives on those - 16 CTAs per SM fit with this, see B9_CRC_MINB)
+    const uint64_t want = (H == B9_H_CRC32) ? avg_task_bytes * T * 27 / 20 + 768 : avg_task_bytes * T * 11 / 10 + 768;
     uint32_t in_cap = (uint32_t)std::min<uint64_t>(48u << 10, std::max<uint64_t>(1u << 10, want));
     in_cap = (in_cap + 127u) & ~127u;
     if (cap_override) in_cap = cap_override;

@@ -803,7 +803,10 @@ template <int HANDLER> struct D3Cfg {
     static constexpr int G = (HANDLER == 0) ? B9_IDENTITY_G : 1;
     // tasks per warp-tile. crc32 (configs[2]: zipf 32..4096-byte strings, ~1 KB on average) works on a task
     // with the whole warp, so its tiles are small: 4 tasks keep the stage buffer at ~5 KB, which leaves L1 room for the shift tables.
-    static constexpr int T = (HANDLER == 1) ? 4 : (HANDLER == 3) ? 8 : 32 / G;
+#ifndef B9_JSON_T
+#define B9_JSON_T 8
+#endif
+    static constexpr int T = (HANDLER == 1) ? 4 : (HANDLER == 3) ? B9_JSON_T : 32 / G;
 };
 constexpr int D2_THREADS = 4;                // host: the smallest warp-tile (sizes the per-tile count arrays)
 
@@ -1341,10 +1344,20 @@ __device__ __noinline__ void d3_identity_tail(const DrainArgs& a, uint8_t* __res
 }
 
 template <int HANDLER>
+// resident CTAs per SM the register allocation aims for. crc32's byte loop waits on its table loads and more warps hide
+// them: 2.389 ms per 1M zipf strings with 96 registers / 10 CTAs, 2.249 with 80 / 12, 2.150 with 72 / 14, 2.005 with
+// 64 / 16 and a stage buffer that lets 16 fit (profiles/r2_c1_*, r2_c2_*, r2_c3_*). identity is limited to 9 CTAs by its
+// stage buffers, not by registers.
 #ifndef B9_CRC_MINB
-#define B9_CRC_MINB 9
+#define B9_CRC_MINB 16
 #endif
-__global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : 9)) drain3_kernel(DrainArgs a, uint32_t in_cap, uint32_t warp_stride) {
+#ifndef B9_VADD_MINB
+#define B9_VADD_MINB 9
+#endif
+#ifndef B9_JSON_MINB
+#define B9_JSON_MINB 9
+#endif
+__global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : HANDLER == 2 ? B9_VADD_MINB : HANDLER == 3 ? B9_JSON_MINB : 9)) drain3_kernel(DrainArgs a, uint32_t in_cap, uint32_t warp_stride) {
     constexpr int G = D3Cfg<HANDLER>::G, T = D3Cfg<HANDLER>::T;
     extern __shared__ __align__(128) uint8_t d3_smem[];
     __shared__ uint32_t s_crc_table[HANDLER == 1 ? 256 : 1];

@@ -59,6 +59,7 @@ struct Segment {             // one push = one contiguous byte range of the payl
     uint32_t n;
     uint64_t phys_start, bytes;
     cudaEvent_t ready;           // recorded on the ingest stream once the batch is fully on the device
+    uint32_t max_len = 0;        // longest task of the batch (0 = not known: tasks that arrived in a rebalance)
 };
 
 constexpr uint64_t RING_SLACK = 256;   // readable bytes past the ring end (vector loads may over-read)
@@ -199,7 +200,7 @@ template <int H> uint32_t drain3_warp_stride(uint32_t in_cap) {
     const size_t ctl = (sizeof(D3Warp<D3Cfg<H>::T>) + 127u) & ~(size_t)127u;
     return (uint32_t)(ctl + (((size_t)in_cap + 64u + 127u) & ~(size_t)127u));
 }
-template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes, uint32_t cap_override, int sm_count, cudaStream_t s, int* grid_out) {
+template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes, uint32_t max_task_len, uint32_t cap_override, int sm_count, cudaStream_t s, int* grid_out) {
     constexpr int T = D3Cfg<H>::T;
     // stage buffer per warp sized for the window's average warp-tile: T tasks x 1.1 + 768 B, within [1 KiB, 48 KiB].
     // Tiles that do not fit are processed straight from global memory (same code, generic loads).
@@ -207,6 +208,10 @@ template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes,
     // cost resident warps, and its byte loop lives on those - 16 CTAs per SM fit with this, see B9_CRC_MINB)
     const uint64_t want = (H == B9_H_CRC32) ? avg_task_bytes * T * 27 / 20 + 768 : avg_task_bytes * T * 11 / 10 + 768;
     uint32_t in_cap = (uint32_t)std::min<uint64_t>(48u << 10, std::max<uint64_t>(1u << 10, want));
+    // no tile of the window is longer than T of its longest tasks (+ the alignment of its first byte): with uniform task
+    // sizes (configs[3]: every task 372 bytes) the headroom above buys nothing and costs a resident CTA per SM
+    static const bool tight = !(getenv("B9_STAGE_TIGHT") && atoi(getenv("B9_STAGE_TIGHT")) == 0);      // (=0: the A/B switch)
+    if (tight && H != B9_H_CRC32 && max_task_len) in_cap = (uint32_t)std::min<uint64_t>(in_cap, std::max<uint64_t>(1u << 10, (uint64_t)max_task_len * T + 32u));
     in_cap = (in_cap + 127u) & ~127u;
     if (cap_override) in_cap = cap_override;
     const uint32_t stride = drain3_warp_stride<H>(in_cap);
@@ -475,15 +480,17 @@ static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload,
     // the O(n) host-side validation of the index below runs while the bytes are already on the wire
     if (bytes) CU(cudaMemcpyAsync(c->d_payload + start, payload + offsets[0], bytes, cudaMemcpyHostToDevice, s));
     uint64_t n_cancelled = 0;
+    uint32_t seg_max_len = 0;
     {
         const uint32_t maxb = c->max_task_bytes;
-        uint64_t bad = ~0ull, big = ~0ull, prev = offsets[0];
+        uint64_t bad = ~0ull, big = ~0ull, prev = offsets[0], longest = 0;
         for (uint32_t i = 0; i < n; ++i) {
             const uint64_t cur = offsets[i + 1];
             if (cur < prev) { if (bad == ~0ull) bad = i; }
-            else if (cur - prev > maxb) { if (big == ~0ull) big = i; }
+            else { if (cur - prev > maxb && big == ~0ull) big = i; longest = std::max(longest, cur - prev); }
             prev = cur;
         }
+        seg_max_len = (uint32_t)std::min<uint64_t>(longest, maxb);
         if (bad != ~0ull || big != ~0ull) {
             give_back();
             cudaStreamSynchronize(s);            // the stray DMA must not outlive the caller's buffer
@@ -515,7 +522,7 @@ static int push_impl(b9_ctx* c, const uint8_t* task_ids, const uint8_t* payload,
     CU(cudaEventRecord(ready, s));
     {
         std::lock_guard<std::mutex> lk(c->mu);
-        c->segs.push_back(Segment{tail, n, start, bytes, ready});
+        c->segs.push_back(Segment{tail, n, start, bytes, ready, seg_max_len});
         c->write_pos = start + b9_seg_span(bytes);
         c->tail_task += n;
         c->pending_bytes += bytes;
@@ -778,6 +785,9 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     }
     if (n == 0) { c->have_results = true; return 0; }
     uint64_t in_bytes = 0;                                                  // payload bytes of the window
+    uint32_t win_max_len = 0; bool max_known = true;                        // its longest task, when every batch in it told
+    for (const Piece& pc : pieces) { if (pc.sg.max_len) win_max_len = std::max(win_max_len, pc.sg.max_len); else max_known = false; }
+    if (!max_known) win_max_len = 0;
     for (const Piece& pc : pieces) {
         CU(cudaStreamWaitEvent(s, pc.sg.ready, 0));                         // this batch's H2D + ingest must have landed
         uint64_t o0 = 0, o1 = 0;
@@ -802,10 +812,10 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     CU(cudaEventRecord(c->ev_a, s));
     cudaError_t le;
     switch (handler) {
-    case B9_H_IDENTITY: le = launch_drain3<0>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
-    case B9_H_CRC32:    le = launch_drain3<1>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
-    case B9_H_VADD_F32: le = launch_drain3<2>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
-    default:            le = launch_drain3<3>(a, in_bytes / n, c->stage_bytes_override, c->sm_count, s, &grid); break;
+    case B9_H_IDENTITY: le = launch_drain3<0>(a, in_bytes / n, win_max_len, c->stage_bytes_override, c->sm_count, s, &grid); break;
+    case B9_H_CRC32:    le = launch_drain3<1>(a, in_bytes / n, win_max_len, c->stage_bytes_override, c->sm_count, s, &grid); break;
+    case B9_H_VADD_F32: le = launch_drain3<2>(a, in_bytes / n, win_max_len, c->stage_bytes_override, c->sm_count, s, &grid); break;
+    default:            le = launch_drain3<3>(a, in_bytes / n, win_max_len, c->stage_bytes_override, c->sm_count, s, &grid); break;
     }
     if (le != cudaSuccess) return fail(B9_EIO, "drain kernel launch failed: %s", cudaGetErrorString(le));
     CU(cudaEventRecord(c->ev_b, s));
@@ -1435,7 +1445,7 @@ int b9_rebalance(b9_ctx* c, b9_rebalance_info* info) {
         if (!c->event_pool.empty()) { ready = c->event_pool.back(); c->event_pool.pop_back(); }
         else CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
         CU(cudaEventRecord(ready, s));
-        c->segs.push_back(Segment{c->tail_task, (uint32_t)rk, start, pb, ready});
+        c->segs.push_back(Segment{c->tail_task, (uint32_t)rk, start, pb, ready, 0u});
         c->write_pos = start + b9_seg_span(pb);
         c->tail_task += rk; c->pending_bytes += pb;
     }

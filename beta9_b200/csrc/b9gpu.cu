@@ -802,7 +802,7 @@ int64_t b9_drain_launch(b9_ctx* c, int handler, uint32_t max_tasks, int peek) {
     a.out_status = c->d_out_status; a.out_has = c->d_out_has; a.out_len = c->d_out_len; a.ctl = c->d_ctl; a.tile_base = (const uint32_t*)c->d_tile_state; a.block_base = (const uint32_t*)c->d_tile_state + ((size_t)c->max_drain_tasks / D2_THREADS + 2); a.handler = handler;
     a.count_mode = count_mode;
     a.slow = c->d_slow; a.crc_shift_tabs = c->d_crc_shift;
-    a.static_rounds = 0; a.one = 1u;
+    a.static_rounds = 0;
     c->drain_epoch = (c->drain_epoch + 1u) & 0xFFFFFFu;
     if (c->drain_epoch == 0u) { c->drain_epoch = 1u; CU(cudaMemsetAsync(c->d_slow, 0, (size_t)c->max_drain_tasks * sizeof(SlowItem), s)); }   // the 24-bit tag wrapped: forget old tags
     a.epoch = c->drain_epoch;

@@ -57,25 +57,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // any byte of the four words outside printable ASCII, or equal to '"' or '\\'?
 // Exactness: a false positive can only occur in a group that also holds a byte >= 0x80, which is
 // "special" anyway (carries out of a byte need a byte >= 0x80 / 0xA0 below them).
-// `one` is the integer 1 as a run-time value (DrainArgs.one): x * one + K is an IMAD on the FMA pipe, where x + K would
-// be an IADD3 on the ALU pipe with all the logic ops — the scan is ALU-pipe bound (profiles/r2_s1_*), and the two pipes
-// issue independently (B9_SWAR_IMAD=0 keeps plain adds for A/B timing).
-#ifndef B9_SWAR_IMAD
-#define B9_SWAR_IMAD 0
-#endif
-__device__ __forceinline__ uint32_t add_k(uint32_t x, uint32_t k, uint32_t one) {
-#if B9_SWAR_IMAD
-    return x * one + k;
-#else
-    (void)one; return x + k;
-#endif
-}
-__device__ __forceinline__ bool swar_special16(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t one) {
+__device__ __forceinline__ bool swar_special16(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     const uint32_t K1 = 0x01010101u, K60 = 0x60606060u, K7F = 0x7F7F7F7Fu, Q = 0x22222222u, S = 0x5C5C5C5Cu, H = 0x80808080u;
-    uint32_t hi = (x | y | z | w) | (add_k(x, K1, one) | add_k(y, K1, one) | add_k(z, K1, one) | add_k(w, K1, one));          // >= 0x7F
-    uint32_t lo = add_k(x, K60, one) & add_k(y, K60, one) & add_k(z, K60, one) & add_k(w, K60, one);                          // bit7 clear: < 0x20
-    uint32_t eq = add_k(x ^ Q, K7F, one) & add_k(y ^ Q, K7F, one) & add_k(z ^ Q, K7F, one) & add_k(w ^ Q, K7F, one)           // bit7 clear: == '"'
-                & add_k(x ^ S, K7F, one) & add_k(y ^ S, K7F, one) & add_k(z ^ S, K7F, one) & add_k(w ^ S, K7F, one);          //            == '\\'
+    uint32_t hi = (x | y | z | w) | ((x + K1) | (y + K1) | (z + K1) | (w + K1));          // >= 0x7F
+    uint32_t lo = (x + K60) & (y + K60) & (z + K60) & (w + K60);                          // bit7 clear: < 0x20
+    uint32_t eq = ((x ^ Q) + K7F) & ((y ^ Q) + K7F) & ((z ^ Q) + K7F) & ((w ^ Q) + K7F)           // bit7 clear: == '"'
+                & ((x ^ S) + K7F) & ((y ^ S) + K7F) & ((z ^ S) + K7F) & ((w ^ S) + K7F);          //            == '\\'
     return ((hi | ~lo | ~eq) & H) != 0;
 }
 __device__ __forceinline__ bool byte_special(uint32_t c) { return c < 0x20u || c >= 0x7Fu || c == '"' || c == '\\'; }
@@ -92,7 +79,7 @@ __device__ __forceinline__ uint32_t byte_range_mask(uint32_t word, uint32_t lo, 
 // clean, identical on all G lanes. Must be called by all 32 lanes of the warp (`active` masks the
 // loads of lanes whose task does not exist).
 template <int G>
-__device__ __forceinline__ uint32_t quick_clean_framed(const uint8_t* __restrict__ p, uint32_t len, int sub, bool active, uint32_t one) {
+__device__ __forceinline__ uint32_t quick_clean_framed(const uint8_t* __restrict__ p, uint32_t len, int sub, bool active) {
     uint32_t bad_frame = 0, special = 0;
     if (active && len >= FRAME_PRE_LEN + FRAME_SUF_LEN) {
         // frame: 11 + 17 bytes compared as 32-bit words ("{\"ar" "gs\":" " [\""  /  "\"], " "\"kwa" "rgs\"" ": {}" "}")
@@ -127,28 +114,13 @@ __device__ __forceinline__ uint32_t quick_clean_framed(const uint8_t* __restrict
                 m = byte_range_mask(2, lo, hi); v.z = (v.z & m) | (A & ~m);
                 m = byte_range_mask(3, lo, hi); v.w = (v.w & m) | (A & ~m);
             }
-            special |= swar_special16(v.x, v.y, v.z, v.w, one) ? 1u : 0u;
+            special |= swar_special16(v.x, v.y, v.z, v.w) ? 1u : 0u;
         }
     } else bad_frame = 1;
     uint32_t bits = bad_frame | (special << 1);
     #pragma unroll
     for (int d = 1; d < G; d <<= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, d);
     return (bits & 1u ? 0u : 1u) | (bits & 2u ? 0u : 2u);
-}
-
-// the frame part of quick_clean_framed alone (thread per task): is the payload {"args": ["...."], "kwargs": {}} ?
-__device__ __forceinline__ bool quick_frame_only(const uint8_t* __restrict__ p, uint32_t len) {
-    if (len < FRAME_PRE_LEN + FRAME_SUF_LEN) return false;
-    const uint8_t* q = p + len - FRAME_SUF_LEN;
-    bool bad = ld_u32_unaligned(p) != 0x7261227Bu;
-    bad |= ld_u32_unaligned(p + 4) != 0x3A227367u;
-    bad |= (ld_u32_unaligned(p + 8) & 0x00FFFFFFu) != 0x00225B20u;
-    bad |= ld_u32_unaligned(q) != 0x202C5D22u;
-    bad |= ld_u32_unaligned(q + 4) != 0x61776B22u;
-    bad |= ld_u32_unaligned(q + 8) != 0x22736772u;
-    bad |= ld_u32_unaligned(q + 12) != 0x7D7B203Au;
-    bad |= q[16] != '}';
-    return !bad;
 }
 
 // up to 15 bytes, destination alignment known to allow the 1/2/4/8-byte ladder used by the callers
@@ -915,7 +887,7 @@ __device__ __noinline__ uint32_t d3_stage_scattered(const uint8_t* __restrict__ 
 
 // out-of-line generic-pointer versions for tiles that could not be staged (and other cold paths)
 template <int G>
-__device__ __noinline__ uint32_t quick_clean_framed_generic(const uint8_t* p, uint32_t len, int sub, bool active) { return quick_clean_framed<G>(p, len, sub, active, 1u); }
+__device__ __noinline__ uint32_t quick_clean_framed_generic(const uint8_t* p, uint32_t len, int sub, bool active) { return quick_clean_framed<G>(p, len, sub, active); }
 template <int G>
 __device__ __noinline__ void group_copy_staged(uint8_t* dst, const uint8_t* src, uint32_t n, int sub) { group_copy<G>(dst, src, n, sub); }   // (tiles the coalesced copy does not take)
 template <int G>
@@ -1415,7 +1387,6 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : H
         const uint4 m_id = mregs.id;                                       // (lane == task for G == 1)
         const uint32_t m_len = valid ? hdr_len(mregs.hdr) : 0u;
         const bool m_ready = valid && !(hdr_flags(mregs.hdr) & 1u);
-        const uint32_t m_flags = hdr_flags(mregs.hdr);
         const uint64_t m_end = m_off + m_len;
         uint64_t prev = __shfl_up_sync(0xffffffffu, m_end, 1);
         if (lane == 0) prev = m_off;
@@ -1442,24 +1413,6 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : H
         t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
         if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
         t_raw = fetch();
-#ifndef B9_SPEC_TOP
-#define B9_SPEC_TOP 0
-#endif
-        // identity, B9_SPEC_TOP: the tile's result range is reserved from the slot words ALONE (a framed task's result is as
-        // long as its token: length - 26 for JSON, length - 24 for a cloudpickle record), so the cursor add's round trip runs
-        // beside the bulk copy's; tasks that are deferred after all leave holes in the blob.
-        uint32_t top_len = 0, top_ex = 0, top_tb = 0; unsigned long long top_base = 0;
-        if constexpr (B9_SPEC_TOP && HANDLER == 0 && T == 32 && G == 1) {
-            if (staged) {
-                if (m_ready && !(m_flags & B9_TF_HTTP_BODY_BIT)) {
-                    if (m_flags & B9_TF_PICKLE_BIT) top_len = m_len >= 39u ? m_len - 24u : 0u;
-                    else top_len = m_len > FRAME_PRE_LEN + FRAME_SUF_LEN ? m_len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2u : 0u;
-                }
-                top_ex = warp_excl_scan(top_len, lane);
-                top_tb = __shfl_sync(0xffffffffu, top_ex + top_len, 31);
-                if (lane == 0 && top_tb) top_base = atomicAdd(&a.ctl->bytes, (unsigned long long)((top_tb + 15u) & ~15u));
-            }
-        }
         __syncwarp();                                                      // W.* visible to all lanes
         if (staged) { mbar_wait(&W.mbar, parity); parity ^= 1u; }
 
@@ -1472,32 +1425,12 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : H
         const bool my_pickle = mine && (W.flg[k] & B9_TF_PICKLE_BIT) != 0;
         TaskRec rec; rec.ready = mine; rec.status = 0; rec.has = 0; rec.mode = OM_NONE; rec.out_len = 0; rec.src_off = 0; rec.src_len = 0; rec.value = 0;
         bool clobbered = false;
-#ifndef B9_SPEC_LAYOUT
-#define B9_SPEC_LAYOUT 0
-#endif
-        // identity, speculative layout (B9_SPEC_LAYOUT): a framed task's result, if the task turns out to be a copy, is as long
-        // as its token — known from the frame alone. So the tile's range is reserved BEFORE the body scan (the cursor add's
-        // round trip runs beside the scan instead of between scan and copy), every framed task gets its place, and a task
-        // that is deferred after all leaves a hole in the blob (its record is written by the tail with bytes of its own).
-        uint32_t spec_len = 0, spec_ex = 0, spec_tb = 0; unsigned long long spec_base = 0;
-        const bool spec = (B9_SPEC_LAYOUT || B9_SPEC_TOP) && HANDLER == 0 && T == 32 && G == 1 && staged;
-        if (B9_SPEC_TOP) { spec_len = top_len; spec_ex = top_ex; spec_tb = top_tb; spec_base = top_base; }
-        else if (spec) {
-            if (mine && !my_http) {
-                const uint8_t* p = sbuf + my_soff;
-                if (my_pickle) { const PickleStr ps = pickle_str_frame(p, my_len); if (ps.ok) spec_len = 11u + ps.hdr + ps.n + 2u; }
-                else if ((quick_frame_only(p, my_len)) && my_len - FRAME_PRE_LEN - FRAME_SUF_LEN > 0u) spec_len = my_len - FRAME_PRE_LEN - FRAME_SUF_LEN + 2u;
-            }
-            spec_ex = warp_excl_scan(spec_len, lane);
-            spec_tb = __shfl_sync(0xffffffffu, spec_ex + spec_len, 31);
-            if (lane == 0 && spec_tb) spec_base = atomicAdd(&a.ctl->bytes, (unsigned long long)((spec_tb + 15u) & ~15u));
-        }
         if (HANDLER == 0) {
             // identity: settle the common case here (canonical frame, clean body -> the token is its own
             // json.dumps); everything else is put on the work list of the kernel's tail (d3_identity_tail), so that
             // this loop stays small enough for the instruction cache and no worker stalls on a 1 % case
             uint32_t q;
-            if (staged) q = quick_clean_framed<G>(sbuf + my_soff, my_len, sub, mine, a.one);
+            if (staged) q = quick_clean_framed<G>(sbuf + my_soff, my_len, sub, mine);
             else        q = quick_clean_framed_generic<G>(a.payload + my_goff, my_len, sub, mine);
             if (mine) {
                 if (q == 3u) {
@@ -1581,9 +1514,9 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : H
         }
 
         // ---------------- compaction (ballot) + sizes (scan) + ONE cursor add per warp-tile -------------
-        const uint32_t my_bytes = spec ? spec_len : ((sub == 0) ? rec.out_len : 0u);
-        const uint32_t ex_bytes0 = spec ? spec_ex : warp_excl_scan(my_bytes, lane);
-        const uint32_t tb = spec ? spec_tb : __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
+        const uint32_t my_bytes = (sub == 0) ? rec.out_len : 0u;
+        const uint32_t ex_bytes0 = warp_excl_scan(my_bytes, lane);
+        const uint32_t tb = __shfl_sync(0xffffffffu, ex_bytes0 + my_bytes, 31);
         const uint32_t ex_bytes = __shfl_sync(0xffffffffu, ex_bytes0, k * G);      // every lane of a task sees the task's offset
         const uint32_t ex_cnt = __popc(ready_mask_t & ((1u << k) - 1u));
         // thread-per-task handlers reserve whole 16-byte units, so that every tile's range starts on a vector
@@ -1592,18 +1525,17 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : H
         // instructions cost more than its coalescing saves — 0.2038 -> 0.2215 ms per 1M tasks, profiles/r2_s1_*)
         constexpr bool COAL = (T == 32 && G == 1 && HANDLER == 0);
         const uint32_t tb_alloc = COAL ? ((tb + 15u) & ~15u) : tb;
-        unsigned long long base = spec_base;
-        if (!spec && lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb_alloc);
+        unsigned long long base = 0;
+        if (lane == 0 && tb) base = atomicAdd(&a.ctl->bytes, (unsigned long long)tb_alloc);
         base = __shfl_sync(0xffffffffu, base, 0);
         const bool fits = base + tb_alloc <= a.out_cap;
         if (!fits && lane == 0) a.ctl->overflow = 1u;
         bool coal = false;
         if constexpr (COAL) {
-            // (speculative layout: every framed task's token is copied to its place, also those that were deferred after all)
-            const uint32_t c_len = spec ? spec_len : ((mine && rec.has && rec.mode == OM_COPY) ? rec.src_len : 0u);
-            const bool ok_me = (spec ? (rec.mode != OM_COPY || rec.out_len == c_len) : rec.out_len == c_len) && (c_len == 0u || c_len >= 16u);
+            const uint32_t c_len = (mine && rec.has && rec.mode == OM_COPY) ? rec.src_len : 0u;
+            const bool ok_me = rec.out_len == c_len && (c_len == 0u || c_len >= 16u);
             coal = staged && fits && tb != 0u && tb <= D3_COPY_MAX_BYTES && __all_sync(0xffffffffu, ok_me);
-            if (coal) d3_copy_tile(W.ct, sbuf, a.out_payload + base, c_len, ex_bytes0, my_soff + (spec ? 10u : rec.src_off), tb, lane);
+            if (coal) d3_copy_tile(W.ct, sbuf, a.out_payload + base, c_len, ex_bytes0, my_soff + rec.src_off, tb, lane);
         }
 
         // ---------------- phase B: G lanes per task ----------------------------------------------------

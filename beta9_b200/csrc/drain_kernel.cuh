@@ -65,7 +65,6 @@ struct DrainArgs {
     SlowItem* slow;                 // identity: [n_tasks] work list of deferred tasks
     uint32_t epoch;                 // identity: this launch's tag in SlowItem.w0 (1 .. 2^24 - 1)
     const uint32_t* crc_shift_tabs; // crc32: [levels][4][256] "advance the CRC register over 2^k zero bytes" tables
-    uint32_t one;                   // the integer 1 (a run-time value the compiler cannot fold: see swar_special16)
     uint32_t static_rounds;         // a worker's first static_rounds tiles are worker + q * workers, the rest come from the ticket counter
 };
 

@@ -34,7 +34,7 @@ def main():
         if "drain3_kernelILi0" in name:
             with open(os.path.join(ROOT, "profiles", f"{TAG}_sass_drain3_identity.txt"), "w") as f:
                 f.write(f"// cuobjdump -sass of {dem} ({len(ops)} instructions), libb9gpu.so built from this tree\n")
-                f.write("\n".join(re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", ln) for ln in lines) + "\n")
+                f.write("\n".join(re.sub(r"^\s+(/\*[0-9a-f]+\*/)\s+", r"\1 ", re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", ln)) for ln in lines) + "\n")
     path = os.path.join(ROOT, "profiles", f"{TAG}_sass_evidence.txt")
     open(path, "w").write("\n".join(out) + "\n")
     print(path)

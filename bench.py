@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--tasks", type=int, default=0, help="tasks per GPU per step (default: the config's total / its GPU count)")
     ap.add_argument("--chars", type=int, default=256)
     ap.add_argument("--handler", default="", help="override the config's handler")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=120, help="steps of the end-to-end legs (about a second of timed region at one GPU)")
     ap.add_argument("--sustain-seconds", type=float, default=1.0, help="bursts of K steps are repeated until their timed regions add up to this")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cancelled", type=float, default=0.0, help="fraction of the resident tasks pushed with B9_TF_CANCELLED")
@@ -407,9 +407,9 @@ def main():
 
     # ------------------------------------------------------------------ end to end through the C ABI, host buffers
     # Every step copies that step's inputs host->device from pinned memory and reads that step's result
-    # records back device->host. Steps are software-pipelined the way a gateway would run them: the push of
-    # batch k+1 is enqueued (b9_batch_push_async) before batch k is drained, so H2D(k+1) overlaps the kernel
-    # and D2H(k) on the full-duplex link. Two input buffer sets alternate; results land in one pinned set.
+    # records back device->host. Steps are pipelined the way a gateway would run them: one thread pushes
+    # (b9_batch_push_async), one drains, so H2D(k+1) overlaps the kernel and D2H(k) on the full-duplex link.
+    # Two input buffer sets alternate; results land in one pinned set.
     pins = []
     for _ in range(2):
         pi = dq.pinned(n * 16); pp = dq.pinned(in_bytes); po = dq.pinned((n + 1) * 8)
@@ -434,11 +434,29 @@ def main():
             raise SystemExit(f"drain returned {r}: " + L.last_error())
 
     def e2e_run(steps, push):
-        push(0)
+        # a producer thread pushes, this thread drains — one goroutine per side in the gateway; the library runs the two
+        # sides concurrently, so the host-side work of push k+1 (index validation, ring placement) is
+        # off the drain's critical path and both DMA directions stay busy. At most two batches are in the ring: buffer
+        # set k & 1 is reused only after batch k - 2 has been drained.
+        room, ready, err = threading.Semaphore(2), threading.Semaphore(0), []
+
+        def producer():
+            try:
+                for k in range(steps):
+                    room.acquire()
+                    push(k)
+                    ready.release()
+            except BaseException as e:          # noqa: BLE001
+                err.append(e); ready.release()
+        th = threading.Thread(target=producer, daemon=True)
+        th.start()
         for k in range(steps):
-            if k + 1 < steps:
-                push(k + 1)
+            ready.acquire()
+            if err:
+                raise SystemExit(f"push failed: {err[0]}")
             e2e_drain()
+            room.release()
+        th.join()
 
     def check_records():            # the records that came back are the real ones
         e_off = o_off.view(np.uint64, n); e_len = o_len.view(np.uint32, n)
@@ -482,27 +500,7 @@ def main():
             raise SystemExit("push_v failed: " + L.last_error())
 
     def packed_run(steps):
-        # a producer thread packs + pushes (b9_batch_push_v), this thread drains: the library runs the two sides
-        # concurrently (one goroutine per side in the gateway); at most two batches are in the ring
-        room, ready, err = threading.Semaphore(2), threading.Semaphore(0), []
-
-        def producer():
-            try:
-                for k in range(steps):
-                    room.acquire()
-                    packed_push(k)
-                    ready.release()
-            except BaseException as e:          # noqa: BLE001
-                err.append(e); ready.release()
-        th = threading.Thread(target=producer, daemon=True)
-        th.start()
-        for k in range(steps):
-            ready.acquire()
-            if err:
-                raise SystemExit(f"packed push failed: {err[0]}")
-            e2e_drain()
-            room.release()
-        th.join()
+        e2e_run(steps, packed_push)             # the producer thread packs + pushes (b9_batch_push_v), this thread drains
 
     packed_run(3)
     barrier()
@@ -618,7 +616,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "tasks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / args.e2e_steps,
                     "frac_of_link": e2e_value / link["tasks_per_sec"],
-                    "api": "b9_batch_push_async + b9_drain, pinned host buffers, push of step k+1 overlapped with drain of step k"},
+                    "api": "b9_batch_push_async on a producer thread + b9_drain on the main thread, pinned host buffers, at most two batches in the ring"},
             "e2e_packed": {"value": packed_value, "unit": "tasks/s", "ms_per_step": 1e3 * packed_elapsed / args.e2e_steps,
                            "pack_threads": pack_threads, "frac_of_link": packed_value / link["tasks_per_sec"],
                            "api": "b9_batch_push_v (payloads scattered over pageable memory, gathered into pinned arenas by the library) on a producer thread + b9_drain on the main thread"},

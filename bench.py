@@ -167,13 +167,32 @@ def bind_to_gpu_numa_node(local_rank: int) -> str:
 
 
 def kernel_source_hash() -> str:
-    """sha256 over the CUDA sources the drain kernels are built from: stamps profiles/ncu_traffic.json entries."""
+    """Identity of the drain kernels of THIS build: sha256 over the SASS of every `drain3_kernel<..>` in the library the
+    bench loads (cuobjdump; host-side edits of the library do not change it, any change of the kernels does). Falls back
+    to the CUDA sources' text when cuobjdump is missing. Stamps profiles/ncu_traffic.json entries."""
+    so = os.environ.get("B9GPU_LIB") or os.path.join(ROOT, "beta9_b200", "libb9gpu.so")
+    try:
+        txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=120, check=True).stdout
+        h = hashlib.sha256()
+        found = 0
+        for part in txt.split("Function : ")[1:]:
+            if "drain3_kernel" not in part.split("\n", 1)[0]:
+                continue
+            found += 1
+            for ln in part.split("\n"):
+                ln = ln.strip()
+                if ln.startswith("/*") and ";" in ln:                      # an instruction line (not its encoding word)
+                    h.update(ln.split("*/", 1)[1].split(";")[0].strip().encode()); h.update(b"\n")
+        if found:
+            return "sass:" + h.hexdigest()[:16]
+    except Exception:                                                       # noqa: BLE001
+        pass
     h = hashlib.sha256()
     d = os.path.join(ROOT, "beta9_b200", "csrc")
     for f in sorted(os.listdir(d)):
         if f.endswith((".cu", ".cuh", ".h")):
             h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
-    return h.hexdigest()[:16]
+    return "src:" + h.hexdigest()[:16]
 
 
 def workload_key(args, n_tasks) -> str:
@@ -191,9 +210,10 @@ def ncu_traffic(args, n_tasks):
     e = table.get(workload_key(args, n_tasks))
     if e is None:
         return None, "no capture of this workload"
-    if e.get("src_hash") != kernel_source_hash():
-        return None, f"stale capture (kernel sources {e.get('src_hash')} != {kernel_source_hash()})"
-    return e.get("dram_bytes"), f"ncu --set full, {e.get('captured', '?')}, kernel sources {e.get('src_hash')}"
+    mine = kernel_source_hash()
+    if e.get("src_hash") != mine:
+        return None, f"stale capture (kernels {e.get('src_hash')} != {mine})"
+    return e.get("dram_bytes"), f"ncu --set full, {e.get('captured', '?')}, kernels {e.get('src_hash')}"
 
 
 def workload(args, rank, n=None):

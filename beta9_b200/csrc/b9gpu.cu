@@ -598,7 +598,15 @@ int b9_batch_push_v(b9_ctx* c, const uint8_t* task_ids, const uint8_t* const* pa
     c->pack_pool->run([&](int t) {
         const uint32_t lo = lo_of(t), hi = lo_of(t + 1);
         uint64_t o = part[(size_t)t];
+        // the payloads sit anywhere in pageable memory: without a hint every task starts with a TLB miss and a chain of
+        // cache misses the copy then waits for; the first lines of the task PF ahead are requested while this one is copied
+        constexpr uint32_t PF = 8;
         for (uint32_t i = lo; i < hi; ++i) {
+            if (i + PF < hi) {
+                const uint8_t* q = payloads[i + PF];
+                const uint32_t ql = lengths[i + PF];
+                for (uint32_t b = 0; b < ql && b < 512u; b += 64u) __builtin_prefetch(q + b, 0, 0);
+            }
             A.offsets[i] = o;
             const uint32_t l = lengths[i];
             if (l) memcpy(A.payload + o, payloads[i], l);

@@ -239,8 +239,13 @@ template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes,
         if (e != cudaSuccess) return e;
     }
     if (allow_static && H == B9_H_IDENTITY) {
+        // B9_DYNAMIC_ROUNDS: how many of a worker's last rounds come from the ticket counter. One is enough when every
+        // tile costs the same; with 1 % of escape-dense strings a tile that holds one takes ~25 % longer (the warp checks its
+        // escapes), a worker's static share can hold a dozen of them, and one round of slack does not absorb that: 3 rounds
+        // measured 6.47 against 6.29 G tasks/s on the mix and 7.46 against 7.47 on clean input (profiles/r2_d1_*, r2_d2_*)
+        static const uint64_t dyn = getenv("B9_DYNAMIC_ROUNDS") ? (uint64_t)std::max(1, atoi(getenv("B9_DYNAMIC_ROUNDS"))) : 3u;
         const uint64_t rounds = a.n_tiles / ((uint64_t)grid * D3_WARPS);
-        a.static_rounds = rounds > 1 ? (uint32_t)(rounds - 1) : 0u;
+        a.static_rounds = rounds > dyn ? (uint32_t)(rounds - dyn) : 0u;
     }
     drain3_kernel<H><<<grid, D3_WARPS * 32, smem, s>>>(a, in_cap, stride);
     return cudaGetLastError();

@@ -15,4 +15,4 @@ timeout 300 python scripts/ncu_traffic.py > gpurun_out/${TAG}_traffic.log 2>&1
 # launch list of the same command (per-launch times are cold-cache and serialised: shares of the step, not absolutes)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --no-cpu-baseline --e2e-steps 1 --steps 2 --warmup 1 --sustain-seconds 0 > gpurun_out/ncu_b.log 2>&1
 fi
-tail -3 gpurun_out/${TAG}_*.err | tail -30
+tail -n 3 gpurun_out/${TAG}_*.err | tail -n 30

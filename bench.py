@@ -166,17 +166,18 @@ def bind_to_gpu_numa_node(local_rank: int) -> str:
     return "unchanged"
 
 
-def kernel_source_hash() -> str:
-    """Identity of the drain kernels of THIS build: sha256 over the SASS of every `drain3_kernel<..>` in the library the
-    bench loads (cuobjdump; host-side edits of the library do not change it, any change of the kernels does). Falls back
-    to the CUDA sources' text when cuobjdump is missing. Stamps profiles/ncu_traffic.json entries."""
+def kernel_source_hash(handler_index: int = 0) -> str:
+    """Identity of a drain kernel of THIS build: sha256 over the SASS of `drain3_kernel<handler_index>` in the library the
+    bench loads (cuobjdump; host-side edits of the library and changes to the other handlers' kernels do not change it,
+    any change of this kernel does). Falls back to the CUDA sources' text when cuobjdump is missing. Stamps
+    profiles/ncu_traffic.json entries."""
     so = os.environ.get("B9GPU_LIB") or os.path.join(ROOT, "beta9_b200", "libb9gpu.so")
     try:
         txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=120, check=True).stdout
         h = hashlib.sha256()
         found = 0
         for part in txt.split("Function : ")[1:]:
-            if "drain3_kernel" not in part.split("\n", 1)[0]:
+            if f"drain3_kernelILi{handler_index}E" not in part.split("\n", 1)[0]:
                 continue
             found += 1
             for ln in part.split("\n"):

@@ -202,27 +202,42 @@ template <int H> uint32_t drain3_warp_stride(uint32_t in_cap) {
 }
 template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes, uint32_t max_task_len, uint32_t cap_override, int sm_count, cudaStream_t s, int* grid_out) {
     constexpr int T = D3Cfg<H>::T;
-    // stage buffer per warp sized for the window's average warp-tile: T tasks x 1.1 + 768 B, within [1 KiB, 48 KiB].
+    static const bool tight = !(getenv("B9_STAGE_TIGHT") && atoi(getenv("B9_STAGE_TIGHT")) == 0);      // (=0: the A/B switch)
+    uint32_t in_cap = 0, stride = 0; size_t smem = 0; int per_sm = 0;
+    // stage buffer per warp sized for the window's average warp-tile: tt tasks x 1.1 + 768 B, within [1 KiB, 48 KiB].
     // Tiles that do not fit are processed straight from global memory (same code, generic loads).
     // (crc32's configuration has long-tailed sizes - zipf strings - and gets a third of a tile of headroom: more would
     // cost resident warps, and its byte loop lives on those - 16 CTAs per SM fit with this, see B9_CRC_MINB)
-    const uint64_t want = (H == B9_H_CRC32) ? avg_task_bytes * T * 27 / 20 + 768 : avg_task_bytes * T * 11 / 10 + 768;
-    uint32_t in_cap = (uint32_t)std::min<uint64_t>(48u << 10, std::max<uint64_t>(1u << 10, want));
-    // no tile of the window is longer than T of its longest tasks (+ the alignment of its first byte): with uniform task
-    // sizes (configs[3]: every task 372 bytes) the headroom above buys nothing and costs a resident CTA per SM
-    static const bool tight = !(getenv("B9_STAGE_TIGHT") && atoi(getenv("B9_STAGE_TIGHT")) == 0);      // (=0: the A/B switch)
-    if (tight && H != B9_H_CRC32 && max_task_len) in_cap = (uint32_t)std::min<uint64_t>(in_cap, std::max<uint64_t>(1u << 10, (uint64_t)max_task_len * T + 32u));
-    in_cap = (in_cap + 127u) & ~127u;
-    if (cap_override) in_cap = cap_override;
-    const uint32_t stride = drain3_warp_stride<H>(in_cap);
-    const size_t smem = (size_t)stride * D3_WARPS;
-    cudaError_t e = cudaFuncSetAttribute(drain3_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto size_for = [&](uint32_t tt) -> cudaError_t {
+        const uint64_t want = (H == B9_H_CRC32) ? avg_task_bytes * tt * 27 / 20 + 768 : avg_task_bytes * tt * 11 / 10 + 768;
+        in_cap = (uint32_t)std::min<uint64_t>(48u << 10, std::max<uint64_t>(1u << 10, want));
+        // no tile of the window is longer than tt of its longest tasks (+ the alignment of its first byte): with uniform task
+        // sizes (configs[3]: every task 372 bytes) the headroom above buys nothing and costs a resident CTA per SM
+        if (tight && H != B9_H_CRC32 && max_task_len) in_cap = (uint32_t)std::min<uint64_t>(in_cap, std::max<uint64_t>(1u << 10, (uint64_t)max_task_len * tt + 32u));
+        in_cap = (in_cap + 127u) & ~127u;
+        if (cap_override) in_cap = cap_override;
+        stride = drain3_warp_stride<H>(in_cap);
+        smem = (size_t)stride * D3_WARPS;
+        cudaError_t e = cudaFuncSetAttribute(drain3_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drain3_kernel<H>, D3_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        return cudaSuccess;
+    };
+    uint32_t tt = (uint32_t)T;
+    cudaError_t e = size_for(tt);
     if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drain3_kernel<H>, D3_WARPS * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    a.n_tiles = (a.n_tasks + T - 1) / T;
+    // json_sum works on a document with the whole warp: a window of about one 8-document tile per resident warp ends in a
+    // ragged last round (configs[4]: 25 k documents per GPU over ~2960 warps); tiles of 4 balance it - 0.087 against
+    // 0.100 ms - while larger windows prefer 8 (0.218 against 0.227 ms at 100 k, profiles/r2_j2_*)
+    if (H == B9_H_JSON_SUM && T >= 8 && (uint64_t)(a.n_tasks + T - 1) / T < 3ull * (uint64_t)per_sm * (uint64_t)sm_count * D3_WARPS) {
+        tt = 4u;
+        e = size_for(tt);
+        if (e != cudaSuccess) return e;
+    }
+    a.tile_tasks = tt;
+    a.n_tiles = (a.n_tasks + tt - 1) / tt;
     const uint32_t ctas_needed = (a.n_tiles + D3_WARPS - 1) / D3_WARPS;
     const int grid = (int)std::min<uint32_t>(ctas_needed, (uint32_t)(per_sm * sm_count));
     *grid_out = grid;
@@ -233,7 +248,7 @@ template <int H> cudaError_t launch_drain3(DrainArgs a, uint64_t avg_task_bytes,
     static const bool allow_static = !(getenv("B9_STATIC_ROUNDS") && atoi(getenv("B9_STATIC_ROUNDS")) == 0);
     if (a.count_mode) {                                                    // cancelled slots in the window: ready-count prefix per warp-tile
         const uint32_t blocks = (a.n_tasks + TC_SLOTS - 1u) / TC_SLOTS;
-        tile_count_kernel<<<blocks, TC_SLOTS, 0, s>>>(a.hdr, a.slot_mask, a.first_task, a.n_tasks, (uint32_t)T, (uint32_t*)a.tile_base, (uint32_t*)a.block_base);
+        tile_count_kernel<<<blocks, TC_SLOTS, 0, s>>>(a.hdr, a.slot_mask, a.first_task, a.n_tasks, tt, (uint32_t*)a.tile_base, (uint32_t*)a.block_base);
         tile_scan_kernel<<<1, 1024, 0, s>>>((uint32_t*)a.block_base, blocks);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

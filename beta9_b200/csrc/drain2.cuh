@@ -800,11 +800,12 @@ struct D3Warp {
 };
 
 struct D3MetaRegs { uint64_t off, hdr; uint4 id; };   // (the id rides along: it is only copied to the record, and loading it a tile ahead takes its latency off the record write)
+// tt = tasks per tile of this launch (<= T; the compile-time T for every handler but json_sum)
 template <int T>
-__device__ __forceinline__ void d3_load_meta(const DrainArgs& a, unsigned long long tile, int lane, D3MetaRegs& r) {
-    const uint32_t t0 = (uint32_t)tile * T;
+__device__ __forceinline__ void d3_load_meta(const DrainArgs& a, unsigned long long tile, int lane, D3MetaRegs& r, uint32_t tt) {
+    const uint32_t t0 = (uint32_t)tile * tt;
     r.off = 0; r.hdr = 0; r.id = make_uint4(0u, 0u, 0u, 0u);
-    if (lane < T && t0 + lane < a.n_tasks) {
+    if ((uint32_t)lane < tt && t0 + lane < a.n_tasks) {
         const uint32_t slot = (uint32_t)((a.first_task + t0 + lane) & a.slot_mask);
         r.hdr = __ldg(a.hdr + slot);
         r.off = __ldg(a.off + slot);
@@ -1331,6 +1332,7 @@ template <int HANDLER>
 #endif
 __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : HANDLER == 2 ? B9_VADD_MINB : HANDLER == 3 ? B9_JSON_MINB : 9)) drain3_kernel(DrainArgs a, uint32_t in_cap, uint32_t warp_stride) {
     constexpr int G = D3Cfg<HANDLER>::G, T = D3Cfg<HANDLER>::T;
+    const uint32_t TT = (HANDLER == 3) ? a.tile_tasks : (uint32_t)T;      // tasks per tile: json_sum's is chosen per launch (<= T)
     extern __shared__ __align__(128) uint8_t d3_smem[];
     __shared__ uint32_t s_crc_table[HANDLER == 1 ? 256 : 1];
     __shared__ __align__(128) uint8_t s_b64[HANDLER == 2 ? 320 : 4];
@@ -1374,14 +1376,14 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : H
     unsigned long long t_cur = fetch(), t_raw = fetch();
     t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
     D3MetaRegs mregs; mregs.off = 0; mregs.hdr = 0; mregs.id = make_uint4(0u, 0u, 0u, 0u);
-    if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
+    if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs, TT);
     uint32_t parity = 0;
 
     while (t_cur < a.n_tiles) {
         // ---------------- stage: decide how the tile's bytes get to shared memory, fire the copy --------
         const unsigned long long tile = t_cur;
-        const uint32_t t0 = (uint32_t)tile * T;
-        const uint32_t nt = min((uint32_t)T, a.n_tasks - t0);
+        const uint32_t t0 = (uint32_t)tile * TT;
+        const uint32_t nt = min(TT, a.n_tasks - t0);
         const bool valid = lane < (int)nt;
         const uint64_t m_off = mregs.off;
         const uint4 m_id = mregs.id;                                       // (lane == task for G == 1)
@@ -1407,11 +1409,11 @@ __global__ void __launch_bounds__(D3_WARPS * 32, (HANDLER == 1 ? B9_CRC_MINB : H
         // record indices: ready counts are known from the slot words alone
         const uint32_t ready_mask_t = __ballot_sync(0xffffffffu, m_ready);       // bit = task index
         const uint32_t rc = __popc(ready_mask_t);
-        const uint32_t base_cnt = a.count_mode ? tile_ready_before(a, tile, (uint32_t)T) : t0;   // (count_mode: from the pre-pass kernels)
+        const uint32_t base_cnt = a.count_mode ? tile_ready_before(a, tile, TT) : t0;   // (count_mode: from the pre-pass kernels)
         if (lane == 0 && tile == a.n_tiles - 1) a.ctl->total_cnt = base_cnt + rc;
         // advance the ticket pipeline (loads/atomics issued here are consumed one iteration later)
         t_cur = __shfl_sync(0xffffffffu, t_raw, 0);
-        if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs);
+        if (t_cur < a.n_tiles) d3_load_meta<T>(a, t_cur, lane, mregs, TT);
         t_raw = fetch();
         __syncwarp();                                                      // W.* visible to all lanes
         if (staged) { mbar_wait(&W.mbar, parity); parity ^= 1u; }
